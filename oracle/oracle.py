@@ -1,0 +1,193 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.c).
+
+TEST INFRASTRUCTURE ONLY — the checker, never the product.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import this module; nothing under
+diskrag_b200/ does.  Parity status: pinned against the real reference (oracle/_ref) and the golden
+vectors under tests/golden/ by tests/test_oracle_vs_reference.py and tests/test_golden.py.
+"""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+DIST_ADC_SEQ, DIST_L2_SQRT, DIST_L2_SQ, DIST_ADC_TREE = 0, 1, 2, 3
+FLAVOR_DOUBLE, FLAVOR_NUMPY, FLAVOR_WARP, FLAVOR_SEQ = 0, 1, 2, 3
+
+
+def build(force: bool = False) -> Path:
+    so = _HERE / "liboracle.so"
+    src = _HERE / "oracle.c"
+    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
+                               str(src), "-o", str(so), "-lm"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(str(build()))
+        _LIB.orc_l2sq_seq.restype = C.c_float
+        _LIB.orc_l2sq.restype = C.c_float
+        _LIB.orc_l2sq_numpy.restype = C.c_float
+        _LIB.orc_l2sq_warp.restype = C.c_float
+        _LIB.orc_np_sum_f32.restype = C.c_float
+        _LIB.orc_cosine_dist.restype = C.c_double
+        _LIB.orc_pq_sdc.restype = C.c_float
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def l2sq(x, y, flavor=FLAVOR_SEQ):
+    x, y = _f32(x), _f32(y)
+    return float(lib().orc_l2sq(_p(x), _p(y), C.c_int(x.size), C.c_int(flavor)))
+
+
+def cosine_dist(x, y):
+    x, y = _f32(x), _f32(y)
+    return float(lib().orc_cosine_dist(_p(x), _p(y), C.c_int(x.size)))
+
+
+def np_sum_f32(a):
+    a = _f32(a)
+    return float(lib().orc_np_sum_f32(_p(a), C.c_long(a.size)))
+
+
+def lut(codebook, q):
+    """codebook f32[M,256,ds], q f32[D] -> f32[M,256] (fast_pq.py:294-318)."""
+    codebook, q = _f32(codebook), _f32(q)
+    M, _, ds = codebook.shape
+    out = np.empty((M, 256), np.float32)
+    lib().orc_lut(_p(codebook), _p(q), C.c_int(M), C.c_int(ds), _p(out))
+    return out
+
+
+def adc(codes, lut_, tree=False):
+    codes = np.ascontiguousarray(codes, np.uint8)
+    lut_ = _f32(lut_)
+    n, M = codes.shape
+    out = np.empty(n, np.float32)
+    lib().orc_adc(_p(codes), _p(lut_), C.c_long(n), C.c_int(M), C.c_int(int(tree)), _p(out))
+    return out
+
+
+def pq_encode(codebook, X):
+    codebook, X = _f32(codebook), _f32(X)
+    M, _, ds = codebook.shape
+    N, D = X.shape
+    out = np.empty((N, M), np.uint8)
+    lib().orc_pq_encode(_p(codebook), _p(X), C.c_long(N), C.c_int(D), C.c_int(M), _p(out))
+    return out
+
+
+def pq_sdc(codebook, c1, c2):
+    codebook = _f32(codebook)
+    c1 = np.ascontiguousarray(c1, np.uint8); c2 = np.ascontiguousarray(c2, np.uint8)
+    M, _, ds = codebook.shape
+    return float(lib().orc_pq_sdc(_p(codebook), _p(c1), _p(c2), C.c_int(M), C.c_int(ds)))
+
+
+def _search(fn_name, adj, codes, lut_, vec, q, flavor, dist_mode, extra, start, L, trace):
+    adj = np.ascontiguousarray(adj, np.uint32)
+    N, R = adj.shape
+    M = 0
+    if codes is not None:
+        codes = np.ascontiguousarray(codes, np.uint8); M = codes.shape[1]
+        lut_ = _f32(lut_)
+    D = 0
+    if vec is not None:
+        vec = _f32(vec); D = vec.shape[1]
+    if q is not None:
+        q = _f32(q)
+    ids = np.full(L + 1, -1, np.int32); d = np.full(L + 1, np.inf, np.float32)
+    hops = C.c_int32(0); nvis = C.c_int32(0)
+    tr = np.full(trace, -1, np.int32) if trace else None
+    n = getattr(lib(), fn_name)(
+        _p(adj), C.c_int(R), C.c_long(N), _p(codes), C.c_int(M), _p(lut_),
+        _p(vec), C.c_int(D), _p(q), C.c_int(flavor), C.c_int(dist_mode), *extra,
+        C.c_int(int(start)), C.c_int(L), _p(ids), _p(d), C.byref(hops), C.byref(nvis),
+        _p(tr), C.c_int(trace))
+    res = {"ids": ids[:n].copy(), "dists": d[:n].copy(), "hops": hops.value, "visited": nvis.value}
+    if trace:
+        res["trace"] = tr[:min(trace, nvis.value)].copy()
+    return res
+
+
+def search_heap(adj, start, L, *, codes=None, lut_=None, vec=None, q=None, dist_mode=DIST_ADC_SEQ,
+                flavor=FLAVOR_DOUBLE, truncate_frontier=False, trace=0):
+    """Literal two-heap form of variants A/B/D (cython_utils.pyx:72-122, vamana_graph.py:607-640,719-760)."""
+    return _search("orc_search_heap", adj, codes, lut_, vec, q, flavor, dist_mode,
+                   (C.c_int(int(truncate_frontier)),), start, L, trace)
+
+
+def search_list(adj, start, L, *, codes=None, lut_=None, vec=None, q=None, dist_mode=DIST_ADC_SEQ,
+                flavor=FLAVOR_WARP, W=1, strict_ties=True, trace=0):
+    """Sorted-L-list form with W expansions per step: the exact statement of the GPU kernel."""
+    return _search("orc_search_list", adj, codes, lut_, vec, q, flavor, dist_mode,
+                   (C.c_int(W), C.c_int(int(strict_ties))), start, L, trace)
+
+
+def rerank(vec, q, ids, k, flavor=FLAVOR_WARP):
+    vec, q = _f32(vec), _f32(q)
+    ids = np.ascontiguousarray(ids, np.int32)
+    oi = np.full(k, -1, np.int32); od = np.full(k, np.inf, np.float32)
+    m = lib().orc_rerank(_p(vec), C.c_int(vec.shape[1]), _p(q), C.c_int(flavor), _p(ids), C.c_int(ids.size),
+                         C.c_int(k), _p(oi), _p(od))
+    return oi[:m], od[:m]
+
+
+def search_batch(adj, vec, Q, start, L, k, *, codes=None, codebook=None, dist_mode=DIST_ADC_SEQ,
+                 flavor=FLAVOR_WARP, W=1, rerank_=True, nthreads=0):
+    adj = np.ascontiguousarray(adj, np.uint32); vec = _f32(vec); Q = _f32(Q)
+    N, R = adj.shape; B, D = Q.shape
+    M = 0
+    if codes is not None:
+        codes = np.ascontiguousarray(codes, np.uint8); M = codes.shape[1]; codebook = _f32(codebook)
+    ids = np.empty((B, k), np.int32); d = np.empty((B, k), np.float32)
+    hops = np.empty(B, np.int32); nvis = np.empty(B, np.int32)
+    lib().orc_search_batch(_p(adj), C.c_int(R), C.c_long(N), _p(codes), C.c_int(M), _p(codebook),
+                           _p(vec), C.c_int(D), _p(Q), C.c_long(B), C.c_int(dist_mode), C.c_int(flavor),
+                           C.c_int(W), C.c_int(int(start)), C.c_int(L), C.c_int(k), C.c_int(int(rerank_)),
+                           _p(ids), _p(d), _p(hops), _p(nvis), C.c_int(nthreads))
+    return ids, d, hops, nvis
+
+
+def vamana_build(P, R, L, alpha, medoid, sigma0, sigma1):
+    """Sequential 2-pass Vamana (cython_utils.pyx:269-492) -> list of rows (python lists)."""
+    P = _f32(P); N, D = P.shape
+    s0 = np.ascontiguousarray(sigma0, np.int32); s1 = np.ascontiguousarray(sigma1, np.int32)
+    cap = R + 1
+    adj = np.empty((N, cap), np.int32); deg = np.empty(N, np.int32)
+    ov = lib().orc_vamana_build(_p(P), C.c_long(N), C.c_int(D), C.c_int(R), C.c_int(L), C.c_float(alpha),
+                                C.c_int(int(medoid)), _p(s0), _p(s1), _p(adj), C.c_int(cap), _p(deg))
+    assert ov == 0
+    return [adj[i, :deg[i]].tolist() for i in range(N)]
+
+
+def medoid(P, samples, skip_self=False):
+    P = _f32(P); s = np.ascontiguousarray(samples, np.int32)
+    return int(lib().orc_medoid(_p(P), C.c_long(P.shape[0]), C.c_int(P.shape[1]), _p(s), C.c_int(s.size),
+                                C.c_int(int(skip_self))))
+
+
+def ground_truth(X, Q, k):
+    X, Q = _f32(X), _f32(Q)
+    out = np.empty((Q.shape[0], k), np.int32)
+    lib().orc_ground_truth(_p(X), C.c_long(X.shape[0]), C.c_int(X.shape[1]), _p(Q), C.c_long(Q.shape[0]),
+                           C.c_int(k), _p(out))
+    return out
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
