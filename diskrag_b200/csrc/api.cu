@@ -1,0 +1,480 @@
+// api.cu — the extern "C" surface of libdiskrag_b200.so (see include/diskrag_b200.h).
+#include "common.cuh"
+
+#include <stdarg.h>
+
+#include <vector>
+
+static thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+void dr_set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+int dr_scratch(void **ptr, size_t *cur, size_t need) {
+    if (*cur >= need) return 0;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cur = 0;
+    DR_CUDA(cudaMalloc(ptr, need));
+    *cur = need;
+    return 0;
+}
+
+// launchers from the other translation units
+int launch_adc(const uint8_t *, const float *, int64_t, int, float *, cudaStream_t);
+int launch_pq_encode(const float *, const float *, int64_t, int, int, uint8_t *, cudaStream_t);
+int launch_pq_train(const float *, int64_t, int, int, int, uint64_t, float *, double *, cudaStream_t);
+int launch_pq_decode(const float *, const uint8_t *, int64_t, int, int, float *, cudaStream_t);
+int launch_rowdist(const float *, const float *, int64_t, int64_t, int, int, float *, cudaStream_t);
+int launch_sdc(const float *, const uint8_t *, const uint8_t *, int64_t, int, int, float *, cudaStream_t);
+int launch_topk_merge(const int32_t *, const float *, int, int64_t, int, int32_t *, float *, cudaStream_t);
+int launch_medoid(const float *, int64_t, int, const int32_t *, int, int, double *, cudaStream_t);
+int launch_vamana_build(const float *, int64_t, int, int, int, float, int64_t, uint64_t, uint32_t *, int32_t *, int, cudaStream_t);
+int launch_deinterleave(const void *, int64_t, int, int, float *, uint32_t *, cudaStream_t);
+int launch_interleave(const float *, const uint32_t *, int64_t, int, int, void *, cudaStream_t);
+
+// small RAII device buffer for the host-pointer entry points
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { DR_CUDA(cudaMalloc(&p, n ? n : 1)); return 0; }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+static int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        dr_set_error("no CUDA device available (%s); libdiskrag_b200 has no CPU fallback", cudaGetErrorString(e));
+        return 3;
+    }
+    DR_CHECK(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+    DR_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+// records <-> split arrays
+__global__ void deinterleave_kernel(const uint32_t *__restrict__ rec, long long N, int D, int R, float *__restrict__ vec,
+                                    uint32_t *__restrict__ adj) {
+    const int W = D + R;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * W) return;
+    long long i = t / W;
+    int j = (int)(t - i * W);
+    uint32_t v = rec[t];
+    if (j < D) vec[(size_t)i * D + j] = __uint_as_float(v);
+    else adj[(size_t)i * R + (j - D)] = v;
+}
+__global__ void interleave_kernel(const float *__restrict__ vec, const uint32_t *__restrict__ adj, long long N, int D, int R,
+                                  uint32_t *__restrict__ rec) {
+    const int W = D + R;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * W) return;
+    long long i = t / W;
+    int j = (int)(t - i * W);
+    rec[t] = j < D ? __float_as_uint(vec[(size_t)i * D + j]) : adj[(size_t)i * R + (j - D)];
+}
+int launch_deinterleave(const void *d_rec, int64_t N, int D, int R, float *d_vec, uint32_t *d_adj, cudaStream_t s) {
+    long long tot = (long long)N * (D + R);
+    if (tot == 0) return 0;
+    deinterleave_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>((const uint32_t *)d_rec, N, D, R, d_vec, d_adj);
+    DR_LAUNCHED();
+    return 0;
+}
+int launch_interleave(const float *d_vec, const uint32_t *d_adj, int64_t N, int D, int R, void *d_rec, cudaStream_t s) {
+    long long tot = (long long)N * (D + R);
+    if (tot == 0) return 0;
+    interleave_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_vec, d_adj, N, D, R, (uint32_t *)d_rec);
+    DR_LAUNCHED();
+    return 0;
+}
+
+extern "C" {
+
+int dr_abi_version(void) { return DR_ABI_VERSION; }
+const char *dr_last_error(void) { return g_err.c_str(); }
+int64_t dr_launch_count(void) { return g_launches.load(); }
+
+int dr_device_count(int *out_count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { n = 0; cudaGetLastError(); }
+    if (out_count) *out_count = n;
+    return 0;
+}
+
+int dr_device_info(int device, int *out_sms, int *out_smem_optin, int64_t *out_total_mem) {
+    if (use_device(device)) return 3;
+    cudaDeviceProp prop;
+    DR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (out_sms) *out_sms = prop.multiProcessorCount;
+    if (out_smem_optin) *out_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (out_total_mem) *out_total_mem = (int64_t)prop.totalGlobalMem;
+    return 0;
+}
+
+static int index_common(dr_index *h, int64_t N, int D, int R, int M, int64_t medoid, int device) {
+    DR_CHECK(N > 0 && D > 0 && R > 0, "dr_index: bad shape N=%lld D=%d R=%d", (long long)N, D, R);
+    DR_CHECK(N < (1ll << 31), "dr_index: N must be < 2^31");
+    DR_CHECK(M == 0 || D % M == 0, "dr_index: D=%d not divisible by M=%d", D, M);
+    DR_CHECK(medoid >= 0 && medoid < N, "dr_index: medoid %lld out of range", (long long)medoid);
+    h->device = device; h->N = N; h->D = D; h->R = R; h->M = M; h->medoid = medoid;
+    cudaDeviceProp prop;
+    DR_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sms = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    DR_CUDA(cudaEventCreate(&h->ev0));
+    DR_CUDA(cudaEventCreate(&h->ev1));
+    return 0;
+}
+
+static int upload_pq(dr_index *h, const uint8_t *codes, const float *codebook) {
+    if (h->M > 0 && codes) {
+        DR_CUDA(cudaMalloc(&h->d_codes, (size_t)h->N * h->M));
+        DR_CUDA(cudaMemcpy(h->d_codes, codes, (size_t)h->N * h->M, cudaMemcpyHostToDevice));
+    }
+    if (h->M > 0 && codebook) {
+        DR_CUDA(cudaMalloc(&h->d_codebook, (size_t)256 * h->D * 4));
+        DR_CUDA(cudaMemcpy(h->d_codebook, codebook, (size_t)256 * h->D * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int dr_index_create_from_records(const void *records, int64_t N, int32_t D, int32_t R, const uint8_t *codes,
+                                 const float *codebook, int32_t M, int64_t medoid, int device, dr_index **out) {
+    if (use_device(device)) return 3;
+    DR_CHECK(records && out, "dr_index_create_from_records: null argument");
+    dr_index *h = new dr_index();
+    int rc = index_common(h, N, D, R, M, medoid, device);
+    if (!rc) {
+        rc = [&]() -> int {
+            const size_t bytes = (size_t)N * 4 * (D + R);
+            DevBuf rec;
+            if (rec.alloc(bytes)) return 1;
+            DR_CUDA(cudaMemcpy(rec.p, records, bytes, cudaMemcpyHostToDevice));
+            DR_CUDA(cudaMalloc(&h->d_vec, (size_t)N * D * 4));
+            DR_CUDA(cudaMalloc(&h->d_adj, (size_t)N * R * 4));
+            if (launch_deinterleave(rec.p, N, D, R, h->d_vec, h->d_adj, 0)) return 1;
+            DR_CUDA(cudaDeviceSynchronize());
+            return upload_pq(h, codes, codebook);
+        }();
+    }
+    if (rc) { dr_index_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int dr_index_create(const float *vec, const uint32_t *adj, const uint8_t *codes, const float *codebook, int64_t N, int32_t D,
+                    int32_t R, int32_t M, int64_t medoid, int device, dr_index **out) {
+    if (use_device(device)) return 3;
+    DR_CHECK(vec && adj && out, "dr_index_create: null argument");
+    dr_index *h = new dr_index();
+    int rc = index_common(h, N, D, R, M, medoid, device);
+    if (!rc) {
+        rc = [&]() -> int {
+            DR_CUDA(cudaMalloc(&h->d_vec, (size_t)N * D * 4));
+            DR_CUDA(cudaMalloc(&h->d_adj, (size_t)N * R * 4));
+            DR_CUDA(cudaMemcpy(h->d_vec, vec, (size_t)N * D * 4, cudaMemcpyHostToDevice));
+            DR_CUDA(cudaMemcpy(h->d_adj, adj, (size_t)N * R * 4, cudaMemcpyHostToDevice));
+            return upload_pq(h, codes, codebook);
+        }();
+    }
+    if (rc) { dr_index_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int dr_index_create_dev(const float *d_vec, const uint32_t *d_adj, const uint8_t *d_codes, const float *d_codebook, int64_t N,
+                        int32_t D, int32_t R, int32_t M, int64_t medoid, int device, dr_index **out) {
+    if (use_device(device)) return 3;
+    DR_CHECK(d_vec && d_adj && out, "dr_index_create_dev: null argument");
+    dr_index *h = new dr_index();
+    int rc = index_common(h, N, D, R, M, medoid, device);
+    if (rc) { dr_index_destroy(h); return rc; }
+    h->owns = false;
+    h->d_vec = const_cast<float *>(d_vec);
+    h->d_adj = const_cast<uint32_t *>(d_adj);
+    h->d_codes = const_cast<uint8_t *>(d_codes);
+    h->d_codebook = const_cast<float *>(d_codebook);
+    *out = h;
+    return 0;
+}
+
+int dr_index_destroy(dr_index *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->owns) {
+        if (h->d_vec) cudaFree(h->d_vec);
+        if (h->d_adj) cudaFree(h->d_adj);
+        if (h->d_codes) cudaFree(h->d_codes);
+        if (h->d_codebook) cudaFree(h->d_codebook);
+    }
+    if (h->d_lut) cudaFree(h->d_lut);
+    if (h->d_counter) cudaFree(h->d_counter);
+    if (h->d_ovf) cudaFree(h->d_ovf);
+    if (h->d_io) cudaFree(h->d_io);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return 0;
+}
+
+int dr_index_info(const dr_index *h, int64_t *N, int32_t *D, int32_t *R, int32_t *M, int64_t *medoid, int *device) {
+    DR_CHECK(h, "dr_index_info: null handle");
+    if (N) *N = h->N;
+    if (D) *D = h->D;
+    if (R) *R = h->R;
+    if (M) *M = h->M;
+    if (medoid) *medoid = h->medoid;
+    if (device) *device = h->device;
+    return 0;
+}
+
+int dr_index_export_records(const dr_index *h, void *records) {
+    DR_CHECK(h && records, "dr_index_export_records: null argument");
+    DR_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->N * 4 * (h->D + h->R);
+    DevBuf rec;
+    if (rec.alloc(bytes)) return 1;
+    if (launch_interleave(h->d_vec, h->d_adj, h->N, h->D, h->R, rec.p, 0)) return 1;
+    DR_CUDA(cudaMemcpy(records, rec.p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_search_kernel_timing(dr_index *h, int enable, double *out_ms, int64_t *out_launches) {
+    DR_CHECK(h, "dr_search_kernel_timing: null handle");
+    if (out_ms) *out_ms = h->timed_ms;
+    if (out_launches) *out_launches = h->timed_launches;
+    h->timing = enable != 0;
+    h->timed_ms = 0.0;
+    h->timed_launches = 0;
+    return 0;
+}
+
+int dr_search_batch_dev(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, const float *d_lut,
+                        int32_t *d_out_ids, float *d_out_dist, int32_t *d_out_hops, int32_t *d_out_visited,
+                        int32_t *d_out_list_ids, float *d_out_list_dist, int32_t *d_out_list_len, int32_t *d_trace,
+                        int32_t trace_cap, int32_t *d_out_status, void *stream) {
+    DR_CHECK(h && p && d_out_ids && (d_Q || B == 0), "dr_search_batch_dev: null argument");
+    DR_CUDA(cudaSetDevice(h->device));
+    return launch_search(h, d_Q, B, p, d_lut, d_out_ids, d_out_dist, d_out_hops, d_out_visited, d_out_list_ids,
+                         d_out_list_dist, d_out_list_len, d_trace, trace_cap, d_out_status, (cudaStream_t)stream);
+}
+
+int dr_search_batch(dr_index *h, const float *Q, int64_t B, const dr_search_params *p, const float *lut, int32_t *out_ids,
+                    float *out_dist, int32_t *out_hops, int32_t *out_visited, int32_t *out_list_ids, float *out_list_dist,
+                    int32_t *out_list_len, int32_t *trace, int32_t trace_cap, int32_t *out_status) {
+    DR_CHECK(h && p && out_ids && (Q || B == 0), "dr_search_batch: null argument");
+    DR_CHECK(p->k >= 1 && p->L >= 1 && p->L <= 512, "dr_search_batch: bad k/L");
+    DR_CUDA(cudaSetDevice(h->device));
+    if (B == 0) return 0;
+    // carve one staging allocation: Q | lut? | ids | dist | hops | visited | status | list_ids | list_dist | list_len | trace
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t szQ = al((size_t)B * h->D * 4);
+    const size_t szLut = lut ? al((size_t)B * h->M * 1024) : 0;
+    const size_t szK = al((size_t)B * p->k * 4), szB = al((size_t)B * 4);
+    const size_t szL = al((size_t)B * p->L * 4);
+    const size_t szT = trace ? al((size_t)B * trace_cap * 4) : 0;
+    size_t total = szQ + szLut + 2 * szK + 4 * szB + 2 * szL + szT;
+    if (dr_scratch(&h->d_io, &h->io_bytes, total)) return 1;
+    char *base = (char *)h->d_io;
+    float *dQ = (float *)base; base += szQ;
+    float *dLut = lut ? (float *)base : nullptr; base += szLut;
+    int32_t *dIds = (int32_t *)base; base += szK;
+    float *dDist = (float *)base; base += szK;
+    int32_t *dHops = (int32_t *)base; base += szB;
+    int32_t *dVis = (int32_t *)base; base += szB;
+    int32_t *dStat = (int32_t *)base; base += szB;
+    int32_t *dLlen = (int32_t *)base; base += szB;
+    int32_t *dLids = (int32_t *)base; base += szL;
+    float *dLdist = (float *)base; base += szL;
+    int32_t *dTrace = trace ? (int32_t *)base : nullptr;
+    cudaStream_t s = 0;
+    DR_CUDA(cudaMemcpyAsync(dQ, Q, (size_t)B * h->D * 4, cudaMemcpyHostToDevice, s));
+    if (lut) DR_CUDA(cudaMemcpyAsync(dLut, lut, (size_t)B * h->M * 1024, cudaMemcpyHostToDevice, s));
+    if (trace) DR_CUDA(cudaMemsetAsync(dTrace, 0xFF, (size_t)B * trace_cap * 4, s));
+    int rc = launch_search(h, dQ, B, p, dLut, dIds, dDist, dHops, dVis, out_list_ids ? dLids : nullptr,
+                           out_list_dist ? dLdist : nullptr, dLlen, dTrace, trace_cap, dStat, s);
+    if (rc) return rc;
+    DR_CUDA(cudaMemcpyAsync(out_ids, dIds, (size_t)B * p->k * 4, cudaMemcpyDeviceToHost, s));
+    if (out_dist) DR_CUDA(cudaMemcpyAsync(out_dist, dDist, (size_t)B * p->k * 4, cudaMemcpyDeviceToHost, s));
+    if (out_hops) DR_CUDA(cudaMemcpyAsync(out_hops, dHops, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (out_visited) DR_CUDA(cudaMemcpyAsync(out_visited, dVis, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (out_status) DR_CUDA(cudaMemcpyAsync(out_status, dStat, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (out_list_len) DR_CUDA(cudaMemcpyAsync(out_list_len, dLlen, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (out_list_ids) DR_CUDA(cudaMemcpyAsync(out_list_ids, dLids, (size_t)B * p->L * 4, cudaMemcpyDeviceToHost, s));
+    if (out_list_dist) DR_CUDA(cudaMemcpyAsync(out_list_dist, dLdist, (size_t)B * p->L * 4, cudaMemcpyDeviceToHost, s));
+    if (trace) DR_CUDA(cudaMemcpyAsync(trace, dTrace, (size_t)B * trace_cap * 4, cudaMemcpyDeviceToHost, s));
+    DR_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dr_lut_build_dev(dr_index *h, const float *d_Q, int64_t B, float *d_out, void *stream) {
+    DR_CHECK(h && h->d_codebook && h->M > 0, "dr_lut_build: index has no codebook");
+    DR_CUDA(cudaSetDevice(h->device));
+    return launch_lut_build(h->d_codebook, d_Q, B, h->D, h->M, d_out, (cudaStream_t)stream);
+}
+
+int dr_lut_build(dr_index *h, const float *Q, int64_t B, float *out) {
+    DR_CHECK(h && h->d_codebook && h->M > 0, "dr_lut_build: index has no codebook");
+    DR_CUDA(cudaSetDevice(h->device));
+    DevBuf q, o;
+    if (q.alloc((size_t)B * h->D * 4) || o.alloc((size_t)B * h->M * 1024)) return 1;
+    DR_CUDA(cudaMemcpy(q.p, Q, (size_t)B * h->D * 4, cudaMemcpyHostToDevice));
+    if (launch_lut_build(h->d_codebook, q.as<float>(), B, h->D, h->M, o.as<float>(), 0)) return 1;
+    DR_CUDA(cudaMemcpy(out, o.p, (size_t)B * h->M * 1024, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_pq_lut(const float *codebook, const float *Q, int64_t B, int32_t D, int32_t M, float *out, int device) {
+    if (use_device(device)) return 3;
+    DR_CHECK(M > 0 && D % M == 0, "dr_pq_lut: D=%d not divisible by M=%d", D, M);
+    DevBuf cb, q, o;
+    if (cb.alloc((size_t)256 * D * 4) || q.alloc((size_t)B * D * 4) || o.alloc((size_t)B * M * 1024)) return 1;
+    DR_CUDA(cudaMemcpy(cb.p, codebook, (size_t)256 * D * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(q.p, Q, (size_t)B * D * 4, cudaMemcpyHostToDevice));
+    if (launch_lut_build(cb.as<float>(), q.as<float>(), B, D, M, o.as<float>(), 0)) return 1;
+    DR_CUDA(cudaMemcpy(out, o.p, (size_t)B * M * 1024, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_pq_train_dev(const float *d_X, int64_t N, int32_t D, int32_t M, int32_t iters, uint64_t seed, float *d_out_codebook,
+                    double *out_mse, int device, void *stream) {
+    if (use_device(device)) return 3;
+    return launch_pq_train(d_X, N, D, M, iters, seed, d_out_codebook, out_mse, (cudaStream_t)stream);
+}
+
+int dr_pq_train(const float *X, int64_t N, int32_t D, int32_t M, int32_t iters, uint64_t seed, float *out_codebook,
+                double *out_mse, int device) {
+    if (use_device(device)) return 3;
+    DevBuf x, cb;
+    if (x.alloc((size_t)N * D * 4) || cb.alloc((size_t)256 * D * 4)) return 1;
+    DR_CUDA(cudaMemcpy(x.p, X, (size_t)N * D * 4, cudaMemcpyHostToDevice));
+    if (launch_pq_train(x.as<float>(), N, D, M, iters, seed, cb.as<float>(), out_mse, 0)) return 1;
+    DR_CUDA(cudaMemcpy(out_codebook, cb.p, (size_t)256 * D * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_pq_encode_dev(const float *d_codebook, const float *d_X, int64_t N, int32_t D, int32_t M, uint8_t *d_out_codes,
+                     int device, void *stream) {
+    if (use_device(device)) return 3;
+    return launch_pq_encode(d_codebook, d_X, N, D, M, d_out_codes, (cudaStream_t)stream);
+}
+
+int dr_pq_encode(const float *codebook, const float *X, int64_t N, int32_t D, int32_t M, uint8_t *out_codes, int device) {
+    if (use_device(device)) return 3;
+    DevBuf x, cb, c;
+    if (x.alloc((size_t)N * D * 4) || cb.alloc((size_t)256 * D * 4) || c.alloc((size_t)N * M)) return 1;
+    DR_CUDA(cudaMemcpy(x.p, X, (size_t)N * D * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(cb.p, codebook, (size_t)256 * D * 4, cudaMemcpyHostToDevice));
+    if (launch_pq_encode(cb.as<float>(), x.as<float>(), N, D, M, c.as<uint8_t>(), 0)) return 1;
+    DR_CUDA(cudaMemcpy(out_codes, c.p, (size_t)N * M, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_pq_decode(const float *codebook, const uint8_t *codes, int64_t N, int32_t D, int32_t M, float *out, int device) {
+    if (use_device(device)) return 3;
+    DR_CHECK(M > 0 && D % M == 0, "dr_pq_decode: D=%d not divisible by M=%d", D, M);
+    DevBuf cb, c, o;
+    if (cb.alloc((size_t)256 * D * 4) || c.alloc((size_t)N * M) || o.alloc((size_t)N * D * 4)) return 1;
+    DR_CUDA(cudaMemcpy(cb.p, codebook, (size_t)256 * D * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(c.p, codes, (size_t)N * M, cudaMemcpyHostToDevice));
+    if (launch_pq_decode(cb.as<float>(), c.as<uint8_t>(), N, D, M, o.as<float>(), 0)) return 1;
+    DR_CUDA(cudaMemcpy(out, o.p, (size_t)N * D * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_adc(const uint8_t *codes, const float *lut, int64_t n, int32_t M, float *out, int device) {
+    if (use_device(device)) return 3;
+    DevBuf c, l, o;
+    if (c.alloc((size_t)n * M) || l.alloc((size_t)M * 1024) || o.alloc((size_t)n * 4)) return 1;
+    DR_CUDA(cudaMemcpy(c.p, codes, (size_t)n * M, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(l.p, lut, (size_t)M * 1024, cudaMemcpyHostToDevice));
+    if (launch_adc(c.as<uint8_t>(), l.as<float>(), n, M, o.as<float>(), 0)) return 1;
+    DR_CUDA(cudaMemcpy(out, o.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int rowdist_host(const float *A, const float *B, int64_t n, int64_t nb, int32_t D, int op, float *out, int device) {
+    if (use_device(device)) return 3;
+    DR_CHECK(nb == n || nb == 1, "row distance: B must have n rows or 1 row (n=%lld nb=%lld)", (long long)n, (long long)nb);
+    DevBuf a, b, o;
+    if (a.alloc((size_t)n * D * 4) || b.alloc((size_t)nb * D * 4) || o.alloc((size_t)n * 4)) return 1;
+    DR_CUDA(cudaMemcpy(a.p, A, (size_t)n * D * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(b.p, B, (size_t)nb * D * 4, cudaMemcpyHostToDevice));
+    if (launch_rowdist(a.as<float>(), b.as<float>(), n, nb, D, op, o.as<float>(), 0)) return 1;
+    DR_CUDA(cudaMemcpy(out, o.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int dr_l2sq_batch(const float *A, const float *B, int64_t n, int64_t nb, int32_t D, float *out, int device) {
+    return rowdist_host(A, B, n, nb, D, 0, out, device);
+}
+int dr_dot_batch(const float *A, const float *B, int64_t n, int64_t nb, int32_t D, float *out, int device) {
+    return rowdist_host(A, B, n, nb, D, 1, out, device);
+}
+int dr_cosine_batch(const float *A, const float *B, int64_t n, int64_t nb, int32_t D, float *out, int device) {
+    return rowdist_host(A, B, n, nb, D, 2, out, device);
+}
+
+int dr_pq_sdc_batch(const float *codebook, const uint8_t *c1, const uint8_t *c2, int64_t n, int32_t M, int32_t ds, float *out,
+                    int device) {
+    if (use_device(device)) return 3;
+    DevBuf cb, a, b, o;
+    if (cb.alloc((size_t)M * 256 * ds * 4) || a.alloc((size_t)n * M) || b.alloc((size_t)n * M) || o.alloc((size_t)n * 4)) return 1;
+    DR_CUDA(cudaMemcpy(cb.p, codebook, (size_t)M * 256 * ds * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(a.p, c1, (size_t)n * M, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(b.p, c2, (size_t)n * M, cudaMemcpyHostToDevice));
+    if (launch_sdc(cb.as<float>(), a.as<uint8_t>(), b.as<uint8_t>(), n, M, ds, o.as<float>(), 0)) return 1;
+    DR_CUDA(cudaMemcpy(out, o.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_medoid(const float *X, int64_t N, int32_t D, const int32_t *samples, int32_t ns, int64_t *out_medoid, int device) {
+    if (use_device(device)) return 3;
+    DR_CHECK(ns >= 1 && ns <= N, "dr_medoid: need 1 <= ns <= N");
+    DevBuf x, sm, sums;
+    if (x.alloc((size_t)N * D * 4) || sm.alloc((size_t)ns * 4) || sums.alloc((size_t)ns * 8)) return 1;
+    DR_CUDA(cudaMemcpy(x.p, X, (size_t)N * D * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(sm.p, samples, (size_t)ns * 4, cudaMemcpyHostToDevice));
+    if (launch_medoid(x.as<float>(), N, D, sm.as<int32_t>(), ns, N <= ns ? 1 : 0, sums.as<double>(), 0)) return 1;
+    std::vector<double> hs(ns);
+    DR_CUDA(cudaMemcpy(hs.data(), sums.p, (size_t)ns * 8, cudaMemcpyDeviceToHost));
+    int best = 0;
+    for (int i = 1; i < ns; ++i) if (hs[i] < hs[best]) best = i;
+    *out_medoid = samples[best];
+    return 0;
+}
+
+int dr_vamana_build_dev(const float *d_X, int64_t N, int32_t D, int32_t R, int32_t L, float alpha, int64_t medoid,
+                        uint64_t seed, uint32_t *d_out_adj, int32_t *d_out_deg, int device, void *stream) {
+    if (use_device(device)) return 3;
+    return launch_vamana_build(d_X, N, D, R, L, alpha, medoid, seed, d_out_adj, d_out_deg, device, (cudaStream_t)stream);
+}
+
+int dr_vamana_build(const float *X, int64_t N, int32_t D, int32_t R, int32_t L, float alpha, int64_t medoid, uint64_t seed,
+                    uint32_t *out_adj, int32_t *out_deg, int device) {
+    if (use_device(device)) return 3;
+    DevBuf x, adj, deg;
+    if (x.alloc((size_t)N * D * 4) || adj.alloc((size_t)N * R * 4) || deg.alloc((size_t)N * 4)) return 1;
+    DR_CUDA(cudaMemcpy(x.p, X, (size_t)N * D * 4, cudaMemcpyHostToDevice));
+    if (launch_vamana_build(x.as<float>(), N, D, R, L, alpha, medoid, seed, adj.as<uint32_t>(), deg.as<int32_t>(), device, 0)) return 1;
+    DR_CUDA(cudaDeviceSynchronize());
+    DR_CUDA(cudaMemcpy(out_adj, adj.p, (size_t)N * R * 4, cudaMemcpyDeviceToHost));
+    if (out_deg) DR_CUDA(cudaMemcpy(out_deg, deg.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_topk_merge_dev(const int32_t *d_ids, const float *d_dist, int32_t G, int64_t B, int32_t k, int32_t *d_out_ids,
+                      float *d_out_dist, int device, void *stream) {
+    if (use_device(device)) return 3;
+    return launch_topk_merge(d_ids, d_dist, G, B, k, d_out_ids, d_out_dist, (cudaStream_t)stream);
+}
+
+}  // extern "C"

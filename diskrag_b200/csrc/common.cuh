@@ -1,0 +1,138 @@
+// common.cuh — shared host/device helpers for libdiskrag_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/diskrag_b200.h"
+
+typedef unsigned long long u64;
+
+// ---------------------------------------------------------------------------------------------
+// host side: errors, launch accounting, the index handle
+// ---------------------------------------------------------------------------------------------
+void dr_set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define DR_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            dr_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define DR_CHECK(cond, ...)                \
+    do {                                   \
+        if (!(cond)) {                     \
+            dr_set_error(__VA_ARGS__);     \
+            return 2;                      \
+        }                                  \
+    } while (0)
+
+#define DR_LAUNCHED()                                  \
+    do {                                               \
+        g_launches.fetch_add(1);                       \
+        DR_CUDA(cudaGetLastError());                   \
+    } while (0)
+
+struct dr_index {
+    int device = 0;
+    int64_t N = 0;
+    int D = 0, R = 0, M = 0;
+    int64_t medoid = 0;
+    bool owns = true;
+    float *d_vec = nullptr;       // [N, D]
+    uint32_t *d_adj = nullptr;    // [N, R] 0-padded, stored order
+    uint8_t *d_codes = nullptr;   // [N, M]
+    float *d_codebook = nullptr;  // [M, 256, ds]
+    // scratch (grown on demand, reused across calls)
+    float *d_lut = nullptr; size_t lut_bytes = 0;
+    u64 *d_counter = nullptr;
+    uint32_t *d_ovf = nullptr; size_t ovf_bytes = 0;
+    void *d_io = nullptr; size_t io_bytes = 0;  // staging for the host-pointer API
+    int sms = 0, smem_optin = 0;
+    // search-kernel timing (bench roofline)
+    bool timing = false; double timed_ms = 0.0; long long timed_launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+int dr_scratch(void **ptr, size_t *cur, size_t need);  // grow-only device scratch
+
+// internal launchers (defined in the respective .cu files)
+int launch_lut_build(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, float *d_out, cudaStream_t s);
+int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, const float *d_lut,
+                  int32_t *ids, float *dist, int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist,
+                  int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+#define DR_FULL 0xFFFFFFFFu
+#define DR_EMPTY 0xFFFFFFFFu
+#define DR_KEY_MAX 0xFFFFFFFFFFFFFFFFull
+
+// order-preserving float -> uint32 (total order equals the float order; -0.0 is folded into +0.0 by the caller)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(b);
+}
+// search-list key: (distance, id) ascending == the reference's tuple order; bit 0 = expanded flag
+__device__ __forceinline__ u64 make_key(float d, uint32_t id) {
+    return ((u64)f2ord(d + 0.0f) << 32) | ((u64)id << 1);
+}
+__device__ __forceinline__ uint32_t key_id(u64 k) { return (uint32_t)(k & 0xFFFFFFFFull) >> 1; }
+__device__ __forceinline__ float key_dist(u64 k) { return ord2f((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_dbits(u64 k) { return (uint32_t)(k >> 32); }
+
+__device__ __forceinline__ float warp_sum_butterfly(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = __fadd_rn(v, __shfl_xor_sync(DR_FULL, v, off));
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// Canonical exact fp32 squared L2 of one row against a query held in shared memory, one warp per row.
+// Order (restated by oracle.c:orc_l2sq_warp): lane l owns elements (j*32+l)*VW+c, VW = 4 if D%4==0
+// else 1; per lane fmaf accumulation in increasing index; xor-butterfly 16,8,4,2,1.
+__device__ __forceinline__ float warp_l2sq(const float *__restrict__ row, const float *__restrict__ q, int D, int lane) {
+    float acc = 0.0f;
+    if ((D & 3) == 0) {
+        int base = lane * 4;
+#pragma unroll 4
+        for (; base < D; base += 128) {
+            float4 a = ldg_f4(row + base);
+            float4 b = *reinterpret_cast<const float4 *>(q + base);
+            float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y), d2 = __fsub_rn(a.z, b.z), d3 = __fsub_rn(a.w, b.w);
+            acc = __fmaf_rn(d0, d0, acc);
+            acc = __fmaf_rn(d1, d1, acc);
+            acc = __fmaf_rn(d2, d2, acc);
+            acc = __fmaf_rn(d3, d3, acc);
+        }
+    } else {
+        for (int i = lane; i < D; i += 32) {
+            float d = __fsub_rn(__ldg(row + i), q[i]);
+            acc = __fmaf_rn(d, d, acc);
+        }
+    }
+    return warp_sum_butterfly(acc);
+}
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+#endif  // __CUDACC__

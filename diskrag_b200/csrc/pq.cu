@@ -1,0 +1,313 @@
+// pq.cu — product-quantiser kernels: K2 ADC table build, K3 k-means training / encode / decode, ADC sums.
+//
+// K2 replaces DiskANNPQ.compute_distance_table (fast_pq.py:294-318).  The table is produced on CUDA
+// cores in exactly numpy's fp32 operation order (diff, square, pairwise row reduction) so that the
+// traversal that consumes it is bit-identical to the reference's; the job is bound by writing
+// B x M x 1 KiB of table to HBM, not by its 3*256*D flops per query, so there is nothing for the
+// tensor pipe to win here.
+// K3 replaces DiskANNPQ.fit / encode / decode (fast_pq.py:197-292) (sklearn KMeans per subspace).
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// numpy float32 pairwise row sum of t_j = (cen[j] - q[j])^2   (oracle.c: np_pairwise_sum_f32)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqdiff(const float *cen, const float *q, int j) {
+    float d = __fsub_rn(cen[j], q[j]);
+    return __fmul_rn(d, d);
+}
+
+__device__ float np_pairwise_sqdiff(const float *cen, const float *q, int n) {
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, sqdiff(cen, q, i));
+        return res;
+    } else if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = sqdiff(cen, q, j);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], sqdiff(cen, q, i + j));
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, sqdiff(cen, q, i));
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return __fadd_rn(np_pairwise_sqdiff(cen, q, n2), np_pairwise_sqdiff(cen + n2, q + n2, n - n2));
+    }
+}
+
+// compile-time sub-dimension: centroid in registers, fully unrolled numpy order
+template <int DS>
+__device__ __forceinline__ float np_pairwise_ct(const float (&cr)[DS], const float *__restrict__ q) {
+    float t[DS];
+#pragma unroll
+    for (int j = 0; j < DS; ++j) {
+        float d = __fsub_rn(cr[j], q[j]);
+        t[j] = __fmul_rn(d, d);
+    }
+    if (DS < 8) {
+        float res = 0.0f;
+#pragma unroll
+        for (int i = 0; i < DS; ++i) res = __fadd_rn(res, t[i]);
+        return res;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = t[j];
+#pragma unroll
+    for (int i = 8; i < DS - (DS % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], t[i + j]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+#pragma unroll
+    for (int i = DS - (DS % 8); i < DS; ++i) res = __fadd_rn(res, t[i]);
+    return res;
+}
+
+// grid (M, ceil(B/QT)); 256 threads: thread c owns centroid c of subspace m and walks the query tile.
+#define LUT_QT 64
+template <int DS>  // DS == 0: runtime sub-dimension
+__global__ void __launch_bounds__(256) lut_kernel(const float *__restrict__ codebook, const float *__restrict__ Q,
+                                                  long long B, int D, int M, float *__restrict__ out) {
+    extern __shared__ float s_qs[];  // [LUT_QT][ds]
+    const int m = blockIdx.x, ds = DS ? DS : D / M, c = threadIdx.x;
+    const long long b0 = (long long)blockIdx.y * LUT_QT;
+    const int nb = (int)((B - b0 < LUT_QT) ? (B - b0) : LUT_QT);
+    for (int i = threadIdx.x; i < nb * ds; i += blockDim.x) {
+        int bb = i / ds, j = i - bb * ds;
+        s_qs[i] = __ldg(Q + (size_t)(b0 + bb) * D + m * ds + j);
+    }
+    __syncthreads();
+    const float *cen = codebook + ((size_t)m * 256 + c) * ds;
+    float *o = out + ((size_t)b0 * M + m) * 256 + c;
+    if (DS) {
+        float cr[DS ? DS : 1];
+#pragma unroll
+        for (int j = 0; j < (DS ? DS : 1); ++j) cr[j] = __ldg(cen + j);
+        for (int bb = 0; bb < nb; ++bb) o[(size_t)bb * M * 256] = np_pairwise_ct<(DS ? DS : 1)>(cr, s_qs + bb * (DS ? DS : 1));
+    } else {
+        for (int bb = 0; bb < nb; ++bb) o[(size_t)bb * M * 256] = np_pairwise_sqdiff(cen, s_qs + bb * ds, ds);
+    }
+}
+
+int launch_lut_build(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, float *d_out, cudaStream_t s) {
+    DR_CHECK(M > 0 && D % M == 0, "dr_lut_build: D=%d not divisible by M=%d", D, M);
+    if (B == 0) return 0;
+    const int ds = D / M;
+    const size_t smem = (size_t)LUT_QT * ds * sizeof(float);
+    DR_CHECK(smem <= 48 * 1024, "dr_lut_build: sub-dimension %d too large", ds);
+    const long long tiles = (B + LUT_QT - 1) / LUT_QT;
+    for (long long t0 = 0; t0 < tiles; t0 += 65535) {  // gridDim.y limit
+        long long nt = tiles - t0 < 65535 ? tiles - t0 : 65535;
+        dim3 grid(M, (unsigned)nt);
+        const float *q = d_Q + (size_t)t0 * LUT_QT * D;
+        float *o = d_out + (size_t)t0 * LUT_QT * M * 256;
+        long long bb = B - t0 * LUT_QT;
+        switch (ds) {
+#define LUT_CASE(X) case X: lut_kernel<X><<<grid, 256, smem, s>>>(d_codebook, q, bb, D, M, o); break;
+            LUT_CASE(4) LUT_CASE(8) LUT_CASE(12) LUT_CASE(16) LUT_CASE(24) LUT_CASE(32) LUT_CASE(48) LUT_CASE(64)
+#undef LUT_CASE
+            default: lut_kernel<0><<<grid, 256, smem, s>>>(d_codebook, q, bb, D, M, o); break;
+        }
+        DR_LAUNCHED();
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ADC sums, sequential order (fast_pq.py:320-328): one thread per code row
+// ---------------------------------------------------------------------------------------------------
+__global__ void adc_kernel(const uint8_t *__restrict__ codes, const float *__restrict__ lut, long long n, int M,
+                           float *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *code = codes + (size_t)i * M;
+    float acc = 0.0f;
+    for (int m = 0; m < M; ++m) acc = __fadd_rn(acc, __ldg(lut + m * 256 + code[m]));
+    out[i] = acc;
+}
+
+int launch_adc(const uint8_t *d_codes, const float *d_lut, int64_t n, int M, float *d_out, cudaStream_t s) {
+    if (n == 0) return 0;
+    adc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_codes, d_lut, n, M, d_out);
+    DR_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: nearest-centroid assignment (encode) and Lloyd k-means
+//   grid (ceil(N/256), M), 256 threads: the CTA stages subspace m's 256 centroids in shared memory,
+//   each thread owns one point's sub-vector in registers and scans the centroids (broadcast reads).
+//   Lowest index wins ties (strict <), as sklearn's argmin does.
+// ---------------------------------------------------------------------------------------------------
+#define PQ_MAX_DS 64
+template <bool ACCUM>
+__global__ void __launch_bounds__(256) assign_kernel(const float *__restrict__ X, long long N, int D, int M,
+                                                     long long stride, long long offset,
+                                                     const float *__restrict__ codebook, uint8_t *__restrict__ codes,
+                                                     float *__restrict__ sums, int *__restrict__ counts,
+                                                     double *__restrict__ sse) {
+    extern __shared__ float s_pq[];  // centroids [256][ds]; ACCUM: + sums [256][ds] + counts [256]
+    const int m = blockIdx.y, ds = D / M;
+    float *s_cen = s_pq;
+    float *s_sum = s_pq + 256 * ds;
+    int *s_cnt = reinterpret_cast<int *>(s_sum + 256 * ds);
+    for (int i = threadIdx.x; i < 256 * ds; i += blockDim.x) {
+        s_cen[i] = __ldg(codebook + (size_t)m * 256 * ds + i);
+        if (ACCUM) s_sum[i] = 0.0f;
+    }
+    if (ACCUM) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float best = 0.0f;
+    if (i < N) {
+        const long long row = i * stride + offset;  // training subsample walks every stride-th row
+        const float *x = X + (size_t)row * D + m * ds;
+        float xr[PQ_MAX_DS];
+        for (int j = 0; j < ds; ++j) xr[j] = __ldg(x + j);
+        int bi = 0;
+        best = __int_as_float(0x7f800000);
+        for (int c = 0; c < 256; ++c) {
+            const float *cen = s_cen + c * ds;
+            float acc = 0.0f;
+            for (int j = 0; j < ds; ++j) {
+                float d = __fsub_rn(xr[j], cen[j]);
+                acc = __fmaf_rn(d, d, acc);
+            }
+            if (acc < best) { best = acc; bi = c; }
+        }
+        if (codes) codes[(size_t)i * M + m] = (uint8_t)bi;
+        if (ACCUM) {
+            for (int j = 0; j < ds; ++j) atomicAdd(&s_sum[bi * ds + j], xr[j]);
+            atomicAdd(&s_cnt[bi], 1);
+        }
+    }
+    if (ACCUM) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 256 * ds; t += blockDim.x)
+            if (s_sum[t] != 0.0f) atomicAdd(&sums[(size_t)m * 256 * ds + t], s_sum[t]);
+        for (int t = threadIdx.x; t < 256; t += blockDim.x)
+            if (s_cnt[t]) atomicAdd(&counts[m * 256 + t], s_cnt[t]);
+        if (sse) {
+            float v = (i < N) ? best : 0.0f;
+            v = warp_sum_butterfly(v);
+            if ((threadIdx.x & 31) == 0) atomicAdd(sse, (double)v);
+        }
+    }
+}
+
+// new centroid = mean of its members; an empty cluster is re-seeded from a pseudo-random training row
+__global__ void update_kernel(float *__restrict__ codebook, const float *__restrict__ sums, const int *__restrict__ counts,
+                              const float *__restrict__ X, long long N, int D, int M, unsigned long long seed, int iter) {
+    const int ds = D / M;
+    const int mc = blockIdx.x;  // m*256 + c
+    const int cnt = counts[mc];
+    const int m = mc >> 8;
+    for (int j = threadIdx.x; j < ds; j += blockDim.x) {
+        float v;
+        if (cnt > 0) v = sums[(size_t)mc * ds + j] / (float)cnt;
+        else {
+            unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(mc * 131 + iter * 7919 + 1);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+            v = X[(size_t)(z % (unsigned long long)N) * D + m * ds + j];
+        }
+        codebook[(size_t)mc * ds + j] = v;
+    }
+}
+
+__global__ void init_codebook_kernel(float *__restrict__ codebook, const float *__restrict__ X, long long N, int D, int M,
+                                     unsigned long long seed) {
+    const int ds = D / M;
+    const int mc = blockIdx.x, m = mc >> 8, c = mc & 255;
+    // 256 distinct rows per subspace: an affine walk with an odd stride over N (distinct while 256*step < N wraps rarely)
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(m + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    unsigned long long step = (unsigned long long)N / 256ull;
+    if (step == 0) step = 1;
+    unsigned long long row = (z % (unsigned long long)N + (unsigned long long)c * step) % (unsigned long long)N;
+    for (int j = threadIdx.x; j < ds; j += blockDim.x) codebook[(size_t)mc * ds + j] = X[(size_t)row * D + m * ds + j];
+}
+
+static size_t assign_smem(int ds, bool accum) { return (size_t)256 * ds * 4 * (accum ? 2 : 1) + (accum ? 1024 : 0); }
+
+int launch_pq_encode(const float *d_codebook, const float *d_X, int64_t N, int D, int M, uint8_t *d_codes, cudaStream_t s) {
+    DR_CHECK(M > 0 && D % M == 0, "dr_pq_encode: D=%d not divisible by M=%d", D, M);
+    const int ds = D / M;
+    DR_CHECK(ds <= PQ_MAX_DS, "dr_pq_encode: sub-dimension %d > %d not supported", ds, PQ_MAX_DS);
+    if (N == 0) return 0;
+    size_t smem = assign_smem(ds, false);
+    DR_CUDA(cudaFuncSetAttribute(assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((N + 255) / 256), M);
+    assign_kernel<false><<<grid, 256, smem, s>>>(d_X, N, D, M, 1, 0, d_codebook, d_codes, nullptr, nullptr, nullptr);
+    DR_LAUNCHED();
+    return 0;
+}
+
+int launch_pq_train(const float *d_X, int64_t N, int D, int M, int iters, uint64_t seed, float *d_codebook,
+                    double *out_mse, cudaStream_t s) {
+    DR_CHECK(M > 0 && D % M == 0, "dr_pq_train: D=%d not divisible by M=%d", D, M);
+    DR_CHECK(N >= 256, "dr_pq_train: need at least 256 training vectors (got %lld)", (long long)N);
+    const int ds = D / M;
+    DR_CHECK(ds <= PQ_MAX_DS, "dr_pq_train: sub-dimension %d > %d not supported", ds, PQ_MAX_DS);
+    if (iters <= 0) iters = 25;
+    // training subsample: every stride-th row (sklearn trains on all rows; 1024 rows per centroid is plenty)
+    long long ntrain = N, stride = 1;
+    const long long cap = 262144;
+    if (N > cap) { stride = N / cap; ntrain = N / stride; }
+    float *d_sums = nullptr; int *d_counts = nullptr; double *d_sse = nullptr;
+    DR_CUDA(cudaMalloc(&d_sums, (size_t)M * 256 * ds * 4));
+    DR_CUDA(cudaMalloc(&d_counts, (size_t)M * 256 * 4));
+    DR_CUDA(cudaMalloc(&d_sse, 8));
+    init_codebook_kernel<<<M * 256, 32, 0, s>>>(d_codebook, d_X, N, D, M, seed);
+    DR_LAUNCHED();
+    size_t smem = assign_smem(ds, true);
+    DR_CUDA(cudaFuncSetAttribute(assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((ntrain + 255) / 256), M);
+    for (int it = 0; it < iters; ++it) {
+        DR_CUDA(cudaMemsetAsync(d_sums, 0, (size_t)M * 256 * ds * 4, s));
+        DR_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)M * 256 * 4, s));
+        DR_CUDA(cudaMemsetAsync(d_sse, 0, 8, s));
+        assign_kernel<true><<<grid, 256, smem, s>>>(d_X, ntrain, D, M, stride, 0, d_codebook, nullptr, d_sums, d_counts, d_sse);
+        DR_LAUNCHED();
+        if (it + 1 < iters) {  // the last pass only measures the error of the final codebook
+            update_kernel<<<M * 256, 32, 0, s>>>(d_codebook, d_sums, d_counts, d_X, N, D, M, seed, it);
+            DR_LAUNCHED();
+        }
+    }
+    if (out_mse) {
+        double sse = 0.0;
+        DR_CUDA(cudaMemcpyAsync(&sse, d_sse, 8, cudaMemcpyDeviceToHost, s));
+        DR_CUDA(cudaStreamSynchronize(s));
+        *out_mse = sse / ((double)ntrain * (double)D);
+    } else {
+        DR_CUDA(cudaStreamSynchronize(s));
+    }
+    cudaFree(d_sums); cudaFree(d_counts); cudaFree(d_sse);
+    return 0;
+}
+
+// decode (fast_pq.py:269-292): gather centroids
+__global__ void decode_kernel(const float *__restrict__ codebook, const uint8_t *__restrict__ codes, long long N, int D, int M,
+                              float *__restrict__ out) {
+    const int ds = D / M;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * D) return;
+    long long i = t / D;
+    int j = (int)(t - i * D), m = j / ds, jj = j - m * ds;
+    out[t] = __ldg(codebook + ((size_t)m * 256 + codes[(size_t)i * M + m]) * ds + jj);
+}
+
+int launch_pq_decode(const float *d_codebook, const uint8_t *d_codes, int64_t N, int D, int M, float *d_out, cudaStream_t s) {
+    if (N == 0) return 0;
+    long long tot = (long long)N * D;
+    decode_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_codebook, d_codes, N, D, M, d_out);
+    DR_LAUNCHED();
+    return 0;
+}

@@ -1,0 +1,182 @@
+"""GPU parity tests of K1 (batched beam search) through the C ABI.
+
+Bar: bit-exact ids / ADC distances / hop counts / visited order against (a) the golden vectors the real
+reference produced and (b) the oracle on seeded cases; exact fp32 distances within 1e-4 relative of the
+reference's numpy values (bit-equal to the oracle's restatement of the GPU summation order)."""
+import numpy as np
+import pytest
+
+from conftest import canon, make_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gidx(golden):
+    from diskrag_b200.engine import GpuIndex
+    g = golden
+    idx = GpuIndex.from_records(g["records"], g["N"], g["D"], g["R"], g["codes"], g["codebook"], g["medoid"])
+    yield idx
+    idx.close()
+
+
+def test_lut_bit_exact_vs_reference(golden, gidx):
+    T = gidx.lut(golden["Q"][:8])
+    assert np.array_equal(T, golden["exp_lut"])
+
+
+@pytest.mark.parametrize("L", [10, 40])
+@pytest.mark.parametrize("own_lut", [True, False])
+def test_variant_A_golden(golden, gidx, orc, L, own_lut):
+    g = golden
+    lut = None if own_lut else np.stack([orc.lut(g["codebook"], q) for q in g["Q"]])
+    r = gidx.search(g["Q"], k=min(10, L), L=L, W=1, dist="pq", adc_order="seq", rerank=False, lut=lut, want_list=True,
+                    trace=2048)
+    for qi in range(g["Q"].shape[0]):
+        exp_ids = g[f"exp_A_ids_L{L}"][qi]; exp_d = g[f"exp_A_dist_L{L}"][qi]
+        a = canon(exp_ids, exp_d)
+        n = r.list_len[qi]
+        b = canon(r.list_ids[qi, :n], r.list_dists[qi, :n])
+        assert np.array_equal(a[0], b[0]), qi
+        assert np.array_equal(a[1], b[1]), qi            # ADC distances bit-for-bit
+        h = orc.search_heap(g["adj"], g["medoid"], L, codes=g["codes"], lut_=orc.lut(g["codebook"], g["Q"][qi]),
+                            dist_mode=orc.DIST_ADC_SEQ, trace=2048)
+        assert r.hops[qi] == h["hops"] and r.visited[qi] == h["visited"]
+        assert np.array_equal(r.trace[qi, :h["visited"]], h["trace"])   # visited / neighbour order
+        # top-k without rerank = head of the list
+        assert np.array_equal(r.ids[qi], b[0][:r.ids.shape[1]])
+
+
+def test_rerank_golden(golden, gidx):
+    g = golden
+    r = gidx.search(g["Q"], k=10, L=40, W=1, dist="pq", rerank=True)
+    for qi in range(g["Q"].shape[0]):
+        np.testing.assert_allclose(r.dists[qi], g["exp_rerank_d2"][qi], rtol=1e-4)   # north-star tolerance
+        a = canon(r.ids[qi], np.round(r.dists[qi], 5)); b = canon(g["exp_rerank_ids"][qi], np.round(g["exp_rerank_d2"][qi], 5))
+        assert set(a[0]) == set(b[0])
+
+
+def test_variant_D_golden(golden, gidx):
+    g = golden
+    r = gidx.search(g["Q"], k=10, L=40, W=1, dist="exact", rerank=False, sqrt_out=True)
+    for qi in range(g["Q"].shape[0]):
+        np.testing.assert_allclose(r.dists[qi], g["exp_D_dist"][qi], rtol=1e-4)
+        assert set(r.ids[qi].tolist()) == set(g["exp_D_ids"][qi].tolist())
+
+
+def test_variant_B_golden(golden, gidx):
+    g = golden
+    r = gidx.search(g["Q"], k=10, L=40, W=1, dist="exact", rerank=False, want_list=True)
+    for qi in range(g["Q"].shape[0]):
+        exp = g["exp_B_ids"][qi]; exp = exp[exp >= 0]
+        n = r.list_len[qi]
+        assert set(r.list_ids[qi, :n].tolist()) == set(exp.tolist())
+
+
+CASES = [
+    # N, D, M, R, Lbuild, seed, dup
+    (1500, 32, 4, 8, 16, 1, 40),      # tiny codes -> massive ADC ties (ghost path)
+    (3000, 96, 12, 20, 32, 2, 0),     # R not a power of two, M % 16 != 0 (byte-load path)
+    (4000, 128, 32, 32, 48, 3, 16),   # M % 16 == 0 (128-bit code loads)
+    (2500, 64, 16, 64, 64, 4, 0),     # R = 64: two adjacency chunks per row
+    (1200, 30, 5, 12, 24, 5, 0),      # D % 4 != 0 (scalar distance path), odd M
+]
+
+
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: f"N{c[0]}D{c[1]}M{c[2]}R{c[3]}")
+def case(request, orc):
+    N, D, M, R, Lb, seed, dup = request.param
+    from diskrag_b200.engine import GpuIndex
+    c = make_case(orc, N, D, M, R, Lb, seed, nq=24, dup=dup)
+    c["idx"] = GpuIndex.from_arrays(c["X"], c["adj"], c["codes"], c["codebook"], c["medoid"])
+    yield c
+    c["idx"].close()
+
+
+@pytest.mark.parametrize("L", [1, 7, 50, 128])
+def test_pq_traversal_vs_oracle(case, orc, L):
+    c = case
+    r = c["idx"].search(c["Q"], k=min(5, L), L=L, W=1, dist="pq", adc_order="seq", rerank=False, want_list=True, trace=8192)
+    ties = 0
+    for qi in range(c["Q"].shape[0]):
+        T = orc.lut(c["codebook"], c["Q"][qi])
+        h = orc.search_heap(c["adj"], c["medoid"], L, codes=c["codes"], lut_=T, dist_mode=orc.DIST_ADC_SEQ, trace=8192)
+        n = r.list_len[qi]
+        a = canon(h["ids"], h["dists"]); b = canon(r.list_ids[qi, :n], r.list_dists[qi, :n])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (qi, L)
+        assert (r.hops[qi], r.visited[qi]) == (h["hops"], h["visited"]), (qi, L)
+        assert np.array_equal(r.trace[qi, :min(8192, h["visited"])], h["trace"]), (qi, L)
+        ties += len(set(h["dists"].tolist())) != len(h["dists"])
+    if c["M"] == 4:
+        assert ties > 0
+
+
+@pytest.mark.parametrize("L", [5, 64])
+def test_exact_traversal_vs_oracle(case, orc, L):
+    c = case
+    r = c["idx"].search(c["Q"], k=min(5, L), L=L, W=1, dist="exact", rerank=False, want_list=True, trace=8192)
+    for qi in range(c["Q"].shape[0]):
+        l = orc.search_list(c["adj"], c["medoid"], L, vec=c["X"], q=c["Q"][qi], dist_mode=orc.DIST_L2_SQ,
+                            flavor=orc.FLAVOR_WARP, W=1, strict_ties=True, trace=8192)
+        n = r.list_len[qi]
+        assert np.array_equal(l["ids"], r.list_ids[qi, :n]) and np.array_equal(l["dists"], r.list_dists[qi, :n]), (qi, L)
+        assert (r.hops[qi], r.visited[qi]) == (l["hops"], l["visited"])
+        assert np.array_equal(r.trace[qi, :l["visited"]], l["trace"])
+
+
+@pytest.mark.parametrize("W", [2, 4, 8])
+@pytest.mark.parametrize("adc", ["seq", "tree"])
+def test_beam_W_vs_oracle(case, orc, W, adc):
+    """Throughput mode (W > 1 expansions per step, tree ADC) is checked bit-for-bit against its restatement."""
+    c = case
+    L = 48
+    r = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", adc_order=adc, rerank=True, want_list=True)
+    for qi in range(c["Q"].shape[0]):
+        T = orc.lut(c["codebook"], c["Q"][qi])
+        l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=T,
+                            dist_mode=orc.DIST_ADC_TREE if adc == "tree" else orc.DIST_ADC_SEQ, W=W, strict_ties=False)
+        n = r.list_len[qi]
+        assert np.array_equal(l["ids"], r.list_ids[qi, :n]) and np.array_equal(l["dists"], r.list_dists[qi, :n]), (qi, W)
+        assert (r.hops[qi], r.visited[qi]) == (l["hops"], l["visited"])
+        oi, od = orc.rerank(c["X"], c["Q"][qi], l["ids"], 10, flavor=orc.FLAVOR_WARP)
+        assert np.array_equal(oi, r.ids[qi, :len(oi)]) and np.array_equal(od, r.dists[qi, :len(od)])
+
+
+def test_visited_overflow_table(case, orc):
+    """Force a tiny shared-memory visited table so the global overflow table is exercised; results must not change."""
+    c = case
+    L = 100
+    r0 = c["idx"].search(c["Q"], k=10, L=L, W=1, dist="pq", rerank=False, want_list=True)
+    r1 = c["idx"].search(c["Q"], k=10, L=L, W=1, dist="pq", rerank=False, want_list=True, hash_cap=256)
+    assert r0.visited.max() > 192   # 3/4 of 256: the overflow path really ran
+    assert np.array_equal(r0.list_ids, r1.list_ids) and np.array_equal(r0.list_dists, r1.list_dists)
+    assert np.array_equal(r0.hops, r1.hops) and np.array_equal(r0.visited, r1.visited)
+    r2 = c["idx"].search(c["Q"], k=10, L=L, W=1, dist="pq", rerank=False, want_list=True)   # table was cleaned
+    assert np.array_equal(r0.list_ids, r2.list_ids)
+
+
+def test_edge_cases(case):
+    c = case
+    idx = c["idx"]
+    r = idx.search(np.zeros((0, c["D"]), np.float32), k=3, L=8)
+    assert r.ids.shape == (0, 3)
+    r = idx.search(c["Q"][:1], k=10, L=10, dist="exact", rerank=False)     # single query
+    assert (r.ids[0] >= 0).all()
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((1, c["D"] + 1), np.float32))                  # dimension mismatch
+    with pytest.raises(ValueError):
+        idx.search(c["Q"][:1], k=20, L=10)                                 # k > L
+    # chunked launches give the same answers as one launch
+    a = idx.search(c["Q"], k=5, L=32, chunk=5)
+    b = idx.search(c["Q"], k=5, L=32)
+    assert np.array_equal(a.ids, b.ids) and np.array_equal(a.dists, b.dists)
+    # k larger than what the graph can reach is padded with -1 / inf
+    from diskrag_b200.engine import GpuIndex
+    tiny = GpuIndex.from_arrays(c["X"][:3], np.array([[1, 0], [0, 0], [2, 2]], np.uint32), medoid=0)
+    r = tiny.search(c["Q"][:2], k=3, L=3, dist="exact", rerank=False)
+    assert (r.ids[:, 2] == -1).all() and np.isinf(r.dists[:, 2]).all() and (r.ids[:, :2] >= 0).all()
+    tiny.close()
+
+
+def test_export_records_roundtrip(golden, gidx):
+    assert np.array_equal(gidx.export_records(), golden["records"])
