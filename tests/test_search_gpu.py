@@ -107,7 +107,7 @@ def test_pq_traversal_vs_oracle(case, orc, L):
         assert (r.hops[qi], r.visited[qi]) == (h["hops"], h["visited"]), (qi, L)
         assert np.array_equal(r.trace[qi, :min(8192, h["visited"])], h["trace"]), (qi, L)
         ties += len(set(h["dists"].tolist())) != len(h["dists"])
-    if c["M"] == 4:
+    if c["M"] == 4 and L >= 50:
         assert ties > 0
 
 
