@@ -38,6 +38,7 @@ int launch_topk_merge(const int32_t *, const float *, int, int64_t, int, int32_t
 int launch_medoid(const float *, int64_t, int, const int32_t *, int, int, double *, cudaStream_t);
 int launch_vamana_build(const float *, int64_t, int, int, int, float, int64_t, uint64_t, uint32_t *, int32_t *, int, cudaStream_t);
 int launch_deinterleave(const void *, int64_t, int, int, float *, uint32_t *, cudaStream_t);
+int launch_prune_one(const float *, int, int, float, int, uint32_t *, int32_t *, cudaStream_t);
 int launch_interleave(const float *, const uint32_t *, int64_t, int, int, void *, cudaStream_t);
 
 // small RAII device buffer for the host-pointer entry points
@@ -220,6 +221,7 @@ int dr_index_destroy(dr_index *h) {
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_ovf) cudaFree(h->d_ovf);
     if (h->d_io) cudaFree(h->d_io);
+    if (h->d_deleted) cudaFree(h->d_deleted);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -468,6 +470,43 @@ int dr_vamana_build(const float *X, int64_t N, int32_t D, int32_t R, int32_t L, 
     DR_CUDA(cudaDeviceSynchronize());
     DR_CUDA(cudaMemcpy(out_adj, adj.p, (size_t)N * R * 4, cudaMemcpyDeviceToHost));
     if (out_deg) DR_CUDA(cudaMemcpy(out_deg, deg.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dr_robust_prune(const float *p, const float *cand, int32_t n, int32_t D, float alpha, int32_t R, int32_t *out_sel,
+                    int32_t *out_n, int device) {
+    if (use_device(device)) return 3;
+    DR_CHECK(p && out_sel && out_n && (cand || n == 0), "dr_robust_prune: null argument");
+    const int stride = n > R ? n : R;
+    DevBuf x, row, deg;
+    if (x.alloc((size_t)(n + 1) * D * 4) || row.alloc((size_t)stride * 4) || deg.alloc(4)) return 1;
+    if (n) DR_CUDA(cudaMemcpy(x.p, cand, (size_t)n * D * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy((char *)x.p + (size_t)n * D * 4, p, (size_t)D * 4, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> ids(stride, 0);
+    for (int i = 0; i < n; ++i) ids[i] = (uint32_t)i;
+    DR_CUDA(cudaMemcpy(row.p, ids.data(), (size_t)stride * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(deg.p, &n, 4, cudaMemcpyHostToDevice));
+    if (launch_prune_one(x.as<float>(), n, D, alpha, R, row.as<uint32_t>(), deg.as<int32_t>(), 0)) return 1;
+    int cnt = 0;
+    DR_CUDA(cudaMemcpy(&cnt, deg.p, 4, cudaMemcpyDeviceToHost));
+    DR_CUDA(cudaMemcpy(ids.data(), row.p, (size_t)stride * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt; ++i) out_sel[i] = (int32_t)ids[i];
+    *out_n = cnt;
+    return 0;
+}
+
+int dr_index_set_deleted(dr_index *h, const uint8_t *mask) {
+    DR_CHECK(h, "dr_index_set_deleted: null handle");
+    DR_CUDA(cudaSetDevice(h->device));
+    if (!mask) { if (h->d_deleted) cudaFree(h->d_deleted); h->d_deleted = nullptr; return 0; }
+    if (!h->d_deleted) DR_CUDA(cudaMalloc(&h->d_deleted, (size_t)h->N));
+    DR_CUDA(cudaMemcpy(h->d_deleted, mask, (size_t)h->N, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int dr_index_set_start(dr_index *h, int64_t start) {
+    DR_CHECK(h && start >= 0 && start < h->N, "dr_index_set_start: out of range");
+    h->medoid = start;
     return 0;
 }
 

@@ -1,8 +1,324 @@
-// build.cu — K5 GPU Vamana build (placeholder until the batched build lands).
+// build.cu — K5: Vamana index construction on the GPU.
+//
+// Replaces build_vamana_index_cython + greedy_search_fast_cython + robust_prune_fast_cython
+// (cython_utils.pyx:269-492).  The reference inserts points strictly one at a time; here each pass
+// (alpha = 1.0, then alpha — cython_utils.pyx:296,310) walks a random permutation in batches
+// (prefix doubling up to ~2 % of N, as batched Vamana builders do):
+//   1. greedy search of every batch point from the medoid on the current graph snapshot, exact fp32
+//      distances (search.cu in DR_DIST_EXACT mode, queries addressed through a row map);
+//   2. RobustPrune(alpha, R) of  search list ∪ N(p)  -> new out-row of p         (prune_kernel, mode 0);
+//   3. reverse edges: pairs (j, p) for j in N(p) are sorted by target; each target appends the
+//      incoming ids while its row has room, otherwise RobustPrune(N(j) ∪ incoming)  (prune_kernel, mode 1).
+// The prune rule is the reference's: candidates sorted by (d, id); after selecting p*, a candidate p'
+// is dropped when alpha * d2(p*, p') <= d2(p, p')  (alpha on SQUARED distances, cython_utils.pyx:483).
+// Unlike the reference, the search list is a true best-L list (not the FIFO window of :400-423) and the
+// stale-tail re-selection of :460-466 is not reproduced; graphs are compared by recall.
 #include "common.cuh"
 
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <random>
+#include <vector>
+
+#define PR_CMAX 320      // candidate capacity per prune (>= L + R)
+#define PR_THREADS 128
+
+struct PruneArgs {
+    const float *X; int D;
+    uint32_t *adj; int32_t *deg; int R; int stride; float alpha;  // stride: adjacency row pitch (== R in the build)
+    int mode;  // 0: insert prune (search list ∪ N(p)); 1: reverse edges (N(j) ∪ incoming)
+    // mode 0
+    const int32_t *nodes; const int32_t *list_ids; const float *list_dist; const int32_t *list_len; int L;
+    // mode 1
+    const uint32_t *rkeys; const uint32_t *rvals; const int32_t *heads; const int32_t *n_heads; int n_pairs;
+    int n_items;
+};
+
+__global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
+    extern __shared__ __align__(16) float s_vecs[];  // [D] point p, [D] current p*
+    float *s_p = s_vecs, *s_star = s_vecs + a.D;
+    __shared__ uint32_t s_id[PR_CMAX];
+    __shared__ float s_d[PR_CMAX];
+    __shared__ u64 s_key[PR_CMAX];
+    __shared__ uint32_t s_sid[PR_CMAX];
+    __shared__ float s_sd[PR_CMAX];
+    __shared__ unsigned char s_flag[PR_CMAX];  // bit0 known distance, bit1 duplicate; later: alive
+    __shared__ uint32_t s_sel[128];
+    __shared__ int s_n, s_nu, s_nalive;
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int D = a.D, R = a.R, RS = a.stride;
+    const int n_items = a.mode == 0 ? a.n_items : *a.n_heads;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        __syncthreads();
+        // ---- gather candidates -----------------------------------------------------------------------
+        uint32_t node;
+        int n_old = 0;
+        if (a.mode == 0) {
+            node = (uint32_t)a.nodes[item];
+            const int ll = a.list_len[item];
+            const int dg = a.deg[node];
+            for (int i = tid; i < ll && i < PR_CMAX; i += nt) {
+                s_id[i] = (uint32_t)a.list_ids[(size_t)item * a.L + i];
+                s_d[i] = a.list_dist[(size_t)item * a.L + i];
+                s_flag[i] = 1;
+            }
+            for (int i = tid; i < dg && ll + i < PR_CMAX; i += nt) {
+                s_id[ll + i] = a.adj[(size_t)node * RS + i];
+                s_flag[ll + i] = 0;
+            }
+            if (tid == 0) s_n = min(ll + dg, PR_CMAX);
+        } else {
+            const int h0 = a.heads[item];
+            node = a.rkeys[h0];
+            const int dg = a.deg[node];
+            n_old = dg;
+            for (int i = tid; i < dg; i += nt) { s_id[i] = a.adj[(size_t)node * RS + i]; s_flag[i] = 0; }
+            // incoming run: pairs h0.. while the key stays the same
+            if (tid == 0) {
+                int m = dg;
+                for (int i = h0; i < a.n_pairs && a.rkeys[i] == node && m < PR_CMAX; ++i) { s_id[m] = a.rvals[i]; s_flag[m] = 0; ++m; }
+                s_n = m;
+            }
+        }
+        __syncthreads();
+        const int n = s_n;
+        // duplicates (keep the first occurrence) and self
+        for (int i = tid; i < n; i += nt) {
+            uint32_t id = s_id[i];
+            bool dup = (id == node);
+            for (int j = 0; j < i && !dup; ++j) dup = (s_id[j] == id);
+            if (dup) s_flag[i] |= 2;
+        }
+        __syncthreads();
+        if (a.mode == 1) {
+            // room left: append the new ids in order, no distances needed
+            int nu = 0;
+            for (int i = 0; i < n; ++i) nu += (s_flag[i] & 2) ? 0 : 1;   // n is small; every thread counts (uniform)
+            if (nu <= R) {
+                if (tid == 0) {
+                    int m = n_old;
+                    for (int i = n_old; i < n; ++i)
+                        if (!(s_flag[i] & 2)) a.adj[(size_t)node * RS + m++] = s_id[i];
+                    a.deg[node] = m;
+                }
+                continue;
+            }
+        }
+        // ---- distances to p ------------------------------------------------------------------------------
+        for (int i = tid; i < D; i += nt) s_p[i] = __ldg(a.X + (size_t)node * D + i);
+        __syncthreads();
+        for (int i = wid; i < n; i += nw) {
+            if (s_flag[i] & 3) continue;  // known or duplicate
+            float d = warp_l2sq(a.X + (size_t)s_id[i] * D, s_p, D, lane);
+            if (lane == 0) s_d[i] = d;
+        }
+        __syncthreads();
+        // ---- sort by (d, id): rank counting ----------------------------------------------------------------
+        for (int i = tid; i < n; i += nt) s_key[i] = (s_flag[i] & 2) ? DR_KEY_MAX : make_key(s_d[i], s_id[i]);
+        if (tid == 0) s_nu = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+            u64 key = s_key[i];
+            if (key == DR_KEY_MAX) continue;
+            int pos = 0;
+            for (int j = 0; j < n; ++j) pos += (s_key[j] < key) ? 1 : 0;
+            s_sid[pos] = s_id[i];
+            s_sd[pos] = s_d[i];
+            atomicAdd(&s_nu, 1);
+        }
+        __syncthreads();
+        const int nu = s_nu;
+        for (int i = tid; i < nu; i += nt) s_flag[i] = 1;  // alive
+        if (tid == 0) s_nalive = nu;
+        __syncthreads();
+        // ---- greedy alpha-prune ---------------------------------------------------------------------------
+        int cnt = 0;
+        for (int i = 0; i < nu && cnt < R; ++i) {
+            if (!s_flag[i]) continue;  // uniform: flags only change between barriers
+            if (tid == 0) s_sel[cnt] = s_sid[i];
+            ++cnt;
+            if (cnt == R) break;
+            if (s_nalive <= cnt) continue;  // everything still alive is already selected or will be without tests
+            for (int t = tid; t < D; t += nt) s_star[t] = __ldg(a.X + (size_t)s_sid[i] * D + t);
+            __syncthreads();
+            for (int j = i + 1 + wid; j < nu; j += nw) {
+                if (!s_flag[j]) continue;
+                float d = warp_l2sq(a.X + (size_t)s_sid[j] * D, s_star, D, lane);
+                if (lane == 0 && __fmul_rn(a.alpha, d) <= s_sd[j]) { s_flag[j] = 0; atomicSub(&s_nalive, 1); }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        for (int t = tid; t < cnt; t += nt) a.adj[(size_t)node * RS + t] = s_sel[t];
+        if (tid == 0) a.deg[node] = cnt;
+    }
+}
+
+// (target, source) pairs of the batch's new out-rows; unused slots get the sentinel key
+__global__ void emit_pairs_kernel(const int32_t *__restrict__ nodes, int n_items, const uint32_t *__restrict__ adj,
+                                  const int32_t *__restrict__ deg, int R, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items * R) return;
+    int item = t / R, j = t - item * R;
+    uint32_t node = (uint32_t)nodes[item];
+    bool ok = j < deg[node];
+    keys[t] = ok ? adj[(size_t)node * R + j] : DR_EMPTY;
+    vals[t] = node;
+}
+
+__global__ void heads_kernel(const uint32_t *__restrict__ keys, int n, int32_t *__restrict__ heads, int32_t *__restrict__ n_heads) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = keys[i];
+    if (k == DR_EMPTY) return;
+    if (i == 0 || keys[i - 1] != k) heads[atomicAdd(n_heads, 1)] = i;
+}
+
+__global__ void finalize_rows_kernel(uint32_t *__restrict__ adj, const int32_t *__restrict__ deg, long long N, int R) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * R) return;
+    long long i = t / R;
+    int j = (int)(t - i * R);
+    if (j >= deg[i]) adj[t] = 0u;  // DiskANNPersist.save_index pads short rows with 0 (diskann_persist.py:23)
+}
+
+struct BuildBufs {
+    int32_t *sigma = nullptr, *list_ids = nullptr, *list_len = nullptr, *heads = nullptr, *n_heads = nullptr, *topk = nullptr;
+    float *list_dist = nullptr;
+    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
+    void *cub_tmp = nullptr;
+    ~BuildBufs() {
+        cudaFree(sigma); cudaFree(list_ids); cudaFree(list_len); cudaFree(heads); cudaFree(n_heads); cudaFree(topk);
+        cudaFree(list_dist); cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(cub_tmp);
+    }
+};
+
 int launch_vamana_build(const float *d_X, int64_t N, int D, int R, int L, float alpha, int64_t medoid, uint64_t seed,
-                        uint32_t *d_out_adj, int32_t *d_out_deg, int device, cudaStream_t s) {
-    dr_set_error("dr_vamana_build: not implemented yet");
-    return 4;
+                        uint32_t *d_adj, int32_t *d_deg, int device, cudaStream_t s) {
+    DR_CHECK(N >= 1 && D >= 1, "dr_vamana_build: bad shape");
+    DR_CHECK(R >= 1 && R <= 128, "dr_vamana_build: R must be in 1..128 (got %d)", R);
+    DR_CHECK(L >= 1 && L <= 512 && L + R <= PR_CMAX, "dr_vamana_build: need L + R <= %d (L=%d R=%d)", PR_CMAX, L, R);
+    DR_CHECK(medoid >= 0 && medoid < N, "dr_vamana_build: medoid out of range");
+    DR_CHECK(N < (1ll << 31), "dr_vamana_build: N must be < 2^31");
+
+    // a temporary index view over the graph under construction (owns only its scratch)
+    dr_index g;
+    g.device = device; g.N = N; g.D = D; g.R = R; g.M = 0; g.medoid = medoid; g.owns = false;
+    g.d_vec = const_cast<float *>(d_X); g.d_adj = d_adj; g.d_deg = d_deg;
+    cudaDeviceProp prop;
+    DR_CUDA(cudaGetDeviceProperties(&prop, device));
+    g.sms = prop.multiProcessorCount; g.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    struct Guard { dr_index *g; ~Guard() { cudaFree(g->d_counter); cudaFree(g->d_ovf); cudaFree(g->d_lut); cudaFree(g->d_io); } } guard{&g};
+
+    int64_t maxb = N / 50;
+    if (maxb > 16384) maxb = 16384;
+    if (maxb < 1) maxb = 1;
+
+    BuildBufs b;
+    DR_CUDA(cudaMalloc(&b.sigma, (size_t)N * 4));
+    DR_CUDA(cudaMalloc(&b.list_ids, (size_t)maxb * L * 4));
+    DR_CUDA(cudaMalloc(&b.list_dist, (size_t)maxb * L * 4));
+    DR_CUDA(cudaMalloc(&b.list_len, (size_t)maxb * 4));
+    DR_CUDA(cudaMalloc(&b.topk, (size_t)maxb * 4));
+    const int max_pairs = (int)(maxb * R);
+    DR_CUDA(cudaMalloc(&b.keys, (size_t)max_pairs * 4));
+    DR_CUDA(cudaMalloc(&b.vals, (size_t)max_pairs * 4));
+    DR_CUDA(cudaMalloc(&b.keys2, (size_t)max_pairs * 4));
+    DR_CUDA(cudaMalloc(&b.vals2, (size_t)max_pairs * 4));
+    DR_CUDA(cudaMalloc(&b.heads, (size_t)max_pairs * 4));
+    DR_CUDA(cudaMalloc(&b.n_heads, 4));
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, b.keys, b.keys2, b.vals, b.vals2, max_pairs, 0, 32, s);
+    DR_CUDA(cudaMalloc(&b.cub_tmp, cub_bytes));
+
+    DR_CUDA(cudaMemsetAsync(d_deg, 0, (size_t)N * 4, s));
+    DR_CUDA(cudaMemsetAsync(d_adj, 0, (size_t)N * R * 4, s));
+
+    dr_search_params sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.k = 1; sp.L = L; sp.W = 4; sp.dist = DR_DIST_EXACT; sp.rerank = 0;
+
+    const size_t prune_smem = (size_t)2 * D * 4;
+    DR_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prune_smem));
+    int pocc = 0;
+    DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, prune_kernel, PR_THREADS, prune_smem));
+    DR_CHECK(pocc >= 1, "dr_vamana_build: D=%d too large for the prune kernel", D);
+    const int prune_grid_max = g.sms * pocc;
+
+    std::mt19937_64 rng(seed);
+    std::vector<int32_t> sigma(N);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t i = 0; i < N; ++i) sigma[i] = (int32_t)i;
+        std::shuffle(sigma.begin(), sigma.end(), rng);
+        DR_CUDA(cudaMemcpyAsync(b.sigma, sigma.data(), (size_t)N * 4, cudaMemcpyHostToDevice, s));
+        DR_CUDA(cudaStreamSynchronize(s));  // sigma is reused by the next pass
+        const float a_pass = pass == 0 ? 1.0f : alpha;
+        int64_t start = 0;
+        while (start < N) {
+            int64_t bs = (pass == 0) ? std::max<int64_t>(1, std::min<int64_t>(start, maxb)) : maxb;
+            if (bs > N - start) bs = N - start;
+            const int32_t *nodes = b.sigma + start;
+            // 1. search
+            if (launch_search(&g, d_X, bs, &sp, nullptr, b.topk, nullptr, nullptr, nullptr, b.list_ids, b.list_dist, b.list_len,
+                              nullptr, 0, nullptr, s, nodes)) return 1;
+            // 2. prune the batch points
+            PruneArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            pa.X = d_X; pa.D = D; pa.adj = d_adj; pa.deg = d_deg; pa.R = R; pa.stride = R; pa.alpha = a_pass;
+            pa.mode = 0; pa.nodes = nodes; pa.list_ids = b.list_ids; pa.list_dist = b.list_dist; pa.list_len = b.list_len; pa.L = L;
+            pa.n_items = (int)bs;
+            prune_kernel<<<(int)std::min<int64_t>(bs, prune_grid_max), PR_THREADS, prune_smem, s>>>(pa);
+            DR_LAUNCHED();
+            // 3. reverse edges
+            const int np = (int)(bs * R);
+            emit_pairs_kernel<<<(np + 255) / 256, 256, 0, s>>>(nodes, (int)bs, d_adj, d_deg, R, b.keys, b.vals);
+            DR_LAUNCHED();
+            size_t tmp = cub_bytes;
+            cub::DeviceRadixSort::SortPairs(b.cub_tmp, tmp, b.keys, b.keys2, b.vals, b.vals2, np, 0, 32, s);
+            g_launches.fetch_add(1);
+            DR_CUDA(cudaMemsetAsync(b.n_heads, 0, 4, s));
+            heads_kernel<<<(np + 255) / 256, 256, 0, s>>>(b.keys2, np, b.heads, b.n_heads);
+            DR_LAUNCHED();
+            PruneArgs pr = pa;
+            pr.mode = 1; pr.rkeys = b.keys2; pr.rvals = b.vals2; pr.heads = b.heads; pr.n_heads = b.n_heads; pr.n_pairs = np;
+            prune_kernel<<<(int)std::min<int64_t>(np, prune_grid_max), PR_THREADS, prune_smem, s>>>(pr);
+            DR_LAUNCHED();
+            start += bs;
+        }
+    }
+    const long long tot = (long long)N * R;
+    finalize_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_adj, d_deg, N, R);
+    DR_LAUNCHED();
+    DR_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// RobustPrune of one point against an explicit candidate set (robust_prune_cython, cython_utils.pyx:124-167, and
+// the cdef version :435-492).  d_X holds the n candidate rows followed by the point itself (row n); candidate
+// "ids" inside the kernel are the local row numbers, so the caller passes candidates in ascending real-id order
+// to keep the (distance, id) tie order.  d_sel receives the selected local rows, *d_cnt their number.
+int launch_prune_one(const float *d_X, int n, int D, float alpha, int R, uint32_t *d_row, int32_t *d_deg, cudaStream_t s) {
+    DR_CHECK(n >= 0 && n <= PR_CMAX, "dr_robust_prune: at most %d candidates (got %d)", PR_CMAX, n);
+    DR_CHECK(R >= 1 && R <= 128, "dr_robust_prune: R must be in 1..128");
+    // a 1-node "graph": node id n, whose current row lists the candidates 0..n-1
+    static int32_t *d_zero = nullptr;
+    PruneArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.X = d_X; pa.D = D; pa.adj = d_row - (size_t)n * (n > R ? n : R); pa.deg = d_deg - n;  // row/deg of node n land on d_row/d_deg
+    pa.R = R; pa.stride = (n > R ? n : R); pa.alpha = alpha; pa.mode = 0;
+    if (!d_zero) { DR_CUDA(cudaMalloc(&d_zero, 8)); DR_CUDA(cudaMemset(d_zero, 0, 8)); }
+    int32_t *d_node = nullptr;
+    DR_CUDA(cudaMalloc(&d_node, 4));
+    DR_CUDA(cudaMemcpyAsync(d_node, &n, 4, cudaMemcpyHostToDevice, s));
+    pa.nodes = d_node; pa.list_ids = d_zero; pa.list_dist = (const float *)d_zero; pa.list_len = d_zero; pa.L = 1; pa.n_items = 1;
+    const size_t smem = (size_t)2 * D * 4;
+    DR_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prune_kernel<<<1, PR_THREADS, smem, s>>>(pa);
+    DR_LAUNCHED();
+    DR_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_node);
+    return 0;
 }

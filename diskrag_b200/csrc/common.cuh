@@ -49,6 +49,8 @@ struct dr_index {
     bool owns = true;
     float *d_vec = nullptr;       // [N, D]
     uint32_t *d_adj = nullptr;    // [N, R] 0-padded, stored order
+    int32_t *d_deg = nullptr;     // optional true degrees (only while a graph is being built)
+    uint8_t *d_deleted = nullptr; // optional lazy-delete mask (vamana_graph.py:116-125): such nodes are never visited
     uint8_t *d_codes = nullptr;   // [N, M]
     float *d_codebook = nullptr;  // [M, 256, ds]
     // scratch (grown on demand, reused across calls)
@@ -68,7 +70,8 @@ int dr_scratch(void **ptr, size_t *cur, size_t need);  // grow-only device scrat
 int launch_lut_build(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, float *d_out, cudaStream_t s);
 int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, const float *d_lut,
                   int32_t *ids, float *dist, int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist,
-                  int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s);
+                  int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s,
+                  const int32_t *qmap = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // device side

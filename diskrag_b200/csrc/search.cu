@@ -22,6 +22,9 @@
 
 struct SearchArgs {
     const float *vec; const uint32_t *adj; const uint8_t *codes;
+    const int32_t *deg;   // optional true row lengths (graph under construction); NULL = rows are R long, 0-padded
+    const uint8_t *deleted;  // optional lazy-delete mask: masked ids are skipped exactly like the reference's is_deleted test
+    const int32_t *qmap;  // optional: query b is row qmap[b] of Q (build: queries are dataset points)
     const float *Q; const float *lut;
     long long N; int D, R, M;
     long long B; int k, L, W;
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
 
         // ---- stage the query, its ADC table, and clear the visited table --------------------------
         {
-            const float *qg = a.Q + (size_t)b * D;
+            const float *qg = a.Q + (size_t)(a.qmap ? a.qmap[b] : b) * D;
             for (int i = tid; i < D; i += nt) s_q[i] = __ldg(qg + i);
             if (pq) {
                 const float4 *src = reinterpret_cast<const float4 *>(a.lut + (size_t)b * M * 256);
@@ -251,10 +254,12 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
             // (2) adjacency rows -> first-seen neighbours, in stored order (one warp per expanded node)
             for (int s = wid; s < ns; s += nw) {
                 const uint32_t *row = a.adj + (size_t)s_sel[s] * R;
-                for (int j0 = 0; j0 < R; j0 += 32) {
+                const int len = a.deg ? a.deg[s_sel[s]] : R;
+                for (int j0 = 0; j0 < len; j0 += 32) {
                     int j = j0 + lane;
-                    uint32_t nb = (j < R) ? __ldg(row + j) : DR_EMPTY;
-                    bool valid = (j < R) && ((long long)nb < a.N);
+                    uint32_t nb = (j < len) ? row[j] : DR_EMPTY;
+                    bool valid = (j < len) && ((long long)nb < a.N);
+                    if (valid && a.deleted) valid = a.deleted[nb] == 0;
                     unsigned peers = __match_any_sync(DR_FULL, nb);
                     bool leader = (__ffs(peers) - 1) == lane;  // 0-padding repeats an id inside a row
                     bool isnew = false;
@@ -409,7 +414,8 @@ static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, const float *d_lut,
                   int32_t *ids, float *dist, int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist,
-                  int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s) {
+                  int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s,
+                  const int32_t *qmap) {
     DR_CHECK(p->k >= 1 && p->L >= 1 && p->L <= 512 && p->k <= p->L, "dr_search: need 1 <= k <= L <= 512 (k=%d L=%d)", p->k, p->L);
     DR_CHECK(p->W >= 1 && p->W <= 32, "dr_search: W must be in 1..32 (got %d)", p->W);
     const bool pq = p->dist == DR_DIST_PQ;
@@ -421,6 +427,8 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
     SearchArgs a;
     memset(&a, 0, sizeof(a));
     a.vec = h->d_vec; a.adj = h->d_adj; a.codes = h->d_codes;
+    a.deg = h->d_deg;
+    a.deleted = h->d_deleted;
     a.N = h->N; a.D = h->D; a.R = h->R; a.M = h->M;
     a.k = p->k; a.L = p->L; a.W = p->W;
     a.dist = p->dist; a.adc_tree = (pq && p->adc_order == DR_ADC_TREE) ? 1 : 0;
@@ -506,11 +514,12 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
         if (pq) {
             if (d_lut) lut_c = d_lut + (size_t)c0 * h->M * 256;
             else {
+                DR_CHECK(!qmap, "dr_search: qmap with an internal LUT is not supported");
                 if (launch_lut_build(h->d_codebook, d_Q + (size_t)c0 * h->D, cb, h->D, h->M, h->d_lut, s)) return 1;
                 lut_c = h->d_lut;
             }
         }
-        a.Q = d_Q + (size_t)c0 * h->D; a.lut = lut_c; a.B = cb;
+        a.Q = qmap ? d_Q : d_Q + (size_t)c0 * h->D; a.qmap = qmap ? qmap + c0 : nullptr; a.lut = lut_c; a.B = cb;
         a.out_ids = ids + (size_t)c0 * p->k;
         a.out_dist = dist ? dist + (size_t)c0 * p->k : nullptr;
         a.out_hops = hops ? hops + c0 : nullptr;

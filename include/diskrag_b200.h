@@ -82,6 +82,11 @@ int dr_index_create_dev(const float *d_vec, const uint32_t *d_adj, const uint8_t
                         int device, dr_index **out);
 int dr_index_destroy(dr_index *h);
 int dr_index_info(const dr_index *h, int64_t *N, int32_t *D, int32_t *R, int32_t *M, int64_t *medoid, int *device);
+/* lazy deletes (VamanaGraphWithPQ.delete_node, vamana_graph.py:116-125; greedy_search_cython skips is_deleted
+ * nodes, cython_utils.pyx:109): mask u8[N] on the host, non-zero = deleted; NULL clears it. */
+int dr_index_set_deleted(dr_index *h, const uint8_t *mask);
+/* change the entry point of the search (the reference passes start_idx per call) */
+int dr_index_set_start(dr_index *h, int64_t start);
 /* write the index back as an index.dat image (host buffer of N*4*(D+R) bytes) */
 int dr_index_export_records(const dr_index *h, void *records);
 
@@ -159,6 +164,11 @@ int dr_vamana_build(const float *X, int64_t N, int32_t D, int32_t R, int32_t L, 
                     uint64_t seed, uint32_t *out_adj, int32_t *out_deg, int device);
 int dr_vamana_build_dev(const float *d_X, int64_t N, int32_t D, int32_t R, int32_t L, float alpha, int64_t medoid,
                         uint64_t seed, uint32_t *d_out_adj, int32_t *d_out_deg, int device, void *stream);
+
+/* dr_robust_prune replaces robust_prune_cython (cython_utils.pyx:124-167) for one point: p f32[D], cand f32[n,D]
+ *   given in ascending id order (n <= 320) -> out_sel i32[<=R] positions into cand in selection order, *out_n. */
+int dr_robust_prune(const float *p, const float *cand, int32_t n, int32_t D, float alpha, int32_t R, int32_t *out_sel,
+                    int32_t *out_n, int device);
 
 /* ---- multi-GPU merge ------------------------------------------------------------------------------
  * k-way merge of per-shard top-k lists (nothing in the reference): ids i32[G,B,k] (global
