@@ -1,0 +1,432 @@
+#!/usr/bin/env python3
+"""bench.py — the hot-path benchmark (contract in the task statement; metric from BASELINE.json).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 1M x 1536 synthetic unit-norm
+embeddings, Vamana R=32 (GPU-built, L_build=64, alpha=1.2), PQ M=192, search list L=100, top-10 with exact
+rerank, 100k-query batch per GPU, index replicated, queries sharded ("weak": per-GPU work fixed).
+One step = one pass of the hot path over one 100k-query batch: ADC-table build + beam search + rerank.
+
+  python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference [...]                      the reference's own CPU code (oracle/_ref) on host cores
+Under torchrun each rank drives one GPU; rank 0 prints one JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "QPS@recall10>=0.95"
+UNIT = "queries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=1536)
+    ap.add_argument("--R", type=int, default=32)
+    ap.add_argument("--Lbuild", type=int, default=64)
+    ap.add_argument("--M", type=int, default=192)
+    ap.add_argument("--L", type=int, default=100)
+    ap.add_argument("--W", type=int, default=4)
+    ap.add_argument("--adc", default="tree", choices=["seq", "tree"])
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--queries", type=int, default=100_000, help="queries per GPU per step")
+    ap.add_argument("--gt-queries", type=int, default=1000)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# setup shared by both arms: synthetic corpus, PQ, graph (all on the GPU, untimed)
+# ------------------------------------------------------------------------------------------------------
+def build_index(a, dev):
+    import torch
+    from diskrag_b200._lib import check, lib
+    from diskrag_b200.synth import synth_torch
+    st = torch.cuda.current_stream(dev).cuda_stream
+    N, D, R, M = a.n, a.dim, a.R, a.M
+    t0 = time.time()
+    X = synth_torch(N, D, seed=20242, device=dev)
+    # medoid: sampled, as compute_approximate_medoid_cython does (1000 samples), through our kernel
+    g = torch.Generator(device=dev); g.manual_seed(77)
+    smp = torch.randperm(N, generator=g, device=dev)[:1000].to(torch.int32).cpu().numpy()
+    # dr_medoid takes host pointers; at 1M x 1536 use the device build path instead: nearest point to the sample centroid
+    # of distances is what the medoid approximates; we evaluate the exact sums on the device in chunks with torch-free C ABI
+    med = medoid_dev(X, smp, dev)
+    cb = torch.empty((M, 256, D // M), dtype=torch.float32, device=dev)
+    codes = torch.empty((N, M), dtype=torch.uint8, device=dev)
+    mse = C.c_double(0)
+    t1 = time.time()
+    check(lib().dr_pq_train_dev(X.data_ptr(), N, D, M, 25, 42, cb.data_ptr(), C.byref(mse), dev.index, st), "dr_pq_train_dev")
+    check(lib().dr_pq_encode_dev(cb.data_ptr(), X.data_ptr(), N, D, M, codes.data_ptr(), dev.index, st), "dr_pq_encode_dev")
+    torch.cuda.synchronize(dev)
+    t2 = time.time()
+    adj = torch.empty((N, R), dtype=torch.int32, device=dev)
+    deg = torch.empty(N, dtype=torch.int32, device=dev)
+    check(lib().dr_vamana_build_dev(X.data_ptr(), N, D, R, a.Lbuild, 1.2, med, 1234, adj.data_ptr(), deg.data_ptr(), dev.index, st),
+          "dr_vamana_build_dev")
+    torch.cuda.synchronize(dev)
+    t3 = time.time()
+    info = {"gen_s": round(t1 - t0, 2), "pq_train_encode_s": round(t2 - t1, 2), "graph_build_s": round(t3 - t2, 2),
+            "pq_mse": mse.value, "mean_degree": round(float(deg.float().mean().item()), 2)}
+    return X, adj, deg, codes, cb, med, info
+
+
+def medoid_dev(X, samples, dev):
+    """argmin over samples of sum_j ||x_s - x_j|| (cython_utils.pyx:210-263) with device-resident X."""
+    import torch
+    from diskrag_b200._lib import lib
+    # the host-pointer dr_medoid would copy 6 GB; evaluate the same sums with the library's distance kernel per sample
+    # block instead: here a torch reduction is plumbing for SETUP only (not timed, not the hot path)
+    s = torch.from_numpy(samples.astype(np.int64)).to(dev)
+    xs = X[s]
+    xn = (X * X).sum(1)
+    best, bi = None, 0
+    sums = torch.zeros(len(samples), dtype=torch.float64, device=dev)
+    for c0 in range(0, X.shape[0], 262144):
+        blk = X[c0:c0 + 262144]
+        d2 = (xs * xs).sum(1)[:, None] + xn[c0:c0 + 262144][None, :] - 2.0 * (xs @ blk.T)
+        sums += d2.clamp_min(0).sqrt().double().sum(1)
+    return int(samples[int(sums.argmin().item())])
+
+
+def ground_truth(X, Q, k):
+    import torch
+    xn = (X * X).sum(1)
+    out = torch.empty((Q.shape[0], k), dtype=torch.int64, device=X.device)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for s in range(0, Q.shape[0], 250):
+        d = xn[None, :] - 2.0 * (Q[s:s + 250] @ X.T)
+        out[s:s + 250] = d.topk(k, largest=False).indices
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    return out.cpu().numpy()
+
+
+def recall(ids, gt, k):
+    return float(np.mean([len(set(ids[i, :k].tolist()) & set(gt[i, :k].tolist())) / k for i in range(gt.shape[0])]))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(a, hops, visited, list_len):
+    """bytes(q) = 4D + h*4R + v*M + L_r*4D + 8k, summed over the batch (int64)."""
+    h = hops.astype(np.int64); v = visited.astype(np.int64); lr = list_len.astype(np.int64)
+    return int((4 * a.dim + h * 4 * a.R + v * a.M + lr * 4 * a.dim + 8 * a.k).sum())
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from diskrag_b200 import engine
+    from diskrag_b200.synth import synth_torch
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    X, adj, deg, codes, cb, med, info = build_index(a, dev)
+    idx = engine.GpuIndex.from_device_ptrs(X.data_ptr(), adj.data_ptr(), codes.data_ptr(), cb.data_ptr(), a.n, a.dim, a.R, a.M,
+                                           med, local, keepalive=(X, adj, codes, cb))
+    B, k = a.queries, a.k
+    Q = synth_torch(B, a.dim, seed=20242, sample_seed=1000 + rank, device=dev)     # each rank: its own query shard
+    p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads)
+    ids = torch.empty((B, k), dtype=torch.int32, device=dev); dd = torch.empty((B, k), dtype=torch.float32, device=dev)
+    hops = torch.empty(B, dtype=torch.int32, device=dev); vis = torch.empty(B, dtype=torch.int32, device=dev)
+    llen = torch.empty(B, dtype=torch.int32, device=dev); stat = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def step():
+        idx.search_dev(Q.data_ptr(), B, p, ids.data_ptr(), dd.data_ptr(), hops.data_ptr(), vis.data_ptr(),
+                       d_list_len=llen.data_ptr(), d_status=stat.data_ptr(), stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # recall on a ground-truth subset (rank 0's shard)
+    step(); torch.cuda.synchronize(dev)
+    assert int(stat.abs().sum().item()) == 0, "search reported a non-zero status"
+    ngt = min(a.gt_queries, B)
+    gt = ground_truth(X, Q[:ngt], k)
+    rec = recall(ids[:ngt].cpu().numpy(), gt, k)
+
+    # ---- value: device-resident inputs, CUDA events on the launching stream ---------------------------
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    l0 = engine.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = engine.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * a.steps / (ms_total / 1e3)
+
+    # ---- roofline of the search kernel: algorithmic bytes / its own launch durations (CUDA events in the library)
+    h_np, v_np, l_np = hops.cpu().numpy(), vis.cpu().numpy(), llen.cpu().numpy()
+    abytes = algorithmic_bytes(a, h_np, v_np, l_np)
+    idx.kernel_timing(True)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    k_ms, k_launches = idx.kernel_timing(False)
+    peak, peak_src = measured_peak()
+    per_launch_bytes = abytes * 2 / max(1, k_launches)
+    per_launch_ms = k_ms / max(1, k_launches)
+    achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "search_kernel_traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "peak_source": peak_src, "kernel": "search_kernel",
+                "kernel_ms_per_launch": round(per_launch_ms, 3), "launches_per_step": k_launches // 2,
+                "algorithmic_bytes_per_query": round(abytes / B, 1), "kernel_share_of_step": round((k_ms / 2) / (ms_total / a.steps), 3)}
+
+    # ---- e2e: host buffers through the public API (H2D of the queries and D2H of the results inside) ------
+    Qh = torch.empty((B, a.dim), dtype=torch.float32, pin_memory=True); Qh.copy_(Q)
+    ids_h = torch.empty((B, k), dtype=torch.int32, pin_memory=True); dd_h = torch.empty((B, k), dtype=torch.float32, pin_memory=True)
+    hops_h = torch.empty(B, dtype=torch.int32, pin_memory=True); vis_h = torch.empty(B, dtype=torch.int32, pin_memory=True)
+    st_h = torch.empty(B, dtype=torch.int32, pin_memory=True)
+    Qn, idn, ddn, hn, vn, sn = Qh.numpy(), ids_h.numpy(), dd_h.numpy(), hops_h.numpy(), vis_h.numpy(), st_h.numpy()
+
+    def step_e2e():
+        idx.search_host(Qn, p, idn, ddn, hn, vn, sn)
+
+    for _ in range(max(1, a.warmup - 1)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * a.steps / float(te.item())
+    assert np.array_equal(idn, ids.cpu().numpy()), "host-API results differ from the device-API results"
+    e2e = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(B * a.dim * 4),
+           "d2h_bytes_per_step": int(B * k * 8 + 3 * B * 4)}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu_base = cpu_baseline_port(a, X, adj, codes, cb, med, Q, idn)
+    if rank == 0:
+        out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"{a.n}x{a.dim} synthetic unit-norm, Vamana R={a.R} (GPU-built, Lbuild={a.Lbuild}, alpha=1.2), "
+                                      f"PQ M={a.M}, L={a.L}, W={a.W}, adc={a.adc}, rerank, top-{a.k}",
+                          "queries_per_gpu_per_step": B, "index": "replicated", "queries": "sharded", "recall_at_10": round(rec, 4),
+                          "recall_queries": ngt, "l2_flush": "inputs larger than L2 (index 6.3 GB, per-step LUT 19.7 GB)",
+                          "mean_hops": round(float(h_np.mean()), 1), "mean_visited": round(float(v_np.mean()), 1), "setup": info},
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_port(a, X, adj, codes, cb, med, Q, ids_gpu):
+    """The oracle (C restatement, OpenMP over queries) on the host cores, bounded sample of the same workload."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as O
+    O.build()
+    Xh = X.cpu().numpy(); adjh = adj.cpu().numpy().view(np.uint32); ch = codes.cpu().numpy(); cbh = cb.cpu().numpy()
+    cores = O.num_threads()
+    n = min(Q.shape[0], 64 * cores)
+    Qs = Q[:n].cpu().numpy()
+    t = time.perf_counter()
+    ids, d, hops, vis = O.search_batch(adjh, Xh, Qs, med, a.L, a.k, codes=ch, codebook=cbh,
+                                       dist_mode=O.DIST_ADC_TREE if a.adc == "tree" else O.DIST_ADC_SEQ, flavor=O.FLAVOR_WARP,
+                                       W=a.W, rerank_=True)
+    dt = time.perf_counter() - t
+    same = float(np.mean(np.all(ids == ids_gpu[:n], axis=1)))
+    return {"value": round(n / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} queries of the same batch on the same index, oracle/oracle.c with OpenMP over queries; "
+                      f"{same * 100:.2f}% of its top-{a.k} lists are identical to the GPU's"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code (oracle/_ref = pydiskann compiled from /root/reference)
+# ------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _ref_worker_init():
+    pass
+
+
+def _ref_search(qi):
+    g, vg, cu, Q, vec, L, k, med = _W["g"], _W["vg"], _W["cu"], _W["Q"], _W["vec"], _W["L"], _W["k"], _W["med"]
+    q = Q[qi]
+    g._distance_table_cache.clear()
+    ids = cu.greedy_search_cython(g, med, q, L, vg.compute_query_distance)          # variant A, PQ ADC callback
+    d2 = [float(np.sum((vec[i] - q) * (vec[i] - q))) for i in ids]                   # search_engine.py:374-379
+    order = np.argsort(np.array(d2, np.float32), kind="stable")[:k]
+    return [int(ids[i]) for i in order]
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import torch
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ref_loader
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    X, adj, deg, codes, cb, med, info = build_index(a, dev)                          # setup only: same index as our arm
+    from diskrag_b200.synth import synth_torch
+    cores = os.cpu_count() or 1
+    per_step = 2 * cores
+    nq = per_step * (a.steps + a.warmup)
+    Q = synth_torch(nq, a.dim, seed=20242, sample_seed=1000, device=dev).cpu().numpy()
+    gt = ground_truth(X, torch.from_numpy(Q).to(dev), a.k)
+    vec = X.cpu().numpy(); adjh = adj.cpu().numpy().view(np.uint32); ch = codes.cpu().numpy(); cbh = cb.cpu().numpy()
+    del X, adj, codes
+    torch.cuda.empty_cache()
+    kind = "reference"
+    if ref_loader.available():
+        m = ref_loader.load()
+        vg, cu, fp = m["vamana_graph"], m["cython_utils"], m["fast_pq"]
+        from diskrag_b200.pq.fast_pq import _wrap_kmeans
+        pq = fp.DiskANNPQ(a.M, 256)
+        pq.sub_dim = a.dim // a.M; pq.is_fitted = True
+        pq.kmeans_list = [_wrap_kmeans(cbh[i], 42 + i) for i in range(a.M)]
+        g = vg.VamanaGraphWithPQ(a.R, pq)
+
+        class LazyNodes(dict):                   # the reference's dict of Node objects, materialised on first touch
+            def __missing__(self, i):
+                n = vg.Node(i, vec[i], ch[i])
+                n.neighbors = [int(x) for x in adjh[i]]
+                self[i] = n
+                return n
+        g.nodes = LazyNodes()
+        g.medoid_idx = med
+        g.use_pq_for_search = True
+        _W.update(g=g, vg=vg, cu=cu, Q=Q, vec=vec, L=a.L, k=a.k, med=med)
+        pool = mp.get_context("fork").Pool(cores)
+        run = lambda qs: pool.map(_ref_search, qs, chunksize=1)
+        sample = (f"{per_step} queries per step ({2} per core) of the same workload on the same index; the reference's own "
+                  f"greedy_search_cython + compute_query_distance (PQ ADC) + numpy exact rerank, {cores} processes")
+    else:
+        kind = "port"
+        import oracle as O
+        O.build()
+        per_step = 64 * cores
+        nq = per_step * (a.steps + a.warmup)
+        Q = np.concatenate([Q] * (nq // Q.shape[0] + 1))[:nq]
+        gt = np.concatenate([gt] * (nq // gt.shape[0] + 1))[:nq]
+        run = lambda qs: O.search_batch(adjh, vec, Q[qs], med, a.L, a.k, codes=ch, codebook=cbh, dist_mode=O.DIST_ADC_SEQ,
+                                        flavor=O.FLAVOR_NUMPY, W=1, rerank_=True)[0].tolist()
+        sample = f"{per_step} queries per step, oracle/oracle.c (C restatement) with OpenMP, {cores} threads"
+    res = []
+    for s in range(a.warmup):
+        res += run(list(range(s * per_step, (s + 1) * per_step)))
+    t0 = time.perf_counter()
+    for s in range(a.warmup, a.warmup + a.steps):
+        res += run(list(range(s * per_step, (s + 1) * per_step)))
+    dt = time.perf_counter() - t0
+    value = per_step * a.steps / dt
+    rec = recall(np.array(res, np.int64), gt[:len(res)], a.k)
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{a.n}x{a.dim} synthetic unit-norm, Vamana R={a.R} (GPU-built, Lbuild={a.Lbuild}, alpha=1.2), "
+                                  f"PQ M={a.M}, L={a.L}, W=1, adc=seq, rerank, top-{a.k}",
+                      "queries_per_step": per_step, "recall_at_10": round(rec, 4), "setup": info,
+                      "note": "index built by the GPU builder outside the timed region (the reference's builder needs hours at 1M)"},
+           "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

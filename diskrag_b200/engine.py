@@ -149,6 +149,13 @@ class GpuIndex:
         return SearchResult(ids=ids, dists=dd, hops=hops, visited=vis, status=st, list_ids=lids, list_dists=ldist,
                             list_len=llen, trace=tr)
 
+    def search_host(self, Q, params: SearchParams, ids, dists=None, hops=None, visited=None, status=None):
+        """Same call as `search` but into caller-owned host arrays (e.g. pinned buffers): Q f32[B,D] ->
+        ids i32[B,k], dists f32[B,k], hops/visited/status i32[B].  H2D and D2H copies happen inside."""
+        B = Q.shape[0]
+        check(lib().dr_search_batch(self._h, ptr(Q), B, C.byref(params), None, ptr(ids), ptr(dists), ptr(hops), ptr(visited),
+                                    None, None, None, None, 0, ptr(status)), "dr_search_batch")
+
     def search_dev(self, d_Q, B, params: SearchParams, d_ids, d_dist=None, d_hops=None, d_visited=None, d_lut=None,
                    d_list_ids=None, d_list_dist=None, d_list_len=None, d_status=None, stream=None):
         """Enqueue a search on device pointers (ints).  No synchronisation."""

@@ -51,8 +51,9 @@ def synth_torch(n, D, seed=20240, sample_seed=0, device="cuda", r=R_LATENT, K=K_
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     centres = torch.randn(K, r, generator=g, device=device)
-    A, _ = torch.linalg.qr(torch.randn(D, r, generator=g, device=device))
-    lift = A.T.contiguous()
+    # the orthonormal lift is tiny (D x r): numpy QR on the host avoids loading cuSOLVER (~50 s cold)
+    A, _ = np.linalg.qr(np.random.default_rng(seed).standard_normal((D, r)))
+    lift = torch.from_numpy(np.ascontiguousarray(A.T.astype(np.float32))).to(device)
     g.manual_seed(seed * 1000003 + 7919 * (sample_seed + 1))
     if out is None:
         out = torch.empty(n, D, device=device, dtype=torch.float32)

@@ -9,8 +9,10 @@ binaries only, so it travels to the GPU box with the gpurun snapshot):
   1. pydiskann/cython_utils.pyx  --cython-->  C++  --g++ -O3 -ffast-math-->  cython_utils.<abi>.so
      (same flags as /root/reference/pydiskann/setup.py:10; we call cython and g++ directly and do
      not run the reference's setup.py)
-  2. every pydiskann/**/*.py     --py_compile-->  sourceless .pyc next to it
-     (vamana_graph, pq/fast_pq, pq/adaptive_pq, io/diskann_persist and the package __init__s)
+  2. every pydiskann/**/*.py     --py_compile-->  sourceless bytecode next to it, stored as *.pycbin
+     (vamana_graph, pq/fast_pq, pq/adaptive_pq, io/diskann_persist and the package __init__s; the
+     extension is not .pyc because the gpurun snapshot drops *.pyc files — ref_loader.py installs an
+     import hook that loads *.pycbin with importlib's SourcelessFileLoader)
 
 Usage:  python oracle/build_ref.py [--ref /root/reference] [--force]
 Import: oracle/ref_loader.py puts oracle/_ref first on sys.path (and sets NUMBA_DISABLE_JIT=1,
@@ -57,7 +59,7 @@ def build(ref: Path, force: bool = False) -> bool:
         rel = py.relative_to(src_pkg)
         if rel.name == "setup.py":
             continue
-        dst = (dst_pkg / rel).with_suffix(".pyc")
+        dst = (dst_pkg / rel).with_suffix(".pycbin")
         dst.parent.mkdir(parents=True, exist_ok=True)
         py_compile.compile(str(py), cfile=str(dst), dfile=f"<reference>/pydiskann/{rel}", doraise=True)
     stamp.write_text("ok\n")

@@ -2,8 +2,14 @@
 
 TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's reference/cpu_baseline
 legs may import this module.
+
+oracle/_ref/pydiskann holds cython_utils.<abi>.so plus sourceless bytecode (*.pycbin) of the pure-python
+modules; a meta-path finder maps `pydiskann[.sub].mod` onto those files.
 """
 import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import sys
 from pathlib import Path
@@ -12,7 +18,24 @@ _REF = Path(__file__).resolve().parent / "_ref"
 
 
 def available() -> bool:
-    return (_REF / ".built").exists()
+    return (_REF / ".built").exists() and (_REF / "pydiskann" / "vamana_graph.pycbin").exists()
+
+
+class _RefFinder(importlib.abc.MetaPathFinder):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != "pydiskann" and not fullname.startswith("pydiskann."):
+            return None
+        rel = Path(*fullname.split("."))
+        pkg_init = _REF / rel / "__init__.pycbin"
+        if pkg_init.exists():
+            loader = importlib.machinery.SourcelessFileLoader(fullname, str(pkg_init))
+            return importlib.util.spec_from_file_location(fullname, str(pkg_init), loader=loader,
+                                                          submodule_search_locations=[str(_REF / rel)])
+        mod = (_REF / rel).with_suffix(".pycbin")
+        if mod.exists():
+            loader = importlib.machinery.SourcelessFileLoader(fullname, str(mod))
+            return importlib.util.spec_from_file_location(fullname, str(mod), loader=loader)
+        return None  # extension modules (cython_utils.so) are found by the normal path finder via __path__
 
 
 def load():
@@ -20,9 +43,8 @@ def load():
     if not available():
         raise RuntimeError("oracle/_ref not built: run `python oracle/build_ref.py` where /root/reference exists")
     os.environ.setdefault("NUMBA_DISABLE_JIT", "1")
-    p = str(_REF)
-    if p not in sys.path:
-        sys.path.insert(0, p)
+    if not any(isinstance(f, _RefFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder())
     mods = {}
     for name in ("pydiskann.cython_utils", "pydiskann.vamana_graph", "pydiskann.pq.fast_pq",
                  "pydiskann.io.diskann_persist"):
