@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--gt-queries", type=int, default=1000)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-profile", action="store_true", help="wrap one extra step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -224,6 +225,12 @@ def run_ours(a):
     # ---- value: device-resident inputs, CUDA events on the launching stream ---------------------------
     for _ in range(a.warmup):
         step()
+    if a.cuda_profile:
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
     sampler = ClockSampler(local); sampler.start()
     barrier()
     l0 = engine.launch_count()
