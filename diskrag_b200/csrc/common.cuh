@@ -133,6 +133,65 @@ __device__ __forceinline__ float warp_l2sq(const float *__restrict__ row, const 
     return warp_sum_butterfly(acc);
 }
 
+// two rows at once (twice the loads in flight per lane); each row keeps the canonical order of warp_l2sq
+__device__ __forceinline__ void warp_l2sq_x2(const float *__restrict__ rowA, const float *__restrict__ rowB,
+                                             const float *__restrict__ q, int D, int lane, float &dA, float &dB) {
+    float accA = 0.0f, accB = 0.0f;
+    if ((D & 3) == 0) {
+        int base = lane * 4;
+#pragma unroll 4
+        for (; base < D; base += 128) {
+            float4 a = ldg_f4(rowA + base);
+            float4 c = ldg_f4(rowB + base);
+            float4 b = *reinterpret_cast<const float4 *>(q + base);
+            float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y), d2 = __fsub_rn(a.z, b.z), d3 = __fsub_rn(a.w, b.w);
+            accA = __fmaf_rn(d0, d0, accA); accA = __fmaf_rn(d1, d1, accA); accA = __fmaf_rn(d2, d2, accA); accA = __fmaf_rn(d3, d3, accA);
+            float e0 = __fsub_rn(c.x, b.x), e1 = __fsub_rn(c.y, b.y), e2 = __fsub_rn(c.z, b.z), e3 = __fsub_rn(c.w, b.w);
+            accB = __fmaf_rn(e0, e0, accB); accB = __fmaf_rn(e1, e1, accB); accB = __fmaf_rn(e2, e2, accB); accB = __fmaf_rn(e3, e3, accB);
+        }
+    } else {
+        for (int i = lane; i < D; i += 32) {
+            float qq = q[i];
+            float d = __fsub_rn(__ldg(rowA + i), qq), e = __fsub_rn(__ldg(rowB + i), qq);
+            accA = __fmaf_rn(d, d, accA);
+            accB = __fmaf_rn(e, e, accB);
+        }
+    }
+    dA = warp_sum_butterfly(accA);
+    dB = warp_sum_butterfly(accB);
+}
+
+// ---- mbarrier + bulk async copy (TMA 1-D) helpers ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0, both sides 16 B aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;

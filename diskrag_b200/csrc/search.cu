@@ -72,6 +72,40 @@ __device__ __forceinline__ float adc_tree_warp(const uint8_t *__restrict__ code,
     return warp_sum_butterfly(acc);
 }
 
+// Same order, G code rows per warp at once: each lane fetches one (two) 32-bit words of every row first — all loads
+// in flight together — and the byte a lane needs (m = lane + 32 j) is pulled from its owner lane by shuffle.
+// Needs M % 4 == 0 and M <= 256.
+template <int G>
+__device__ __forceinline__ void adc_tree_group(const uint8_t *__restrict__ codes, int M, const float *__restrict__ lut,
+                                               const uint32_t (&ids)[G], int cnt, int lane, float (&out)[G]) {
+    const int words = M >> 2;
+    uint32_t w0[G], w1[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        w0[g] = 0u; w1[g] = 0u;
+        if (g < cnt) {
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M);
+            if (lane < words) w0[g] = __ldg(cw + lane);
+            if (lane + 32 < words) w1[g] = __ldg(cw + lane + 32);
+        }
+    }
+    const int nj = (M + 31) >> 5;
+    const int sh = (lane & 3) << 3;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g < cnt) {  // cnt is warp-uniform
+            float acc = 0.0f;
+            for (int j = 0; j < nj; ++j) {
+                const int src = (lane >> 2) + ((j & 3) << 3);
+                const uint32_t word = __shfl_sync(DR_FULL, (j < 4) ? w0[g] : w1[g], src);
+                const int m = lane + (j << 5);
+                if (m < M) acc = __fadd_rn(acc, lut[m * 256 + ((word >> sh) & 0xFFu)]);
+            }
+            out[g] = warp_sum_butterfly(acc);
+        }
+    }
+}
+
 __device__ __forceinline__ bool visited_insert(uint32_t nb, uint32_t *hash, uint32_t mask, bool use_ovf,
                                                uint32_t *ovf, uint32_t ovf_mask) {
     uint32_t h = hash_u32(nb) & mask;
@@ -143,6 +177,7 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
     u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_hash);  // rerank keys alias the (dead) visited table
 
     __shared__ long long s_b;
+    __shared__ __align__(8) uint64_t s_lutbar;
     __shared__ int s_n, s_nn, s_ns, s_ng, s_mvalid, s_hcount, s_ovfcount, s_useovf, s_ovfused, s_status;
 
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
@@ -154,6 +189,8 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
     uint32_t *my_ovf = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
     const bool pq = (a.dist == DR_DIST_PQ);
     const bool strict = a.strict != 0;
+    uint32_t lut_phase = 0;
+    if (tid == 0) { mbar_init(&s_lutbar, 1); fence_mbar_init(); }
 
     for (;;) {
         __syncthreads();
@@ -166,14 +203,13 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
         {
             const float *qg = a.Q + (size_t)(a.qmap ? a.qmap[b] : b) * D;
             for (int i = tid; i < D; i += nt) s_q[i] = __ldg(qg + i);
-            if (pq) {
-                const float4 *src = reinterpret_cast<const float4 *>(a.lut + (size_t)b * M * 256);
-                float4 *dst = reinterpret_cast<float4 *>(s_lut);
-                const int n4 = M * 64;
-                for (int i = tid; i < n4; i += nt) dst[i] = __ldg(src + i);
+            if (pq && tid == 0) {  // one bulk async copy (TMA engine) of the query's M x 256 table
+                mbar_expect_tx(&s_lutbar, (uint32_t)M * 1024u);
+                bulk_g2s(s_lut, a.lut + (size_t)b * M * 256, (uint32_t)M * 1024u, &s_lutbar);
             }
             for (uint32_t i = tid; i < a.hash_cap; i += nt) s_hash[i] = DR_EMPTY;
             if (tid == 0) { s_ng = 0; s_hcount = 1; s_ovfcount = 0; s_ovfused = 0; s_status = 0; }
+            if (pq) { mbar_wait(&s_lutbar, lut_phase); lut_phase ^= 1u; }
         }
         __syncthreads();
 
@@ -290,6 +326,31 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
                     s_newk[i] = ok ? key : DR_KEY_MAX;
                     if (ok) atomicAdd(&s_mvalid, 1);
                 }
+            } else if (pq && (M & 3) == 0 && M <= 256) {
+                constexpr int G = 4;
+                for (int base = wid; base < nn; base += nw * G) {
+                    uint32_t gid[G];
+                    float gd[G];
+                    int cnt = 0;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const int i = base + g * nw;
+                        gid[g] = 0u;
+                        if (i < nn) { gid[g] = s_newid[i]; cnt = g + 1; }
+                    }
+                    adc_tree_group<G>(a.codes, M, s_lut, gid, cnt, lane, gd);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            if (g < cnt) {
+                                u64 key = make_key(gd[g], gid[g]);
+                                bool ok = !full || (strict ? (key_dbits(key) < worst_db) : (key < worstk));
+                                s_newk[base + g * nw] = ok ? key : DR_KEY_MAX;
+                                if (ok) atomicAdd(&s_mvalid, 1);
+                            }
+                        }
+                    }
+                }
             } else {
                 for (int i = wid; i < nn; i += nw) {
                     uint32_t id = s_newid[i];
@@ -369,9 +430,19 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
         const int k = a.k;
         if (a.rerank) {
             // exact fp32 L2^2 of every list entry (search_engine.py:374-379), stable sort, first k
-            for (int i = wid; i < n; i += nw) {
-                float d2 = warp_l2sq(a.vec + (size_t)key_id(lst[i]) * D, s_q, D, lane);
-                if (lane == 0) s_rrk[i] = ((u64)f2ord(d2 + 0.0f) << 32) | (u64)i;
+            for (int i = wid; i < n; i += 2 * nw) {
+                const int i2 = i + nw;
+                if (i2 < n) {
+                    float dA, dB;
+                    warp_l2sq_x2(a.vec + (size_t)key_id(lst[i]) * D, a.vec + (size_t)key_id(lst[i2]) * D, s_q, D, lane, dA, dB);
+                    if (lane == 0) {
+                        s_rrk[i] = ((u64)f2ord(dA + 0.0f) << 32) | (u64)i;
+                        s_rrk[i2] = ((u64)f2ord(dB + 0.0f) << 32) | (u64)i2;
+                    }
+                } else {
+                    float d2 = warp_l2sq(a.vec + (size_t)key_id(lst[i]) * D, s_q, D, lane);
+                    if (lane == 0) s_rrk[i] = ((u64)f2ord(d2 + 0.0f) << 32) | (u64)i;
+                }
             }
             __syncthreads();
             for (int i = tid; i < n; i += nt) {
@@ -471,7 +542,8 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
     a.hash_cap = hc;
     const int smem = fixed + (int)hc * 4;
 
-    int nt = p->threads > 0 ? p->threads : 256;
+    // one CTA per SM when the table is big: give it 16 warps; small tables keep 8 warps and co-reside
+    int nt = p->threads > 0 ? p->threads : (smem > h->smem_optin / 2 ? 512 : 256);
     DR_CHECK(nt % 32 == 0 && nt >= 32 && nt <= 512, "dr_search: threads must be a multiple of 32 in 32..512");
 
     DR_CUDA(cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
