@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--L", type=int, default=100)
     ap.add_argument("--W", type=int, default=4)
     ap.add_argument("--adc", default="tree", choices=["seq", "tree"])
+    ap.add_argument("--lut", default="u8", choices=["f32", "u8"])
+    ap.add_argument("--prefetch", type=int, default=1)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries", type=int, default=100_000, help="queries per GPU per step")
     ap.add_argument("--gt-queries", type=int, default=1000)
@@ -200,7 +202,8 @@ def run_ours(a):
                                            med, local, keepalive=(X, adj, codes, cb))
     B, k = a.queries, a.k
     Q = synth_torch(B, a.dim, seed=20242, sample_seed=1000 + rank, device=dev)     # each rank: its own query shard
-    p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads)
+    p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut,
+                           prefetch=bool(a.prefetch))
     ids = torch.empty((B, k), dtype=torch.int32, device=dev); dd = torch.empty((B, k), dtype=torch.float32, device=dev)
     hops = torch.empty(B, dtype=torch.int32, device=dev); vis = torch.empty(B, dtype=torch.int32, device=dev)
     llen = torch.empty(B, dtype=torch.int32, device=dev); stat = torch.empty(B, dtype=torch.int32, device=dev)
@@ -268,7 +271,7 @@ def run_ours(a):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "kernel": "search_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "search_fast_kernel" if a.lut == "u8" else "search_kernel",
                 "kernel_ms_per_launch": round(per_launch_ms, 3), "launches_per_step": k_launches // 2,
                 "algorithmic_bytes_per_query": round(abytes / B, 1), "kernel_share_of_step": round((k_ms / 2) / (ms_total / a.steps), 3)}
 
@@ -305,7 +308,7 @@ def run_ours(a):
                "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"{a.n}x{a.dim} synthetic unit-norm, Vamana R={a.R} (GPU-built, Lbuild={a.Lbuild}, alpha=1.2), "
-                                      f"PQ M={a.M}, L={a.L}, W={a.W}, adc={a.adc}, rerank, top-{a.k}",
+                                      f"PQ M={a.M}, L={a.L}, W={a.W}, adc={a.adc}, table={a.lut}, rerank, top-{a.k}",
                           "queries_per_gpu_per_step": B, "index": "replicated", "queries": "sharded", "recall_at_10": round(rec, 4),
                           "recall_queries": ngt, "l2_flush": "inputs larger than L2 (index 6.3 GB, per-step LUT 19.7 GB)",
                           "mean_hops": round(float(h_np.mean()), 1), "mean_visited": round(float(v_np.mean()), 1), "setup": info},
@@ -326,7 +329,8 @@ def cpu_baseline_port(a, X, adj, codes, cb, med, Q, ids_gpu):
     Qs = Q[:n].cpu().numpy()
     t = time.perf_counter()
     ids, d, hops, vis = O.search_batch(adjh, Xh, Qs, med, a.L, a.k, codes=ch, codebook=cbh,
-                                       dist_mode=O.DIST_ADC_TREE if a.adc == "tree" else O.DIST_ADC_SEQ, flavor=O.FLAVOR_WARP,
+                                       dist_mode=O.DIST_ADC_U8 if a.lut == "u8" else (O.DIST_ADC_TREE if a.adc == "tree" else O.DIST_ADC_SEQ),
+                                       flavor=O.FLAVOR_WARP,
                                        W=a.W, rerank_=True)
     dt = time.perf_counter() - t
     same = float(np.mean(np.all(ids == ids_gpu[:n], axis=1)))

@@ -72,11 +72,17 @@ __device__ __forceinline__ float np_pairwise_ct(const float (&cr)[DS], const flo
 }
 
 // grid (M, ceil(B/QT)); 256 threads: thread c owns centroid c of subspace m and walks the query tile.
+// MODE 0: write the fp32 table  out[b][m][c]                                   (reference format)
+// MODE 1: per (b, m) min over c -> mn[b][m]; per b max range -> range_bits[b]  (first pass of the u8 table)
+// MODE 2: q = min(255, rint((T - mn[b][m]) / scale[b])) -> out8[b][m][c]       (second pass of the u8 table)
 #define LUT_QT 64
-template <int DS>  // DS == 0: runtime sub-dimension
+template <int DS, int MODE>  // DS == 0: runtime sub-dimension
 __global__ void __launch_bounds__(256) lut_kernel(const float *__restrict__ codebook, const float *__restrict__ Q,
-                                                  long long B, int D, int M, float *__restrict__ out) {
+                                                  long long B, int D, int M, float *__restrict__ out,
+                                                  float *__restrict__ mn, unsigned *__restrict__ range_bits,
+                                                  const float *__restrict__ scale, uint8_t *__restrict__ out8) {
     extern __shared__ float s_qs[];  // [LUT_QT][ds]
+    __shared__ float s_lo[8][LUT_QT], s_hi[8][LUT_QT];
     const int m = blockIdx.x, ds = DS ? DS : D / M, c = threadIdx.x;
     const long long b0 = (long long)blockIdx.y * LUT_QT;
     const int nb = (int)((B - b0 < LUT_QT) ? (B - b0) : LUT_QT);
@@ -86,39 +92,100 @@ __global__ void __launch_bounds__(256) lut_kernel(const float *__restrict__ code
     }
     __syncthreads();
     const float *cen = codebook + ((size_t)m * 256 + c) * ds;
-    float *o = out + ((size_t)b0 * M + m) * 256 + c;
+    float cr[DS ? DS : 1];
     if (DS) {
-        float cr[DS ? DS : 1];
 #pragma unroll
         for (int j = 0; j < (DS ? DS : 1); ++j) cr[j] = __ldg(cen + j);
-        for (int bb = 0; bb < nb; ++bb) o[(size_t)bb * M * 256] = np_pairwise_ct<(DS ? DS : 1)>(cr, s_qs + bb * (DS ? DS : 1));
-    } else {
-        for (int bb = 0; bb < nb; ++bb) o[(size_t)bb * M * 256] = np_pairwise_sqdiff(cen, s_qs + bb * ds, ds);
     }
+    for (int bb = 0; bb < nb; ++bb) {
+        float v;
+        if (DS) v = np_pairwise_ct<(DS ? DS : 1)>(cr, s_qs + bb * (DS ? DS : 1));
+        else v = np_pairwise_sqdiff(cen, s_qs + bb * ds, ds);
+        if (MODE == 0) {
+            out[((size_t)(b0 + bb) * M + m) * 256 + c] = v;
+        } else if (MODE == 1) {
+            float lo = v, hi = v;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(DR_FULL, lo, off));
+                hi = fmaxf(hi, __shfl_xor_sync(DR_FULL, hi, off));
+            }
+            if ((c & 31) == 0) { s_lo[c >> 5][bb] = lo; s_hi[c >> 5][bb] = hi; }
+        } else {
+            const float lo = mn[(size_t)(b0 + bb) * M + m];
+            float qv = rintf(__fdiv_rn(__fsub_rn(v, lo), scale[b0 + bb]));
+            out8[((size_t)(b0 + bb) * M + m) * 256 + c] = (uint8_t)(qv > 255.0f ? 255.0f : qv);
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        if (c < nb) {
+            float lo = s_lo[0][c], hi = s_hi[0][c];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) { lo = fminf(lo, s_lo[w][c]); hi = fmaxf(hi, s_hi[w][c]); }
+            mn[(size_t)(b0 + c) * M + m] = lo;
+            atomicMax(range_bits + b0 + c, __float_as_uint(__fsub_rn(hi, lo)));  // non-negative floats order like uints
+        }
+    }
+}
+
+// scale[b] = range / 255 (1 when the range is 0); offset[b] = sum_m mn[b][m] sequentially
+__global__ void lut_u8_finalize_kernel(const float *__restrict__ mn, const unsigned *__restrict__ range_bits, long long B, int M,
+                                       float *__restrict__ scale, float *__restrict__ offset) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float range = __uint_as_float(range_bits[b]);
+    scale[b] = range > 0.0f ? __fdiv_rn(range, 255.0f) : 1.0f;
+    float acc = 0.0f;
+    for (int m = 0; m < M; ++m) acc = __fadd_rn(acc, mn[(size_t)b * M + m]);
+    offset[b] = acc;
+}
+
+template <int MODE>
+static int lut_launch(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, float *d_out, float *d_mn,
+                      unsigned *d_range, const float *d_scale, uint8_t *d_out8, cudaStream_t s) {
+    const int ds = D / M;
+    const size_t smem = (size_t)LUT_QT * ds * sizeof(float);
+    DR_CHECK(smem <= 40 * 1024, "dr_lut_build: sub-dimension %d too large", ds);
+    const long long tiles = (B + LUT_QT - 1) / LUT_QT;
+    for (long long t0 = 0; t0 < tiles; t0 += 65535) {  // gridDim.y limit
+        long long nt = tiles - t0 < 65535 ? tiles - t0 : 65535;
+        dim3 grid(M, (unsigned)nt);
+        const size_t qo = (size_t)t0 * LUT_QT;
+        const float *q = d_Q + qo * D;
+        float *o = d_out ? d_out + qo * M * 256 : nullptr;
+        float *mnp = d_mn ? d_mn + qo * M : nullptr;
+        unsigned *rg = d_range ? d_range + qo : nullptr;
+        const float *sc = d_scale ? d_scale + qo : nullptr;
+        uint8_t *o8 = d_out8 ? d_out8 + qo * M * 256 : nullptr;
+        long long bb = B - t0 * LUT_QT;
+        switch (ds) {
+#define LUT_CASE(X) case X: lut_kernel<X, MODE><<<grid, 256, smem, s>>>(d_codebook, q, bb, D, M, o, mnp, rg, sc, o8); break;
+            LUT_CASE(4) LUT_CASE(8) LUT_CASE(12) LUT_CASE(16) LUT_CASE(24) LUT_CASE(32) LUT_CASE(48) LUT_CASE(64)
+#undef LUT_CASE
+            default: lut_kernel<0, MODE><<<grid, 256, smem, s>>>(d_codebook, q, bb, D, M, o, mnp, rg, sc, o8); break;
+        }
+        DR_LAUNCHED();
+    }
+    return 0;
 }
 
 int launch_lut_build(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, float *d_out, cudaStream_t s) {
     DR_CHECK(M > 0 && D % M == 0, "dr_lut_build: D=%d not divisible by M=%d", D, M);
     if (B == 0) return 0;
-    const int ds = D / M;
-    const size_t smem = (size_t)LUT_QT * ds * sizeof(float);
-    DR_CHECK(smem <= 48 * 1024, "dr_lut_build: sub-dimension %d too large", ds);
-    const long long tiles = (B + LUT_QT - 1) / LUT_QT;
-    for (long long t0 = 0; t0 < tiles; t0 += 65535) {  // gridDim.y limit
-        long long nt = tiles - t0 < 65535 ? tiles - t0 : 65535;
-        dim3 grid(M, (unsigned)nt);
-        const float *q = d_Q + (size_t)t0 * LUT_QT * D;
-        float *o = d_out + (size_t)t0 * LUT_QT * M * 256;
-        long long bb = B - t0 * LUT_QT;
-        switch (ds) {
-#define LUT_CASE(X) case X: lut_kernel<X><<<grid, 256, smem, s>>>(d_codebook, q, bb, D, M, o); break;
-            LUT_CASE(4) LUT_CASE(8) LUT_CASE(12) LUT_CASE(16) LUT_CASE(24) LUT_CASE(32) LUT_CASE(48) LUT_CASE(64)
-#undef LUT_CASE
-            default: lut_kernel<0><<<grid, 256, smem, s>>>(d_codebook, q, bb, D, M, o); break;
-        }
-        DR_LAUNCHED();
-    }
-    return 0;
+    return lut_launch<0>(d_codebook, d_Q, B, D, M, d_out, nullptr, nullptr, nullptr, nullptr, s);
+}
+
+// u8 table for the throughput mode: d_out8 u8[B][M][256], d_scale/d_offset f32[B]; d_mn f32[B][M] and d_range u32[B] are scratch
+int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
+                        float *d_offset, float *d_mn, unsigned *d_range, cudaStream_t s) {
+    DR_CHECK(M > 0 && D % M == 0, "dr_lut_build: D=%d not divisible by M=%d", D, M);
+    if (B == 0) return 0;
+    DR_CUDA(cudaMemsetAsync(d_range, 0, (size_t)B * 4, s));
+    if (lut_launch<1>(d_codebook, d_Q, B, D, M, nullptr, d_mn, d_range, nullptr, nullptr, s)) return 1;
+    lut_u8_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(d_mn, d_range, B, M, d_scale, d_offset);
+    DR_LAUNCHED();
+    return lut_launch<2>(d_codebook, d_Q, B, D, M, nullptr, d_mn, nullptr, d_scale, d_out8, s);
 }
 
 // ---------------------------------------------------------------------------------------------------

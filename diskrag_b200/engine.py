@@ -23,11 +23,12 @@ class SearchResult:
 
 
 def make_params(k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_out=False, hash_cap=0, chunk=0,
-                threads=0) -> SearchParams:
+                threads=0, lut="f32", prefetch=False) -> SearchParams:
     return SearchParams(k=k, L=L, W=W, dist=_lib.DR_DIST_PQ if dist == "pq" else _lib.DR_DIST_EXACT,
                         adc_order=_lib.DR_ADC_TREE if adc_order == "tree" else _lib.DR_ADC_SEQ,
                         rerank=int(bool(rerank)), sqrt_out=int(bool(sqrt_out)), hash_cap=hash_cap, chunk=chunk,
-                        threads=threads)
+                        threads=threads, lut_fmt=_lib.DR_LUT_U8 if lut == "u8" else _lib.DR_LUT_F32,
+                        prefetch=int(bool(prefetch)))
 
 
 class GpuIndex:
@@ -123,7 +124,7 @@ class GpuIndex:
 
     # ---- search ---------------------------------------------------------------------------------
     def search(self, Q, k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_out=False, lut=None,
-               want_list=False, trace=0, hash_cap=0, chunk=0, threads=0) -> SearchResult:
+               want_list=False, trace=0, hash_cap=0, chunk=0, threads=0, lut_fmt="f32", prefetch=False) -> SearchResult:
         """Batched search of Q f32[B,D] (host).  Returns host numpy arrays."""
         Q = as_f32(np.atleast_2d(Q))
         B, D = Q.shape
@@ -131,7 +132,7 @@ class GpuIndex:
             raise ValueError(f"query dimension {D} != index dimension {self.D}")
         if dist == "pq" and self.M == 0:
             raise ValueError("index has no PQ codes; use dist='exact'")
-        p = make_params(k, L, W, dist, adc_order, rerank, sqrt_out, hash_cap, chunk, threads)
+        p = make_params(k, L, W, dist, adc_order, rerank, sqrt_out, hash_cap, chunk, threads, lut_fmt, prefetch)
         if lut is not None:
             lut = as_f32(lut).reshape(B, self.M, 256)
         ids = np.empty((B, k), np.int32); dd = np.empty((B, k), np.float32)

@@ -37,6 +37,10 @@ typedef struct dr_index dr_index; /* opaque device-resident index (vectors, adja
 #define DR_ADC_SEQ 0  /* m = 0..M-1 sequential fp32 adds: bit-identical to fast_pq.py:320-328 */
 #define DR_ADC_TREE 1 /* lane-strided partial sums + butterfly: throughput mode, not a reference order */
 
+/* ADC table format held in shared memory */
+#define DR_LUT_F32 0 /* M x 256 fp32, bit-identical to DiskANNPQ.compute_distance_table */
+#define DR_LUT_U8 1  /* M x 256 bytes: q = rint((T - min_m) / scale), scale = max range / 255; exact integer sums */
+
 /* per-query status bits written to out_status */
 #define DR_ST_OK 0
 #define DR_ST_VISITED_OVERFLOW 1 /* visited set exceeded smem + overflow table: result incomplete */
@@ -53,6 +57,8 @@ typedef struct dr_search_params {
     int32_t hash_cap;  /* 0 = auto; else forces the shared-memory visited table size (power of two; tests) */
     int32_t chunk;     /* 0 = auto; queries per launch (bounds the device LUT buffer) */
     int32_t threads;   /* 0 = auto; CTA size (multiple of 32) */
+    int32_t lut_fmt;   /* DR_LUT_F32 (reference arithmetic) | DR_LUT_U8 (throughput: 8-bit table, integer sums) */
+    int32_t prefetch;  /* DR_LUT_U8 only: 1 = L2-prefetch the adjacency row of every accepted candidate */
 } dr_search_params;
 
 /* ---- library ---- */

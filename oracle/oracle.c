@@ -163,6 +163,33 @@ void orc_lut(const float *codebook, const float *q, int M, int ds, float *out) {
         }
 }
 
+/* Throughput-mode table (not a reference format; restated so the GPU's u8 mode can be checked bit-for-bit):
+ * per subspace mn[m] = min_c T[m,c]; range = max_m (max_c T[m,c] - mn[m]); scale = range / 255 (1 if 0);
+ * q[m,c] = min(255, rint((T[m,c] - mn[m]) / scale)); offset = sum_m mn[m] (sequential fp32).
+ * The quantised ADC is the exact integer sum of q[m, code[m]]; d ~ offset + scale * sum.   (pq.cu: lut_u8) */
+void orc_lut_u8(const float *codebook, const float *q, int M, int ds, uint8_t *out, float *scale_out, float *offset_out) {
+    float *T = (float *)malloc(sizeof(float) * 256 * (size_t)M);
+    float *mn = (float *)malloc(sizeof(float) * (size_t)M);
+    orc_lut(codebook, q, M, ds, T);
+    float range = 0.0f, offset = 0.0f;
+    for (int m = 0; m < M; ++m) {
+        float lo = T[m * 256], hi = T[m * 256];
+        for (int c = 1; c < 256; ++c) { float v = T[m * 256 + c]; if (v < lo) lo = v; if (v > hi) hi = v; }
+        mn[m] = lo;
+        float r = hi - lo;
+        if (r > range) range = r;
+        offset += lo;
+    }
+    float scale = range > 0.0f ? range / 255.0f : 1.0f;
+    for (int m = 0; m < M; ++m)
+        for (int c = 0; c < 256; ++c) {
+            float v = rintf((T[m * 256 + c] - mn[m]) / scale);
+            out[m * 256 + c] = (uint8_t)(v > 255.0f ? 255.0f : v);
+        }
+    *scale_out = scale; *offset_out = offset;
+    free(T); free(mn);
+}
+
 /* fast_pq.py:320-328  asymmetric_distance_sq — acc = 0; for m in 0..M-1: acc += T[m, code[m]]
  * strictly sequential fp32. */
 static inline float adc_seq(const uint8_t *code, const float *lut, int M) {
@@ -324,7 +351,7 @@ static void stable_sort_by_dist(ent_t *a, int n) { /* insertion sort: stable, n 
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     const uint32_t *adj; int R; long N;
-    const uint8_t *codes; int M; const float *lut;
+    const uint8_t *codes; int M; const float *lut; /* dist_mode 4: lut points at the u8 table */
     const float *vec; int D; const float *q; int flavor;
     int dist_mode;
 } sctx_t;
@@ -333,6 +360,12 @@ static inline float node_dist(const sctx_t *c, long id) {
     switch (c->dist_mode) {
     case 0: return adc_seq(c->codes + (size_t)id * c->M, c->lut, c->M);
     case 3: return adc_tree(c->codes + (size_t)id * c->M, c->lut, c->M);
+    case 4: { /* u8 table: exact integer sum, reported as a float (sums stay < 2^24) */
+        const uint8_t *t8 = (const uint8_t *)c->lut, *code = c->codes + (size_t)id * c->M;
+        uint32_t acc = 0;
+        for (int m = 0; m < c->M; ++m) acc += t8[m * 256 + code[m]];
+        return (float)acc;
+    }
     case 1: return sqrtf(l2sq_flavor(c->vec + (size_t)id * c->D, c->q, c->D, c->flavor));
     default: return l2sq_flavor(c->vec + (size_t)id * c->D, c->q, c->D, c->flavor);
     }
@@ -543,7 +576,9 @@ void orc_search_batch(const uint32_t *adj, int R, long N,
 #pragma omp for schedule(dynamic, 4)
         for (long b = 0; b < B; ++b) {
             const float *q = Q + (size_t)b * D;
+            float u8scale = 1.0f, u8off = 0.0f;
             if (dist_mode == 0 || dist_mode == 3) orc_lut(codebook, q, M, D / M, lut);
+            if (dist_mode == 4) orc_lut_u8(codebook, q, M, D / M, (uint8_t *)lut, &u8scale, &u8off);
             int32_t h, v;
             int n;
             if (W <= 1)

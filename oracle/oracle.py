@@ -14,7 +14,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _LIB = None
 
-DIST_ADC_SEQ, DIST_L2_SQRT, DIST_L2_SQ, DIST_ADC_TREE = 0, 1, 2, 3
+DIST_ADC_SEQ, DIST_L2_SQRT, DIST_L2_SQ, DIST_ADC_TREE, DIST_ADC_U8 = 0, 1, 2, 3, 4
 FLAVOR_DOUBLE, FLAVOR_NUMPY, FLAVOR_WARP, FLAVOR_SEQ = 0, 1, 2, 3
 
 
@@ -73,6 +73,16 @@ def lut(codebook, q):
     return out
 
 
+def lut_u8(codebook, q):
+    """Throughput-mode table: -> (u8[M,256], scale, offset); d ~ offset + scale * sum."""
+    codebook, q = _f32(codebook), _f32(q)
+    M, _, ds = codebook.shape
+    out = np.empty((M, 256), np.uint8)
+    sc = C.c_float(0); off = C.c_float(0)
+    lib().orc_lut_u8(_p(codebook), _p(q), C.c_int(M), C.c_int(ds), _p(out), C.byref(sc), C.byref(off))
+    return out, float(sc.value), float(off.value)
+
+
 def adc(codes, lut_, tree=False):
     codes = np.ascontiguousarray(codes, np.uint8)
     lut_ = _f32(lut_)
@@ -104,7 +114,7 @@ def _search(fn_name, adj, codes, lut_, vec, q, flavor, dist_mode, extra, start, 
     M = 0
     if codes is not None:
         codes = np.ascontiguousarray(codes, np.uint8); M = codes.shape[1]
-        lut_ = _f32(lut_)
+        lut_ = np.ascontiguousarray(lut_, np.uint8) if dist_mode == DIST_ADC_U8 else _f32(lut_)
     D = 0
     if vec is not None:
         vec = _f32(vec); D = vec.shape[1]

@@ -60,4 +60,6 @@ def test_product_never_imports_oracle():
         txt = p.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt and "ref_loader" not in txt, p
     for p in (ROOT / "diskrag_b200" / "csrc").glob("*"):
-        assert "oracle.c" not in p.read_text().replace("oracle.c:", "").replace("oracle/oracle.c", ""), p
+        txt = p.read_text()
+        assert "liboracle" not in txt and "dlopen" not in txt, p
+        assert not [l for l in txt.splitlines() if l.strip().startswith("#include") and "oracle" in l], p

@@ -142,6 +142,26 @@ def test_beam_W_vs_oracle(case, orc, W, adc):
         assert np.array_equal(oi, r.ids[qi, :len(oi)]) and np.array_equal(od, r.dists[qi, :len(od)])
 
 
+@pytest.mark.parametrize("W", [1, 4])
+def test_u8_table_mode_vs_oracle(case, orc, W):
+    """Throughput mode with the 8-bit ADC table (3 CTAs per SM): bit-for-bit against its restatement."""
+    c = case
+    L = 48
+    r = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=(W == 4))
+    r2 = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=False, lut_fmt="u8", hash_cap=256)
+    for qi in range(c["Q"].shape[0]):
+        t8, sc, off = orc.lut_u8(c["codebook"], c["Q"][qi])
+        l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False)
+        n = r.list_len[qi]
+        assert np.array_equal(l["ids"], r.list_ids[qi, :n]), (qi, W)
+        exp_d = (np.float64(np.float32(sc)) * l["dists"].astype(np.float64) + np.float64(np.float32(off))).astype(np.float32)
+        np.testing.assert_allclose(r.list_dists[qi, :n], exp_d, rtol=1e-6)
+        assert (r.hops[qi], r.visited[qi]) == (l["hops"], l["visited"])
+        oi, od = orc.rerank(c["X"], c["Q"][qi], l["ids"], 10, flavor=orc.FLAVOR_WARP)
+        assert np.array_equal(oi, r.ids[qi, :len(oi)]) and np.array_equal(od, r.dists[qi, :len(od)])
+        assert np.array_equal(r2.ids[qi, :min(10, n)], l["ids"][:10])      # no rerank, tiny visited table -> overflow path
+
+
 def test_visited_overflow_table(case, orc):
     """Force a tiny shared-memory visited table so the global overflow table is exercised; results must not change."""
     c = case
