@@ -42,10 +42,10 @@ def parse():
     ap.add_argument("--Lbuild", type=int, default=64)
     ap.add_argument("--M", type=int, default=192)
     ap.add_argument("--L", type=int, default=100)
-    ap.add_argument("--W", type=int, default=4)
+    ap.add_argument("--W", type=int, default=8)
     ap.add_argument("--adc", default="tree", choices=["seq", "tree"])
     ap.add_argument("--lut", default="u8", choices=["f32", "u8"])
-    ap.add_argument("--prefetch", type=int, default=1)
+    ap.add_argument("--prefetch", type=int, default=0)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries", type=int, default=100_000, help="queries per GPU per step")
     ap.add_argument("--gt-queries", type=int, default=1000)

@@ -129,18 +129,6 @@ __global__ void __launch_bounds__(256) lut_kernel(const float *__restrict__ code
     }
 }
 
-// scale[b] = range / 255 (1 when the range is 0); offset[b] = sum_m mn[b][m] sequentially
-__global__ void lut_u8_finalize_kernel(const float *__restrict__ mn, const unsigned *__restrict__ range_bits, long long B, int M,
-                                       float *__restrict__ scale, float *__restrict__ offset) {
-    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    float range = __uint_as_float(range_bits[b]);
-    scale[b] = range > 0.0f ? __fdiv_rn(range, 255.0f) : 1.0f;
-    float acc = 0.0f;
-    for (int m = 0; m < M; ++m) acc = __fadd_rn(acc, mn[(size_t)b * M + m]);
-    offset[b] = acc;
-}
-
 template <int MODE>
 static int lut_launch(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, float *d_out, float *d_mn,
                       unsigned *d_range, const float *d_scale, uint8_t *d_out8, cudaStream_t s) {
@@ -176,16 +164,150 @@ int launch_lut_build(const float *d_codebook, const float *d_Q, int64_t B, int D
     return lut_launch<0>(d_codebook, d_Q, B, D, M, d_out, nullptr, nullptr, nullptr, nullptr, s);
 }
 
-// u8 table for the throughput mode: d_out8 u8[B][M][256], d_scale/d_offset f32[B]; d_mn f32[B][M] and d_range u32[B] are scratch
+// ---------------------------------------------------------------------------------------------------
+// u8 table for the throughput mode.  The table entry only has to rank centroids inside one subspace, so it is
+// built from  t[c] = ||c||^2 - 2 q_m . c  (the ||q_m||^2 term is constant per subspace and is folded into the
+// per-query offset): one fmaf chain per entry instead of numpy's sub/mul/pairwise-add order.
+//   pass 1 (thread = query): lo[b][m] = min_c t, range[b] = max_m (max_c t - lo)
+//   finalize               : scale[b] = range / 255 (1 if 0), offset[b] = sum_m lo[b][m] + ||q||^2
+//   pass 2 (thread = centroid): out8[b][m][c] = min(255, rint((t - lo[b][m]) / scale[b]))
+// Restated bit-for-bit by oracle.c:orc_lut_u8.
+// ---------------------------------------------------------------------------------------------------
+#define U8_QT 256
+template <int DS>
+__global__ void __launch_bounds__(256) lut_u8_stats_kernel(const float *__restrict__ codebook, const float *__restrict__ Q,
+                                                           long long B, int D, int M, float *__restrict__ lo_out,
+                                                           unsigned *__restrict__ range_bits) {
+    __shared__ __align__(16) float s_c[256 * DS];
+    __shared__ float s_cn[256];
+    const int m = blockIdx.x;
+    const long long b = (long long)blockIdx.y * U8_QT + threadIdx.x;
+    const float *cb = codebook + (size_t)m * 256 * DS;
+    for (int i = threadIdx.x; i < 256 * DS; i += 256) s_c[i] = __ldg(cb + i);
+    __syncthreads();
+    {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < DS; ++j) acc = __fmaf_rn(s_c[threadIdx.x * DS + j], s_c[threadIdx.x * DS + j], acc);
+        s_cn[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (b >= B) return;
+    float q2[DS];
+#pragma unroll
+    for (int j = 0; j < DS; ++j) q2[j] = -2.0f * __ldg(Q + (size_t)b * D + m * DS + j);
+    float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+#pragma unroll 4
+    for (int c = 0; c < 256; ++c) {
+        float acc = s_cn[c];
+#pragma unroll
+        for (int j = 0; j < DS; ++j) acc = __fmaf_rn(q2[j], s_c[c * DS + j], acc);
+        lo = fminf(lo, acc);
+        hi = fmaxf(hi, acc);
+    }
+    lo_out[(size_t)b * M + m] = lo;
+    atomicMax(range_bits + b, __float_as_uint(__fsub_rn(hi, lo)));  // a non-negative float orders like its bits
+}
+
+__global__ void lut_u8_finalize_kernel(const float *__restrict__ lo, const unsigned *__restrict__ range_bits,
+                                       const float *__restrict__ Q, long long B, int D, int M,
+                                       float *__restrict__ scale, float *__restrict__ offset) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float range = __uint_as_float(range_bits[b]);
+    scale[b] = range > 0.0f ? __fdiv_rn(range, 255.0f) : 1.0f;
+    float acc = 0.0f;
+    for (int m = 0; m < M; ++m) acc = __fadd_rn(acc, lo[(size_t)b * M + m]);
+    float qn = 0.0f;
+    for (int j = 0; j < D; ++j) { float v = Q[(size_t)b * D + j]; qn = __fmaf_rn(v, v, qn); }
+    offset[b] = __fadd_rn(acc, qn);
+}
+
+#define U8_QT2 64
+// thread = 4 consecutive centroids of one query row (a 32-bit store), 64 threads per row, 4 query lanes per CTA
+template <int DS>
+__global__ void __launch_bounds__(256) lut_u8_quant_kernel(const float *__restrict__ codebook, const float *__restrict__ Q,
+                                                           long long B, int D, int M, const float *__restrict__ lo_in,
+                                                           const float *__restrict__ scale, uint8_t *__restrict__ out8) {
+    __shared__ __align__(16) float s_q2[U8_QT2 * DS];
+    __shared__ float s_lo[U8_QT2], s_sc[U8_QT2];
+    const int m = blockIdx.x, c4 = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const long long b0 = (long long)blockIdx.y * U8_QT2;
+    const int nb = (int)((B - b0 < U8_QT2) ? (B - b0) : U8_QT2);
+    for (int i = threadIdx.x; i < nb * DS; i += 256) {
+        int bb = i / DS, j = i - bb * DS;
+        s_q2[i] = -2.0f * __ldg(Q + (size_t)(b0 + bb) * D + m * DS + j);
+    }
+    if (threadIdx.x < nb) {
+        s_lo[threadIdx.x] = lo_in[(size_t)(b0 + threadIdx.x) * M + m];
+        s_sc[threadIdx.x] = scale[b0 + threadIdx.x];
+    }
+    float cr[4][DS];
+    float cn[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        cn[t] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < DS; ++j) {
+            cr[t][j] = __ldg(codebook + ((size_t)m * 256 + c4 * 4 + t) * DS + j);
+            cn[t] = __fmaf_rn(cr[t][j], cr[t][j], cn[t]);
+        }
+    }
+    __syncthreads();
+    uint32_t *o = reinterpret_cast<uint32_t *>(out8 + ((size_t)b0 * M + m) * 256) + c4;
+    for (int bb = grp; bb < nb; bb += 4) {
+        uint32_t packed = 0u;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float acc = cn[t];
+#pragma unroll
+            for (int j = 0; j < DS; ++j) acc = __fmaf_rn(s_q2[bb * DS + j], cr[t][j], acc);
+            float qv = rintf(__fdiv_rn(__fsub_rn(acc, s_lo[bb]), s_sc[bb]));
+            packed |= (uint32_t)fminf(fmaxf(qv, 0.0f), 255.0f) << (8 * t);
+        }
+        o[(size_t)bb * M * 64] = packed;
+    }
+}
+
+template <int DS>
+static int lut_u8_launch(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
+                         float *d_offset, float *d_lo, unsigned *d_range, cudaStream_t s) {
+    DR_CUDA(cudaMemsetAsync(d_range, 0, (size_t)B * 4, s));
+    for (long long t0 = 0; t0 * U8_QT < B; t0 += 65535) {
+        long long tiles = (B - t0 * U8_QT + U8_QT - 1) / U8_QT;
+        if (tiles > 65535) tiles = 65535;
+        dim3 grid(M, (unsigned)tiles);
+        const size_t qo = (size_t)t0 * U8_QT;
+        lut_u8_stats_kernel<DS><<<grid, 256, 0, s>>>(d_codebook, d_Q + qo * D, B - (long long)qo, D, M, d_lo + qo * M, d_range + qo);
+        DR_LAUNCHED();
+    }
+    lut_u8_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(d_lo, d_range, d_Q, B, D, M, d_scale, d_offset);
+    DR_LAUNCHED();
+    for (long long t0 = 0; t0 * U8_QT2 < B; t0 += 65535) {
+        long long tiles = (B - t0 * U8_QT2 + U8_QT2 - 1) / U8_QT2;
+        if (tiles > 65535) tiles = 65535;
+        dim3 grid(M, (unsigned)tiles);
+        const size_t qo = (size_t)t0 * U8_QT2;
+        lut_u8_quant_kernel<DS><<<grid, 256, 0, s>>>(d_codebook, d_Q + qo * D, B - (long long)qo, D, M, d_lo + qo * M, d_scale + qo,
+                                                     d_out8 + qo * M * 256);
+        DR_LAUNCHED();
+    }
+    return 0;
+}
+
+// d_out8 u8[B][M][256], d_scale/d_offset f32[B]; d_mn f32[B][M] and d_range u32[B] are scratch
 int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
                         float *d_offset, float *d_mn, unsigned *d_range, cudaStream_t s) {
     DR_CHECK(M > 0 && D % M == 0, "dr_lut_build: D=%d not divisible by M=%d", D, M);
     if (B == 0) return 0;
-    DR_CUDA(cudaMemsetAsync(d_range, 0, (size_t)B * 4, s));
-    if (lut_launch<1>(d_codebook, d_Q, B, D, M, nullptr, d_mn, d_range, nullptr, nullptr, s)) return 1;
-    lut_u8_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(d_mn, d_range, B, M, d_scale, d_offset);
-    DR_LAUNCHED();
-    return lut_launch<2>(d_codebook, d_Q, B, D, M, nullptr, d_mn, nullptr, d_scale, d_out8, s);
+    switch (D / M) {
+#define U8_CASE(X) case X: return lut_u8_launch<X>(d_codebook, d_Q, B, D, M, d_out8, d_scale, d_offset, d_mn, d_range, s);
+        U8_CASE(1) U8_CASE(2) U8_CASE(3) U8_CASE(4) U8_CASE(5) U8_CASE(6) U8_CASE(8) U8_CASE(12) U8_CASE(16) U8_CASE(24) U8_CASE(32)
+#undef U8_CASE
+        default: break;
+    }
+    dr_set_error("dr_search(u8): sub-dimension %d is not instantiated (1-6, 8, 12, 16, 24, 32)", D / M);
+    return 2;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -163,28 +163,38 @@ void orc_lut(const float *codebook, const float *q, int M, int ds, float *out) {
         }
 }
 
-/* Throughput-mode table (not a reference format; restated so the GPU's u8 mode can be checked bit-for-bit):
- * per subspace mn[m] = min_c T[m,c]; range = max_m (max_c T[m,c] - mn[m]); scale = range / 255 (1 if 0);
- * q[m,c] = min(255, rint((T[m,c] - mn[m]) / scale)); offset = sum_m mn[m] (sequential fp32).
- * The quantised ADC is the exact integer sum of q[m, code[m]]; d ~ offset + scale * sum.   (pq.cu: lut_u8) */
+/* Throughput-mode table (not a reference format; restated so the GPU's u8 mode can be checked bit-for-bit,
+ * pq.cu: lut_u8_*): t[m,c] = ||c||^2 - 2 q_m.c as one fmaf chain (cn = fma chain of c_j^2, then fma(-2 q_j, c_j, .));
+ * lo[m] = min_c t; range = max_m (max_c t - lo[m]); scale = range / 255 (1 if 0);
+ * q[m,c] = clamp(rint((t - lo[m]) / scale), 0, 255); offset = (sum_m lo[m], sequential) + ||q||^2 (fma chain).
+ * The quantised ADC is the exact integer sum of q[m, code[m]]; d ~ offset + scale * sum. */
 void orc_lut_u8(const float *codebook, const float *q, int M, int ds, uint8_t *out, float *scale_out, float *offset_out) {
     float *T = (float *)malloc(sizeof(float) * 256 * (size_t)M);
     float *mn = (float *)malloc(sizeof(float) * (size_t)M);
-    orc_lut(codebook, q, M, ds, T);
     float range = 0.0f, offset = 0.0f;
     for (int m = 0; m < M; ++m) {
-        float lo = T[m * 256], hi = T[m * 256];
-        for (int c = 1; c < 256; ++c) { float v = T[m * 256 + c]; if (v < lo) lo = v; if (v > hi) hi = v; }
+        float lo = INFINITY, hi = -INFINITY;
+        for (int c = 0; c < 256; ++c) {
+            const float *cen = codebook + ((size_t)m * 256 + c) * ds;
+            float acc = 0.0f;
+            for (int j = 0; j < ds; ++j) acc = fmaf(cen[j], cen[j], acc);
+            for (int j = 0; j < ds; ++j) acc = fmaf(-2.0f * q[m * ds + j], cen[j], acc);
+            T[m * 256 + c] = acc;
+            lo = fminf(lo, acc); hi = fmaxf(hi, acc);
+        }
         mn[m] = lo;
         float r = hi - lo;
         if (r > range) range = r;
         offset += lo;
     }
+    float qn = 0.0f;
+    for (int j = 0; j < M * ds; ++j) qn = fmaf(q[j], q[j], qn);
+    offset += qn;
     float scale = range > 0.0f ? range / 255.0f : 1.0f;
     for (int m = 0; m < M; ++m)
         for (int c = 0; c < 256; ++c) {
             float v = rintf((T[m * 256 + c] - mn[m]) / scale);
-            out[m * 256 + c] = (uint8_t)(v > 255.0f ? 255.0f : v);
+            out[m * 256 + c] = (uint8_t)fminf(fmaxf(v, 0.0f), 255.0f);
         }
     *scale_out = scale; *offset_out = offset;
     free(T); free(mn);

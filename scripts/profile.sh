@@ -6,6 +6,6 @@ ARGS="--queries 20000 --steps 1 --warmup 1 --gt-queries 200 --no-cpu-baseline --
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py $ARGS > gpurun_out/${TAG}_launches_bench.log 2>&1
 # the dominant kernel, full set with source
-timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:search_kernel -c 1 -f \
+timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:search_ -c 1 -f \
     -o gpurun_out/${TAG}_search python bench.py $ARGS > gpurun_out/${TAG}_full_bench.log 2>&1
 ls -la gpurun_out/
