@@ -1,0 +1,167 @@
+"""The served search seam: GPU stand-ins for the two methods DiskRAG's
+`SearchEngineCorrect` calls per request,
+
+    _pq_accelerated_graph_search(query_vector, k, L, beam_width)   search_engine.py:398-506
+    _exact_graph_search(query_vector, k, L)                        search_engine.py:508-528
+
+with the same return shapes and stats keys, plus a micro-batcher so that concurrent `/search` requests share one
+kernel launch (the reference handles one query at a time on the event loop, app.py:84-111).
+
+Semantics.  The reference's `_pq_accelerated_graph_search` is stochastic (`np.random.random() < 0.2`,
+search_engine.py:394-395) and compares a sqrt'd PQ distance with a squared exact one (:390 vs :460); it is not a
+contract one can be bit-equal to (variant E).  Here the PQ path is deterministic: PQ-ADC traversal
+with list size L, then an exact squared-L2 rerank of the list (what `_compute_exact_distance`, :374-379, computes),
+returning `(d2, id)` like :482-488.  `_exact_graph_search` is variant D with beam_width = 8 exactly as :514-520.
+Everything above the seam (`search`, `faq_search`, text lookup) is unchanged string plumbing and stays in the
+reference.
+"""
+import json
+import queue
+import threading
+import time
+from concurrent.futures import Future
+from pathlib import Path
+
+import numpy as np
+
+from ._lib import as_f32
+from .engine import GpuIndex
+
+
+class GpuSearchEngine:
+    def __init__(self, index_dir, device=0, throughput=True):
+        d = Path(index_dir)
+        if not (d / "meta.json").exists():
+            raise ValueError(f"索引目錄不存在或缺少 meta.json: {d}")       # search_engine.py:29-30
+        self.meta = json.loads((d / "meta.json").read_text())
+        self.medoid_idx = int(self.meta["medoid_idx"])
+        self.dimension = int(self.meta["D"])
+        self.index = GpuIndex.from_dir(d, device)
+        self.use_pq = self.index.M > 0                                      # PQ files missing -> exact search (:49-51)
+        self.n_subvectors = self.index.M
+        self.throughput = throughput
+        self.search_stats = {"total_searches": 0, "total_search_time": 0.0, "total_exact_computations": 0,
+                             "total_pq_computations": 0}
+        self._stats_lock = threading.Lock()
+        self._batcher = None
+
+    # ---- batched core ---------------------------------------------------------------------------------
+    def search_vectors(self, Q, k=10, L=100, pq=None):
+        """Q f32[B, D] -> SearchResult (ids, squared-L2 dists, hops, visited)."""
+        Q = as_f32(np.atleast_2d(Q))
+        if Q.shape[1] != self.dimension:
+            raise ValueError(f"查詢向量維度不匹配: 預期 {self.dimension}, 實際 {Q.shape[1]}")   # :547-551
+        pq = self.use_pq if pq is None else pq
+        L = max(int(L), int(k))
+        if pq:
+            if self.throughput:
+                return self.index.search(Q, k=k, L=L, W=4, dist="pq", rerank=True, lut_fmt="u8")
+            return self.index.search(Q, k=k, L=L, W=1, dist="pq", adc_order="seq", rerank=True)
+        return self.index.search(Q, k=k, L=L, W=1, dist="exact", rerank=False)
+
+    def _account(self, dt, n_exact, n_pq, n=1):
+        with self._stats_lock:
+            s = self.search_stats
+            s["total_searches"] += n; s["total_search_time"] += dt
+            s["total_exact_computations"] += n_exact; s["total_pq_computations"] += n_pq
+
+    # ---- the two seam methods ---------------------------------------------------------------------------
+    def _pq_accelerated_graph_search(self, query_vector, k=10, L=100, beam_width=None):
+        t0 = time.time()
+        r = self.search_vectors(np.asarray(query_vector, np.float32).reshape(1, -1), k=k, L=L, pq=True)
+        dt = time.time() - t0
+        res = [(float(r.dists[0, i]), int(r.ids[0, i])) for i in range(r.ids.shape[1]) if r.ids[0, i] >= 0]
+        n_pq = int(r.visited[0]); n_exact = int(r.list_len[0])
+        self._account(dt, n_exact, n_pq)
+        stats = {"search_time": dt, "nodes_visited": n_pq, "exact_distance_computations": n_exact,
+                 "pq_distance_computations": n_pq, "computation_reduction_rate": 1 - (n_exact / max(1, n_pq)),
+                 "search_steps": int(r.hops[0])}
+        return res, stats
+
+    def _exact_graph_search(self, query_vector, k=10, L=100):
+        t0 = time.time()
+        kk = min(int(k), 8)
+        r = self.index.search(np.asarray(query_vector, np.float32).reshape(1, -1), k=kk, L=8, W=1, dist="exact", rerank=False,
+                              sqrt_out=True)                                 # beam_width=8 is hard-coded at :514-520
+        dt = time.time() - t0
+        res = [(r.dists[0, i], np.uint32(r.ids[0, i])) for i in range(kk) if r.ids[0, i] >= 0]
+        self._account(dt, int(r.visited[0]), 0)
+        return res, {"search_time": dt, "exact_distance_computations": len(res) * 2, "search_type": "exact_beam_search"}
+
+    def get_search_statistics(self):
+        with self._stats_lock:
+            s = dict(self.search_stats)
+        n = max(1, s["total_searches"])
+        s["avg_search_time"] = s["total_search_time"] / n
+        return s
+
+    # ---- micro-batching for concurrent requests -----------------------------------------------------------
+    def start_batcher(self, max_batch=256, max_wait_ms=2.0, k=10, L=100):
+        if self._batcher is None:
+            self._batcher = _MicroBatcher(self, max_batch, max_wait_ms, k, L)
+        return self._batcher
+
+    def submit(self, query_vector) -> Future:
+        """Queue one query; concurrent submitters are answered from one batched launch."""
+        if self._batcher is None:
+            self.start_batcher()
+        return self._batcher.submit(query_vector)
+
+    def close(self):
+        if self._batcher is not None:
+            self._batcher.stop()
+            self._batcher = None
+        self.index.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _MicroBatcher:
+    def __init__(self, engine, max_batch, max_wait_ms, k, L):
+        self.engine, self.max_batch, self.max_wait, self.k, self.L = engine, max_batch, max_wait_ms / 1e3, k, L
+        self.q = queue.Queue()
+        self.alive = True
+        self.batches = 0
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def submit(self, query_vector):
+        f = Future()
+        self.q.put((np.asarray(query_vector, np.float32).ravel(), f))
+        return f
+
+    def _run(self):
+        while self.alive:
+            try:
+                first = self.q.get(timeout=0.05)
+            except queue.Empty:
+                continue
+            items = [first]
+            deadline = time.time() + self.max_wait
+            while len(items) < self.max_batch:
+                left = deadline - time.time()
+                if left <= 0:
+                    break
+                try:
+                    items.append(self.q.get(timeout=left))
+                except queue.Empty:
+                    break
+            try:
+                r = self.engine.search_vectors(np.stack([q for q, _ in items]), k=self.k, L=self.L)
+                self.batches += 1
+                for i, (_, f) in enumerate(items):
+                    f.set_result([(float(r.dists[i, j]), int(r.ids[i, j])) for j in range(r.ids.shape[1]) if r.ids[i, j] >= 0])
+            except Exception as e:  # surface CUDA / shape errors to every waiter
+                for _, f in items:
+                    f.set_exception(e)
+
+    def stop(self):
+        self.alive = False
+        self.t.join(timeout=1.0)
+
+
+SearchEngine = GpuSearchEngine

@@ -151,3 +151,112 @@ def test_dynamic_updates(data):
     g.consolidate_index(R=12, L=24, alpha=1.2)
     res = vg.greedy_search(g, g.medoid_idx, Q[0], 20)
     assert len(res) == 20 and min(res) >= 100 and 1000 not in res
+
+
+def test_search_engine_seam(data, tmp_path, orc):
+    """§8(f1): index directory in the reference's layout -> GpuSearchEngine seam methods + micro-batcher."""
+    import random
+    from diskrag_b200 import vamana_graph as vg
+    from diskrag_b200.io.diskann_persist import DiskANNPersist
+    from diskrag_b200.pq.fast_pq import DiskANNPQ
+    from diskrag_b200.search_engine import GpuSearchEngine
+    X, Q, _ = data
+    X = X[:3000]
+    gt = orc.ground_truth(X, Q, 10)
+    pq = DiskANNPQ(16, 256); pq.fit(X)
+    codes = pq.encode(X)
+    random.seed(1)
+    g = vg.build_vamana(X, R=16, L=32, alpha=1.2)
+    p = DiskANNPersist(dim=64, R=16)
+    p.save_index(tmp_path / "index.dat", g)
+    p.save_pq_codes(tmp_path / "pq_codes.bin", codes)
+    p.save_pq_codebook(tmp_path / "pq_model.pkl", pq)
+    p.save_meta(tmp_path / "meta.json", {"D": 64, "R": 16, "L": 32, "alpha": 1.2, "N": 3000, "medoid_idx": int(g.medoid_idx),
+                                         "n_subvectors": 16, "pq_centroids": 256, "use_pq": True})
+    for throughput in (False, True):
+        eng = GpuSearchEngine(tmp_path, throughput=throughput)
+        res, stats = eng._pq_accelerated_graph_search(Q[0], k=10, L=60)
+        assert len(res) == 10 and all(res[i][0] <= res[i + 1][0] for i in range(9)) and isinstance(res[0][1], int)
+        assert set(stats) == {"search_time", "nodes_visited", "exact_distance_computations", "pq_distance_computations",
+                              "computation_reduction_rate", "search_steps"}
+        # returned distances are exact squared L2 (search_engine.py:374-379)
+        for d2, i in res:
+            np.testing.assert_allclose(d2, float(((X[i] - Q[0]) ** 2).sum()), rtol=1e-4)
+        hits = 0
+        for qi in range(40):
+            r, _ = eng._pq_accelerated_graph_search(Q[qi], k=10, L=60)
+            hits += len({i for _, i in r} & set(gt[qi].tolist()))
+        assert hits / 400 > 0.9
+        ex, st = eng._exact_graph_search(Q[0], k=5)
+        assert len(ex) == 5 and st["search_type"] == "exact_beam_search" and isinstance(ex[0][1], np.uint32)
+        with pytest.raises(ValueError):
+            eng.search_vectors(np.zeros((1, 65), np.float32))
+        # concurrent submitters share launches
+        eng.start_batcher(max_batch=64, max_wait_ms=20.0, k=10, L=60)
+        futs = [eng.submit(Q[qi]) for qi in range(40)]
+        outs = [f.result(timeout=30) for f in futs]
+        assert eng._batcher.batches < 40
+        single, _ = eng._pq_accelerated_graph_search(Q[3], k=10, L=60)
+        assert [i for _, i in outs[3]] == [i for _, i in single]
+        assert eng.get_search_statistics()["total_searches"] >= 41
+        eng.close()
+
+
+def test_whole_package_swap_runs_reference_scenarios(tmp_path):
+    """alias diskrag_b200 as `pydiskann` and run the reference's own integration scenarios
+    (scripts/test_pydiskann_cython.sh:36-82 and test_disk_write_verify.py:20-192) through the reference's import paths."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import diskrag_b200, diskrag_b200.vamana_graph, diskrag_b200.cython_utils
+import diskrag_b200.pq, diskrag_b200.pq.fast_pq, diskrag_b200.io, diskrag_b200.io.diskann_persist
+for name, mod in {"pydiskann": diskrag_b200, "pydiskann.vamana_graph": diskrag_b200.vamana_graph,
+                  "pydiskann.cython_utils": diskrag_b200.cython_utils, "pydiskann.pq": diskrag_b200.pq,
+                  "pydiskann.pq.fast_pq": diskrag_b200.pq.fast_pq, "pydiskann.io": diskrag_b200.io,
+                  "pydiskann.io.diskann_persist": diskrag_b200.io.diskann_persist}.items():
+    sys.modules[name] = mod
+# --- the reference's step 5: known answers vs numpy
+import numpy as np
+from pydiskann.cython_utils import l2_distance_fast_cython as l2_cy, cosine_similarity_cython as cos_cy
+rs = np.random.RandomState(0)
+x = rs.randn(128).astype(np.float32); y = rs.randn(128).astype(np.float32)
+assert np.allclose(l2_cy(x, y), np.sum((x - y) ** 2), rtol=1e-5, atol=1e-6)
+assert np.allclose(cos_cy(x, y), 1.0 - (x @ y) / (np.linalg.norm(x) * np.linalg.norm(y)), rtol=1e-5, atol=1e-6)
+# --- the reference's step 6: PQ + build + PQ beam search
+from pydiskann.vamana_graph import build_vamana_with_pq, beam_search_with_pq, build_vamana, beam_search_from_disk
+from pydiskann.pq.fast_pq import DiskANNPQ
+rs = np.random.RandomState(42)
+X = rs.randn(2000, 64).astype(np.float32)
+pq = DiskANNPQ(n_subvectors=8, n_centroids=256); pq.fit(X)
+g = build_vamana_with_pq(X, pq, R=16, L=32, alpha=1.2)
+g.enable_pq_search(True)
+res = beam_search_with_pq(g, X[0], start_idx=0, beam_width=8, k=5, use_pq=True)
+assert isinstance(res, list) and len(res) > 0
+# --- test_disk_write_verify.py: save, size, reader, disk search, raw bytes of record 0
+from pydiskann.io.diskann_persist import DiskANNPersist, MMapNodeReader
+np.random.seed(42)
+pts = np.random.randn(1000, 128).astype(np.float32)
+graph = build_vamana(pts, R=16, L=32, alpha=1.2)
+p = DiskANNPersist(dim=128, R=16)
+path = %r
+p.save_index(path, graph)
+import os
+assert os.path.getsize(path) == 1000 * 4 * (128 + 16)
+reader = MMapNodeReader(path, dim=128, R=16)
+vec, nbrs = reader.get_node(0)
+assert np.allclose(vec, graph.nodes[0].vector)
+for bw in (8, 16):
+    out = beam_search_from_disk(reader, np.random.randn(128).astype(np.float32), start_id=0, beam_width=bw, k=5)
+    assert len(out) > 0
+raw = open(path, "rb").read(4 * (128 + 16))
+assert np.array_equal(np.frombuffer(raw[:512], np.float32), graph.nodes[0].vector)
+disk_nb = set(int(v) for v in np.frombuffer(raw[512:], np.uint32)[:len(graph.nodes[0].neighbors)])
+assert disk_nb == set(graph.nodes[0].neighbors)
+print("SWAP-OK")
+''' % (str(root), str(tmp_path / "index.dat"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "SWAP-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
