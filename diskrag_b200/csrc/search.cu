@@ -511,6 +511,36 @@ template <int G>
 __device__ __forceinline__ void adc_u8_group(const uint8_t *__restrict__ codes, int M, const uint8_t *__restrict__ lut8,
                                              const uint32_t (&ids)[G], int cnt, int lane, uint32_t (&out)[G]) {
     const int words = M >> 2;
+    if (words > 32 && words <= 48) {
+        // 33..48 code words per row (M = 192 -> 48): the upper <=16 words of TWO rows share one warp pass
+        // (lanes 0-15 row g, lanes 16-31 row g+1), so every lane does 12 lookups per pair instead of 16.
+        const int up = words - 32, hl = lane & 15;
+        uint32_t w0[G], wu[G / 2];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            w0[g] = 0u;
+            if (g < cnt) w0[g] = __ldg(reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M) + lane);
+        }
+#pragma unroll
+        for (int p = 0; p < G / 2; ++p) {
+            const int g = 2 * p + (lane >> 4);
+            wu[p] = 0u;
+            if (g < cnt && hl < up) wu[p] = __ldg(reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M) + 32 + hl);
+        }
+#pragma unroll
+        for (int p = 0; p < G / 2; ++p) {
+            if (2 * p < cnt) {
+                uint32_t u = (hl < up) ? lut8_word(lut8, (32 + hl) << 2, wu[p]) : 0u;
+                uint32_t accA = lut8_word(lut8, lane << 2, w0[2 * p]) + ((lane < 16) ? u : 0u);
+                out[2 * p] = __reduce_add_sync(DR_FULL, accA);
+                if (2 * p + 1 < cnt) {
+                    uint32_t accB = lut8_word(lut8, lane << 2, w0[2 * p + 1]) + ((lane >= 16) ? u : 0u);
+                    out[2 * p + 1] = __reduce_add_sync(DR_FULL, accB);
+                }
+            }
+        }
+        return;
+    }
     uint32_t w0[G], w1[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -553,7 +583,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
 
     __shared__ long long s_b;
     __shared__ __align__(8) uint64_t s_lutbar;
-    __shared__ int s_nn, s_ns, s_mvalid, s_hcount, s_ovfcount, s_useovf, s_ovfused, s_status;
+    __shared__ int s_nn2[2], s_ns, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
 
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -576,7 +606,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
         if (tid == 0) {
             mbar_expect_tx(&s_lutbar, (uint32_t)M * 256u);
             bulk_g2s(s_lut, a.lut8 + (size_t)b * M * 256, (uint32_t)M * 256u, &s_lutbar);
-            s_hcount = 1; s_ovfcount = 0; s_ovfused = 0; s_status = 0;
+            s_hcount = 1; s_ovfcount = 0; s_ovfused = 0; s_status = 0; s_nn2[0] = 0;
         }
         if (a.rerank) {
             const float *qg = a.Q + (size_t)b * D;
@@ -594,64 +624,68 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                 s_hash[hash_u32(a.start) & hmask] = a.start;
             }
         }
-        int cur = 0, n = 1, hops = 0, nvis = 1;
+        int cur = 0, n = 1, hops = 0, nvis = 1, step = 0;
         __syncthreads();
 
         for (;;) {
             u64 *lst = cur ? s_list1 : s_list0;
             u64 *oth = cur ? s_list0 : s_list1;
-            // (1) first W unexpanded entries
-            if (wid == 0) {
-                int found = 0;
-                for (int base = 0; base < n && found < W; base += 32) {
+            // (1+2) warp s finds the s-th unexpanded entry itself (no marking yet, so the scans do not race), loads
+            //       that node's adjacency row and claims its first-seen neighbours
+            int *p_nn = &s_nn2[step & 1];
+            const bool use_ovf_now = (s_hcount + W * R > hlimit);   // same value for every thread (read after the last barrier)
+            if (tid == 0) {
+                s_mvalid = 0;
+                if (use_ovf_now) s_ovfused = 1;
+            }
+            const bool ovf_full = use_ovf_now && (s_ovfcount + W * R > ovf_limit);
+            for (int s = wid; s < W; s += nw) {
+                // rank-s unexpanded entry
+                int found = 0, pos = -1;
+                const bool need_total = (s == 0);   // warp 0 also publishes how many nodes are expanded this step
+                for (int base = 0; base < n && (pos < 0 || (need_total && found < W)); base += 32) {
                     int i = base + lane;
                     u64 kx = (i < n) ? lst[i] : 1ull;
-                    bool un = !(kx & 1ull);
-                    unsigned m = __ballot_sync(DR_FULL, un);
-                    int r = found + __popc(m & lt_mask);
-                    if (un && r < W) { s_sel[r] = key_id(kx); lst[i] = kx | 1ull; }
-                    found += __popc(m);
+                    unsigned m = __ballot_sync(DR_FULL, !(kx & 1ull));
+                    int c = __popc(m);
+                    if (pos < 0 && found + c > s) pos = base + (int)__fns(m, 0, s - found + 1);
+                    found += c;
                 }
-                if (found > W) found = W;
-                if (lane == 0) {
-                    s_ns = found; s_nn = 0; s_mvalid = 0;
-                    int useovf = (s_hcount + W * R > hlimit) ? 1 : 0;
-                    s_useovf = useovf;
-                    if (useovf) {
-                        s_ovfused = 1;
-                        if (s_ovfcount + W * R > ovf_limit) { s_status |= DR_ST_VISITED_OVERFLOW; s_ns = 0; }
-                    }
+                if (need_total && lane == 0) {
+                    int tot = found < W ? found : W;
+                    if (ovf_full) { s_status |= DR_ST_VISITED_OVERFLOW; tot = 0; }
+                    s_ns = tot;
                 }
-            }
-            __syncthreads();
-            const int ns = s_ns;
-            if (ns == 0) break;
-            const bool use_ovf = s_useovf != 0;
-            // (2) adjacency rows -> first-seen neighbours
-            for (int s = wid; s < ns; s += nw) {
-                const uint32_t *row = a.adj + (size_t)s_sel[s] * R;
+                if (pos < 0 || ovf_full) continue;   // warp-uniform
+                if (lane == 0) s_sel[W + s] = (uint32_t)pos;
+                const uint32_t node = key_id(lst[pos]);
+                const uint32_t *row = a.adj + (size_t)node * R;
                 for (int j0 = 0; j0 < R; j0 += 32) {
                     int j = j0 + lane;
                     uint32_t nb = (j < R) ? __ldg(row + j) : DR_EMPTY;
                     bool valid = (j < R) && ((long long)nb < a.N);
                     if (valid && a.deleted) valid = a.deleted[nb] == 0;
-                    unsigned peers = __match_any_sync(DR_FULL, nb);
-                    bool leader = (__ffs(peers) - 1) == lane;
-                    bool isnew = false;
-                    if (valid && leader) isnew = visited_insert(nb, s_hash, hmask, use_ovf, my_ovf, ovf_mask);
+                    bool isnew = false;   // equal ids in one row (0-padding): the CAS admits exactly one of them
+                    if (valid) isnew = visited_insert(nb, s_hash, hmask, use_ovf_now, my_ovf, ovf_mask);
                     unsigned m = __ballot_sync(DR_FULL, isnew);
                     int cnt = __popc(m);
                     int basepos = 0;
                     if (cnt) {
-                        if (lane == 0) basepos = atomicAdd(&s_nn, cnt);
+                        if (lane == 0) basepos = atomicAdd(p_nn, cnt);
                         basepos = __shfl_sync(DR_FULL, basepos, 0);
                     }
                     if (isnew) s_newid[basepos + __popc(m & lt_mask)] = nb;
                 }
             }
             __syncthreads();
+            const int ns = s_ns;
+            if (ns == 0) break;
+            const bool use_ovf = use_ovf_now;
+            if (tid < ns) lst[s_sel[W + tid]] |= 1ull;        // mark the expanded entries (merge reads them after the next barrier)
+            if (tid == 0) s_nn2[(step + 1) & 1] = 0;          // next step's newcomer counter
+            ++step;
             // (3) quantised ADC of the newcomers; the survivors are appended compactly
-            const int nn = s_nn;
+            const int nn = *p_nn;
             const bool full = (n >= L);
             const u64 worstk = lst[n - 1] & ~1ull;
             if (wordpath) {
@@ -666,15 +700,20 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                         if (i < nn) { gid[g] = s_newid[i]; cnt = g + 1; }
                     }
                     adc_u8_group<G>(a.codes, M, s_lut, gid, cnt, lane, gs);
-                    if (lane == 0) {
+                    {   // lane g owns key g; one aggregated counter update per group
+                        uint32_t mysum = gs[0], myid = gid[0];
 #pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            if (g < cnt) {
-                                u64 key = make_ikey(gs[g], gid[g]);
-                                if (!full || key < worstk) {
-                                    s_newk[atomicAdd(&s_mvalid, 1)] = key;
-                                    if (a.prefetch) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)gid[g] * R));
-                                }
+                        for (int g = 1; g < G; ++g) if (lane == g) { mysum = gs[g]; myid = gid[g]; }
+                        const u64 key = make_ikey(mysum, myid);
+                        const bool ok = lane < cnt && (!full || key < worstk);
+                        const unsigned okm = __ballot_sync(DR_FULL, ok);
+                        if (okm) {
+                            int basep = 0;
+                            if (lane == 0) basep = atomicAdd(&s_mvalid, __popc(okm));
+                            basep = __shfl_sync(DR_FULL, basep, 0);
+                            if (ok) {
+                                s_newk[basep + __popc(okm & lt_mask)] = key;
+                                if (a.prefetch) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)myid * R));
                             }
                         }
                     }
@@ -696,35 +735,77 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             nvis += nn;
             hops += ns;
             const int mv = s_mvalid;
-            // (4) rank-merge: only the survivors take part
+            // (4) merge.  Up to 32 survivors: warp 0 sorts them in registers (bitonic, shuffles), then every item finds
+            //     its slot by binary search in the other sequence.  More than 32 (first steps only): rank counting.
             if (mv > 0) {
                 const int total = n + mv;
-                for (int x = tid; x < total; x += nt) {
-                    u64 key;
-                    int pos;
-                    if (x < n) {
-                        key = lst[x];
-                        int c = 0;
-                        for (int j = 0; j < mv; ++j) c += (s_newk[j] < key) ? 1 : 0;
-                        pos = x + c;
-                    } else {
-                        key = s_newk[x - n];
-                        int c = 0;
-                        for (int j = 0; j < mv; ++j) c += (s_newk[j] < key) ? 1 : 0;
-                        int lo = 0, hi = n;
-                        while (lo < hi) {
-                            int mid = (lo + hi) >> 1;
-                            if (lst[mid] < key) lo = mid + 1; else hi = mid;
+                if (mv <= 32) {
+                    if (wid == 0) {
+                        u64 key = lane < mv ? s_newk[lane] : DR_KEY_MAX;
+#pragma unroll
+                        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                                const u64 other = __shfl_xor_sync(DR_FULL, key, j);
+                                const bool up = ((lane & k2) == 0);            // ascending block
+                                const bool lower = ((lane & j) == 0);          // this lane keeps the smaller of the pair
+                                const bool take_min = (up == lower);
+                                const u64 mn = key < other ? key : other, mx = key < other ? other : key;
+                                key = take_min ? mn : mx;
+                            }
                         }
-                        pos = lo + c;
+                        if (lane < mv) s_newk[lane] = key;
                     }
-                    if (pos < L) oth[pos] = key;
+                    __syncthreads();
+                    for (int x = tid; x < total; x += nt) {
+                        u64 key;
+                        int pos;
+                        if (x < n) {
+                            key = lst[x];
+                            int lo = 0, hi = mv;                               // new keys smaller than this old entry
+                            while (lo < hi) {
+                                int mid = (lo + hi) >> 1;
+                                if (s_newk[mid] < key) lo = mid + 1; else hi = mid;
+                            }
+                            pos = x + lo;
+                        } else {
+                            const int j = x - n;
+                            key = s_newk[j];
+                            int lo = 0, hi = n;
+                            while (lo < hi) {
+                                int mid = (lo + hi) >> 1;
+                                if (lst[mid] < key) lo = mid + 1; else hi = mid;
+                            }
+                            pos = lo + j;
+                        }
+                        if (pos < L) oth[pos] = key;
+                    }
+                } else {
+                    for (int x = tid; x < total; x += nt) {
+                        u64 key;
+                        int pos;
+                        if (x < n) {
+                            key = lst[x];
+                            int c = 0;
+                            for (int j = 0; j < mv; ++j) c += (s_newk[j] < key) ? 1 : 0;
+                            pos = x + c;
+                        } else {
+                            key = s_newk[x - n];
+                            int c = 0;
+                            for (int j = 0; j < mv; ++j) c += (s_newk[j] < key) ? 1 : 0;
+                            int lo = 0, hi = n;
+                            while (lo < hi) {
+                                int mid = (lo + hi) >> 1;
+                                if (lst[mid] < key) lo = mid + 1; else hi = mid;
+                            }
+                            pos = lo + c;
+                        }
+                        if (pos < L) oth[pos] = key;
+                    }
                 }
                 cur ^= 1;
                 n = total < L ? total : L;
-                // no barrier here: the next select (warp 0) and everyone else meet at the barrier after (1);
-                // but warp 0 must not read `oth` before all writers are done
-                __syncthreads();
+                __syncthreads();   // the next step's scans read the merged list
             }
         }
 
@@ -808,7 +889,7 @@ static int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr
     const int NC = (p->W * h->R + 1) & ~1;
     a.o_newk = off; off += NC * 8;
     a.o_newid = off; off += NC * 4;
-    a.o_sel = off; off += ((p->W * 4 + 7) / 8) * 8;
+    a.o_sel = off; off += ((2 * p->W * 4 + 7) / 8) * 8;
     a.o_hash = off;
     const int fixed = off;
     // visited table: enough for the typical visit count at <= 3/4 load, then whatever keeps 3 CTAs per SM
