@@ -170,7 +170,7 @@ int launch_lut_build(const float *d_codebook, const float *d_Q, int64_t B, int D
 // per-query offset): one fmaf chain per entry instead of numpy's sub/mul/pairwise-add order.
 //   pass 1 (thread = query): lo[b][m] = min_c t, range[b] = max_m (max_c t - lo)
 //   finalize               : scale[b] = range / 255 (1 if 0), offset[b] = sum_m lo[b][m] + ||q||^2
-//   pass 2 (thread = centroid): out8[b][m][c] = min(255, rint((t - lo[b][m]) / scale[b]))
+//   pass 2 (thread = centroid): out8[b][m][c] = clamp(rint(fma(t, inv, c0)), 0, 255), inv = 1/scale[b], c0 = -(lo[b][m] * inv)
 // Restated bit-for-bit by oracle.c:orc_lut_u8.
 // ---------------------------------------------------------------------------------------------------
 #define U8_QT 256
@@ -224,48 +224,41 @@ __global__ void lut_u8_finalize_kernel(const float *__restrict__ lo, const unsig
 }
 
 #define U8_QT2 64
-// thread = 4 consecutive centroids of one query row (a 32-bit store), 64 threads per row, 4 query lanes per CTA
+// thread = centroid c of subspace m, walking a 64-query tile (coalesced 256 B rows)
 template <int DS>
 __global__ void __launch_bounds__(256) lut_u8_quant_kernel(const float *__restrict__ codebook, const float *__restrict__ Q,
                                                            long long B, int D, int M, const float *__restrict__ lo_in,
                                                            const float *__restrict__ scale, uint8_t *__restrict__ out8) {
     __shared__ __align__(16) float s_q2[U8_QT2 * DS];
     __shared__ float s_lo[U8_QT2], s_sc[U8_QT2];
-    const int m = blockIdx.x, c4 = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int m = blockIdx.x, c = threadIdx.x;
     const long long b0 = (long long)blockIdx.y * U8_QT2;
     const int nb = (int)((B - b0 < U8_QT2) ? (B - b0) : U8_QT2);
     for (int i = threadIdx.x; i < nb * DS; i += 256) {
         int bb = i / DS, j = i - bb * DS;
         s_q2[i] = -2.0f * __ldg(Q + (size_t)(b0 + bb) * D + m * DS + j);
     }
-    if (threadIdx.x < nb) {
-        s_lo[threadIdx.x] = lo_in[(size_t)(b0 + threadIdx.x) * M + m];
-        s_sc[threadIdx.x] = scale[b0 + threadIdx.x];
+    if (threadIdx.x < nb) {   // q = rint(t * inv + c0), inv = 1 / scale, c0 = -(lo * inv)
+        const float inv = __fdiv_rn(1.0f, scale[b0 + threadIdx.x]);
+        s_sc[threadIdx.x] = inv;
+        s_lo[threadIdx.x] = -__fmul_rn(lo_in[(size_t)(b0 + threadIdx.x) * M + m], inv);
     }
-    float cr[4][DS];
-    float cn[4];
+    float cr[DS];
+    float cn = 0.0f;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        cn[t] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < DS; ++j) {
-            cr[t][j] = __ldg(codebook + ((size_t)m * 256 + c4 * 4 + t) * DS + j);
-            cn[t] = __fmaf_rn(cr[t][j], cr[t][j], cn[t]);
-        }
+    for (int j = 0; j < DS; ++j) {
+        cr[j] = __ldg(codebook + ((size_t)m * 256 + c) * DS + j);
+        cn = __fmaf_rn(cr[j], cr[j], cn);
     }
     __syncthreads();
-    uint32_t *o = reinterpret_cast<uint32_t *>(out8 + ((size_t)b0 * M + m) * 256) + c4;
-    for (int bb = grp; bb < nb; bb += 4) {
-        uint32_t packed = 0u;
+    uint8_t *o = out8 + ((size_t)b0 * M + m) * 256 + c;
+    for (int bb = 0; bb < nb; ++bb) {
+        float acc = cn;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            float acc = cn[t];
-#pragma unroll
-            for (int j = 0; j < DS; ++j) acc = __fmaf_rn(s_q2[bb * DS + j], cr[t][j], acc);
-            float qv = rintf(__fdiv_rn(__fsub_rn(acc, s_lo[bb]), s_sc[bb]));
-            packed |= (uint32_t)fminf(fmaxf(qv, 0.0f), 255.0f) << (8 * t);
-        }
-        o[(size_t)bb * M * 64] = packed;
+        for (int j = 0; j < DS; ++j) acc = __fmaf_rn(s_q2[bb * DS + j], cr[j], acc);
+        uint32_t qv;
+        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(qv) : "f"(__fmaf_rn(acc, s_sc[bb], s_lo[bb])));   // round-half-even, clamp to [0, 255]
+        o[(size_t)bb * M * 256] = (uint8_t)qv;
     }
 }
 

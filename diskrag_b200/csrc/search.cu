@@ -516,16 +516,16 @@ __device__ __forceinline__ void adc_u8_group(const uint8_t *__restrict__ codes, 
         // (lanes 0-15 row g, lanes 16-31 row g+1), so every lane does 12 lookups per pair instead of 16.
         const int up = words - 32, hl = lane & 15;
         uint32_t w0[G], wu[G / 2];
+        const uint32_t *rowp[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            w0[g] = 0u;
-            if (g < cnt) w0[g] = __ldg(reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M) + lane);
-        }
+        for (int g = 0; g < G; ++g) rowp[g] = reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M);
+#pragma unroll
+        for (int g = 0; g < G; ++g) w0[g] = (g < cnt) ? __ldg(rowp[g] + lane) : 0u;
 #pragma unroll
         for (int p = 0; p < G / 2; ++p) {
+            const uint32_t *rp = (lane < 16) ? rowp[2 * p] : rowp[2 * p + 1];
             const int g = 2 * p + (lane >> 4);
-            wu[p] = 0u;
-            if (g < cnt && hl < up) wu[p] = __ldg(reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M) + 32 + hl);
+            wu[p] = (g < cnt && hl < up) ? __ldg(rp + 32 + hl) : 0u;
         }
 #pragma unroll
         for (int p = 0; p < G / 2; ++p) {

@@ -166,7 +166,7 @@ void orc_lut(const float *codebook, const float *q, int M, int ds, float *out) {
 /* Throughput-mode table (not a reference format; restated so the GPU's u8 mode can be checked bit-for-bit,
  * pq.cu: lut_u8_*): t[m,c] = ||c||^2 - 2 q_m.c as one fmaf chain (cn = fma chain of c_j^2, then fma(-2 q_j, c_j, .));
  * lo[m] = min_c t; range = max_m (max_c t - lo[m]); scale = range / 255 (1 if 0);
- * q[m,c] = clamp(rint((t - lo[m]) / scale), 0, 255); offset = (sum_m lo[m], sequential) + ||q||^2 (fma chain).
+ * q[m,c] = clamp(rint(fma(t, inv, c0)), 0, 255) with inv = 1/scale, c0 = -(lo[m]*inv); offset = (sum_m lo[m], sequential) + ||q||^2 (fma chain).
  * The quantised ADC is the exact integer sum of q[m, code[m]]; d ~ offset + scale * sum. */
 void orc_lut_u8(const float *codebook, const float *q, int M, int ds, uint8_t *out, float *scale_out, float *offset_out) {
     float *T = (float *)malloc(sizeof(float) * 256 * (size_t)M);
@@ -191,11 +191,14 @@ void orc_lut_u8(const float *codebook, const float *q, int M, int ds, uint8_t *o
     for (int j = 0; j < M * ds; ++j) qn = fmaf(q[j], q[j], qn);
     offset += qn;
     float scale = range > 0.0f ? range / 255.0f : 1.0f;
-    for (int m = 0; m < M; ++m)
+    const float inv = 1.0f / scale;
+    for (int m = 0; m < M; ++m) {
+        const float c0 = -(mn[m] * inv);
         for (int c = 0; c < 256; ++c) {
-            float v = rintf((T[m * 256 + c] - mn[m]) / scale);
+            float v = rintf(fmaf(T[m * 256 + c], inv, c0));
             out[m * 256 + c] = (uint8_t)fminf(fmaxf(v, 0.0f), 255.0f);
         }
+    }
     *scale_out = scale; *offset_out = offset;
     free(T); free(mn);
 }
