@@ -222,6 +222,10 @@ int dr_index_destroy(dr_index *h) {
     if (h->d_ovf) cudaFree(h->d_ovf);
     if (h->d_io) cudaFree(h->d_io);
     if (h->d_deleted) cudaFree(h->d_deleted);
+    if (h->s_in) {
+        cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_comp); cudaStreamDestroy(h->s_out);
+        for (int i = 0; i < DR_PIPE_EVENTS; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_done[i]); }
+    }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -298,23 +302,52 @@ int dr_search_batch(dr_index *h, const float *Q, int64_t B, const dr_search_para
     int32_t *dLids = (int32_t *)base; base += szL;
     float *dLdist = (float *)base; base += szL;
     int32_t *dTrace = trace ? (int32_t *)base : nullptr;
-    cudaStream_t s = 0;
-    DR_CUDA(cudaMemcpyAsync(dQ, Q, (size_t)B * h->D * 4, cudaMemcpyHostToDevice, s));
-    if (lut) DR_CUDA(cudaMemcpyAsync(dLut, lut, (size_t)B * h->M * 1024, cudaMemcpyHostToDevice, s));
-    if (trace) DR_CUDA(cudaMemsetAsync(dTrace, 0xFF, (size_t)B * trace_cap * 4, s));
-    int rc = launch_search(h, dQ, B, p, dLut, dIds, dDist, dHops, dVis, out_list_ids ? dLids : nullptr,
-                           out_list_dist ? dLdist : nullptr, dLlen, dTrace, trace_cap, dStat, s);
-    if (rc) return rc;
-    DR_CUDA(cudaMemcpyAsync(out_ids, dIds, (size_t)B * p->k * 4, cudaMemcpyDeviceToHost, s));
-    if (out_dist) DR_CUDA(cudaMemcpyAsync(out_dist, dDist, (size_t)B * p->k * 4, cudaMemcpyDeviceToHost, s));
-    if (out_hops) DR_CUDA(cudaMemcpyAsync(out_hops, dHops, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (out_visited) DR_CUDA(cudaMemcpyAsync(out_visited, dVis, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (out_status) DR_CUDA(cudaMemcpyAsync(out_status, dStat, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (out_list_len) DR_CUDA(cudaMemcpyAsync(out_list_len, dLlen, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (out_list_ids) DR_CUDA(cudaMemcpyAsync(out_list_ids, dLids, (size_t)B * p->L * 4, cudaMemcpyDeviceToHost, s));
-    if (out_list_dist) DR_CUDA(cudaMemcpyAsync(out_list_dist, dLdist, (size_t)B * p->L * 4, cudaMemcpyDeviceToHost, s));
-    if (trace) DR_CUDA(cudaMemcpyAsync(trace, dTrace, (size_t)B * trace_cap * 4, cudaMemcpyDeviceToHost, s));
-    DR_CUDA(cudaStreamSynchronize(s));
+    // Pipeline: the batch is cut into pieces; the H2D copy of piece i+1 (copy stream) overlaps the search of piece i
+    // (compute stream) and the D2H of piece i-1 (output stream).  With pageable host memory the copies degrade to
+    // synchronous staging, which is still correct.
+    if (!h->s_in) {
+        DR_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        DR_CUDA(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+        DR_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < DR_PIPE_EVENTS; ++i) {
+            DR_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            DR_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    int64_t piece = B;
+    if (!lut && !trace && B >= 8192) {
+        int64_t np = (B + 16383) / 16384;
+        if (np > DR_PIPE_EVENTS) np = DR_PIPE_EVENTS;
+        piece = (B + np - 1) / np;
+    }
+    if (trace) DR_CUDA(cudaMemsetAsync(dTrace, 0xFF, (size_t)B * trace_cap * 4, h->s_comp));
+    int pi = 0;
+    for (int64_t c0 = 0; c0 < B; c0 += piece, ++pi) {
+        const int64_t cb = (B - c0 < piece) ? (B - c0) : piece;
+        DR_CUDA(cudaMemcpyAsync(dQ + (size_t)c0 * h->D, Q + (size_t)c0 * h->D, (size_t)cb * h->D * 4, cudaMemcpyHostToDevice, h->s_in));
+        if (lut) DR_CUDA(cudaMemcpyAsync(dLut, lut, (size_t)B * h->M * 1024, cudaMemcpyHostToDevice, h->s_in));
+        DR_CUDA(cudaEventRecord(h->ev_in[pi], h->s_in));
+        DR_CUDA(cudaStreamWaitEvent(h->s_comp, h->ev_in[pi], 0));
+        int rc = launch_search(h, dQ + (size_t)c0 * h->D, cb, p, dLut, dIds + (size_t)c0 * p->k, dDist + (size_t)c0 * p->k,
+                               dHops + c0, dVis + c0, out_list_ids ? dLids + (size_t)c0 * p->L : nullptr,
+                               out_list_dist ? dLdist + (size_t)c0 * p->L : nullptr, dLlen + c0,
+                               dTrace ? dTrace + (size_t)c0 * trace_cap : nullptr, trace_cap, dStat + c0, h->s_comp);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        DR_CUDA(cudaEventRecord(h->ev_done[pi], h->s_comp));
+        DR_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[pi], 0));
+        cudaStream_t s = h->s_out;
+        DR_CUDA(cudaMemcpyAsync(out_ids + (size_t)c0 * p->k, dIds + (size_t)c0 * p->k, (size_t)cb * p->k * 4, cudaMemcpyDeviceToHost, s));
+        if (out_dist) DR_CUDA(cudaMemcpyAsync(out_dist + (size_t)c0 * p->k, dDist + (size_t)c0 * p->k, (size_t)cb * p->k * 4, cudaMemcpyDeviceToHost, s));
+        if (out_hops) DR_CUDA(cudaMemcpyAsync(out_hops + c0, dHops + c0, (size_t)cb * 4, cudaMemcpyDeviceToHost, s));
+        if (out_visited) DR_CUDA(cudaMemcpyAsync(out_visited + c0, dVis + c0, (size_t)cb * 4, cudaMemcpyDeviceToHost, s));
+        if (out_status) DR_CUDA(cudaMemcpyAsync(out_status + c0, dStat + c0, (size_t)cb * 4, cudaMemcpyDeviceToHost, s));
+        if (out_list_len) DR_CUDA(cudaMemcpyAsync(out_list_len + c0, dLlen + c0, (size_t)cb * 4, cudaMemcpyDeviceToHost, s));
+        if (out_list_ids) DR_CUDA(cudaMemcpyAsync(out_list_ids + (size_t)c0 * p->L, dLids + (size_t)c0 * p->L, (size_t)cb * p->L * 4, cudaMemcpyDeviceToHost, s));
+        if (out_list_dist) DR_CUDA(cudaMemcpyAsync(out_list_dist + (size_t)c0 * p->L, dLdist + (size_t)c0 * p->L, (size_t)cb * p->L * 4, cudaMemcpyDeviceToHost, s));
+        if (trace) DR_CUDA(cudaMemcpyAsync(trace + (size_t)c0 * trace_cap, dTrace + (size_t)c0 * trace_cap, (size_t)cb * trace_cap * 4, cudaMemcpyDeviceToHost, s));
+    }
+    DR_CUDA(cudaStreamSynchronize(h->s_out));
+    DR_CUDA(cudaStreamSynchronize(h->s_comp));
     return 0;
 }
 

@@ -41,6 +41,8 @@ extern std::atomic<long long> g_launches;
         DR_CUDA(cudaGetLastError());                   \
     } while (0)
 
+#define DR_PIPE_EVENTS 16
+
 struct dr_index {
     int device = 0;
     int64_t N = 0;
@@ -62,6 +64,9 @@ struct dr_index {
     // search-kernel timing (bench roofline)
     bool timing = false; double timed_ms = 0.0; long long timed_launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // host-pointer API pipeline (copy-in / compute / copy-out streams)
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[DR_PIPE_EVENTS] = {}, ev_done[DR_PIPE_EVENTS] = {};
 };
 
 int dr_scratch(void **ptr, size_t *cur, size_t need);  // grow-only device scratch
