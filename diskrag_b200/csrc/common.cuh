@@ -77,6 +77,11 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
                   int32_t *ids, float *dist, int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist,
                   int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s,
                   const int32_t *qmap = nullptr);
+int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, int32_t *ids, float *dist,
+                       int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist, int32_t *list_len,
+                       int32_t *status, cudaStream_t s);   // search_fast.cu: u8-table throughput kernel
+int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
+                        float *d_offset, float *d_mn, unsigned *d_range, int word_layout, cudaStream_t s);  // pq.cu
 
 // ---------------------------------------------------------------------------------------------
 // device side
@@ -200,6 +205,34 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
+}
+
+// visited set: open-addressing table in shared memory (atomicCAS claims a slot); once it is 3/4 full the shared table
+// is frozen (lookups only) and new ids go to the CTA's global overflow table.  Returns true when nb is first seen.
+__device__ __forceinline__ bool visited_insert(uint32_t nb, uint32_t *hash, uint32_t mask, bool use_ovf,
+                                               uint32_t *ovf, uint32_t ovf_mask) {
+    uint32_t h = hash_u32(nb) & mask;
+    if (!use_ovf) {
+        for (;;) {
+            uint32_t old = atomicCAS(&hash[h], DR_EMPTY, nb);
+            if (old == DR_EMPTY) return true;
+            if (old == nb) return false;
+            h = (h + 1) & mask;
+        }
+    }
+    for (;;) {  // shared table is frozen: look up only, then claim in the global overflow table
+        uint32_t cur = hash[h];
+        if (cur == nb) return false;
+        if (cur == DR_EMPTY) break;
+        h = (h + 1) & mask;
+    }
+    h = hash_u32(nb ^ 0x9e3779b9u) & ovf_mask;
+    for (;;) {
+        uint32_t old = atomicCAS(&ovf[h], DR_EMPTY, nb);
+        if (old == DR_EMPTY) return true;
+        if (old == nb) return false;
+        h = (h + 1) & ovf_mask;
+    }
 }
 
 #endif  // __CUDACC__

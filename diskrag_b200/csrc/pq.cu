@@ -262,9 +262,60 @@ __global__ void __launch_bounds__(256) lut_u8_quant_kernel(const float *__restri
     }
 }
 
+// Word layout for the bank-per-lane search table (search_fast.cu): out8[b][w][c][j] = entry of subspace 4w + j,
+// centroid c.  Block = (code word w, 64-query tile); thread c computes the four subspaces' entries of its centroid
+// and stores one packed 32-bit word per query: a warp writes 128 contiguous bytes.  Same arithmetic, entry for
+// entry, as lut_u8_quant_kernel.
+template <int DS>
+__global__ void __launch_bounds__(256) lut_u8_quant_word_kernel(const float *__restrict__ codebook, const float *__restrict__ Q,
+                                                                long long B, int D, int M, const float *__restrict__ lo_in,
+                                                                const float *__restrict__ scale, uint32_t *__restrict__ out32) {
+    __shared__ __align__(16) float s_q2[U8_QT2 * 4 * DS];
+    __shared__ float s_lo[U8_QT2 * 4], s_sc[U8_QT2];
+    const int w = blockIdx.x, c = threadIdx.x, words = M >> 2;
+    const long long b0 = (long long)blockIdx.y * U8_QT2;
+    const int nb = (int)((B - b0 < U8_QT2) ? (B - b0) : U8_QT2);
+    for (int i = threadIdx.x; i < nb * 4 * DS; i += 256) {
+        int bb = i / (4 * DS), j = i - bb * (4 * DS);
+        s_q2[i] = -2.0f * __ldg(Q + (size_t)(b0 + bb) * D + (size_t)w * 4 * DS + j);
+    }
+    if (threadIdx.x < nb) s_sc[threadIdx.x] = __fdiv_rn(1.0f, scale[b0 + threadIdx.x]);
+    __syncthreads();
+    if (threadIdx.x < nb * 4) {   // c0 = -(lo * inv) per (query, subspace of this word)
+        const int bb = threadIdx.x >> 2, j = threadIdx.x & 3;
+        s_lo[threadIdx.x] = -__fmul_rn(lo_in[(size_t)(b0 + bb) * M + 4 * w + j], s_sc[bb]);
+    }
+    float cr[4][DS], cn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cn[j] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < DS; ++i) {
+            cr[j][i] = __ldg(codebook + ((size_t)(4 * w + j) * 256 + c) * DS + i);
+            cn[j] = __fmaf_rn(cr[j][i], cr[j][i], cn[j]);
+        }
+    }
+    __syncthreads();
+    uint32_t *o = out32 + ((size_t)b0 * words + w) * 256 + c;
+    for (int bb = 0; bb < nb; ++bb) {
+        uint32_t packed = 0u;
+        const float inv = s_sc[bb];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = cn[j];
+#pragma unroll
+            for (int i = 0; i < DS; ++i) acc = __fmaf_rn(s_q2[(bb * 4 + j) * DS + i], cr[j][i], acc);
+            uint32_t qv;
+            asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(qv) : "f"(__fmaf_rn(acc, inv, s_lo[bb * 4 + j])));
+            packed |= qv << (8 * j);
+        }
+        o[(size_t)bb * words * 256] = packed;
+    }
+}
+
 template <int DS>
 static int lut_u8_launch(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
-                         float *d_offset, float *d_lo, unsigned *d_range, cudaStream_t s) {
+                         float *d_offset, float *d_lo, unsigned *d_range, int word_layout, cudaStream_t s) {
     DR_CUDA(cudaMemsetAsync(d_range, 0, (size_t)B * 4, s));
     for (long long t0 = 0; t0 * U8_QT < B; t0 += 65535) {
         long long tiles = (B - t0 * U8_QT + U8_QT - 1) / U8_QT;
@@ -279,22 +330,30 @@ static int lut_u8_launch(const float *d_codebook, const float *d_Q, int64_t B, i
     for (long long t0 = 0; t0 * U8_QT2 < B; t0 += 65535) {
         long long tiles = (B - t0 * U8_QT2 + U8_QT2 - 1) / U8_QT2;
         if (tiles > 65535) tiles = 65535;
-        dim3 grid(M, (unsigned)tiles);
         const size_t qo = (size_t)t0 * U8_QT2;
-        lut_u8_quant_kernel<DS><<<grid, 256, 0, s>>>(d_codebook, d_Q + qo * D, B - (long long)qo, D, M, d_lo + qo * M, d_scale + qo,
-                                                     d_out8 + qo * M * 256);
+        if (word_layout) {
+            dim3 grid(M >> 2, (unsigned)tiles);
+            lut_u8_quant_word_kernel<DS><<<grid, 256, 0, s>>>(d_codebook, d_Q + qo * D, B - (long long)qo, D, M, d_lo + qo * M,
+                                                              d_scale + qo, reinterpret_cast<uint32_t *>(d_out8 + qo * M * 256));
+        } else {
+            dim3 grid(M, (unsigned)tiles);
+            lut_u8_quant_kernel<DS><<<grid, 256, 0, s>>>(d_codebook, d_Q + qo * D, B - (long long)qo, D, M, d_lo + qo * M, d_scale + qo,
+                                                         d_out8 + qo * M * 256);
+        }
         DR_LAUNCHED();
     }
     return 0;
 }
 
-// d_out8 u8[B][M][256], d_scale/d_offset f32[B]; d_mn f32[B][M] and d_range u32[B] are scratch
+// d_out8: word_layout == 0: u8[B][M][256];  word_layout == 1 (M % 4 == 0): u8[B][M/4][256][4] (see above);
+// d_scale/d_offset f32[B]; d_mn f32[B][M] and d_range u32[B] are scratch
 int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
-                        float *d_offset, float *d_mn, unsigned *d_range, cudaStream_t s) {
+                        float *d_offset, float *d_mn, unsigned *d_range, int word_layout, cudaStream_t s) {
     DR_CHECK(M > 0 && D % M == 0, "dr_lut_build: D=%d not divisible by M=%d", D, M);
+    DR_CHECK(!word_layout || (M & 3) == 0, "dr_lut_build(u8): the word layout needs M %% 4 == 0 (M=%d)", M);
     if (B == 0) return 0;
     switch (D / M) {
-#define U8_CASE(X) case X: return lut_u8_launch<X>(d_codebook, d_Q, B, D, M, d_out8, d_scale, d_offset, d_mn, d_range, s);
+#define U8_CASE(X) case X: return lut_u8_launch<X>(d_codebook, d_Q, B, D, M, d_out8, d_scale, d_offset, d_mn, d_range, word_layout, s);
         U8_CASE(1) U8_CASE(2) U8_CASE(3) U8_CASE(4) U8_CASE(5) U8_CASE(6) U8_CASE(8) U8_CASE(12) U8_CASE(16) U8_CASE(24) U8_CASE(32)
 #undef U8_CASE
         default: break;

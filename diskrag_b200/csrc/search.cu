@@ -106,32 +106,6 @@ __device__ __forceinline__ void adc_tree_group(const uint8_t *__restrict__ codes
     }
 }
 
-__device__ __forceinline__ bool visited_insert(uint32_t nb, uint32_t *hash, uint32_t mask, bool use_ovf,
-                                               uint32_t *ovf, uint32_t ovf_mask) {
-    uint32_t h = hash_u32(nb) & mask;
-    if (!use_ovf) {
-        for (;;) {
-            uint32_t old = atomicCAS(&hash[h], DR_EMPTY, nb);
-            if (old == DR_EMPTY) return true;
-            if (old == nb) return false;
-            h = (h + 1) & mask;
-        }
-    }
-    for (;;) {  // shared table is frozen: look up only, then claim in the global overflow table
-        uint32_t cur = hash[h];
-        if (cur == nb) return false;
-        if (cur == DR_EMPTY) break;
-        h = (h + 1) & mask;
-    }
-    h = hash_u32(nb ^ 0x9e3779b9u) & ovf_mask;
-    for (;;) {
-        uint32_t old = atomicCAS(&ovf[h], DR_EMPTY, nb);
-        if (old == DR_EMPTY) return true;
-        if (old == nb) return false;
-        h = (h + 1) & ovf_mask;
-    }
-}
-
 // The reference's per-neighbour accept/evict rule, literally, for the (rare) step in which an exact
 // distance tie sits on the list boundary.  Runs on one thread.  (oracle.c: orc_search_list, strict branch)
 __device__ __noinline__ void seq_insert_strict(u64 *lst, int *pn, int L, const u64 *newk, int nn, u64 *ghost, int *png,
@@ -478,503 +452,6 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Throughput kernel: PQ traversal over a u8-quantised ADC table (pq.cu: launch_lut_build_u8), W expansions
-// per step, pure key-order merge, fused exact rerank.  The table is M x 256 BYTES (48 KB at M = 192 instead
-// of 192 KB), so three CTAs share an SM and one CTA's dependent gather latency (adjacency row -> code rows)
-// is covered by the others' ADC / rerank work.  Distances are exact integer sums of table bytes, hence
-// independent of summation order; keys are (sum, id).  Restated bit-for-bit by oracle.c (dist_mode 4).
-// ---------------------------------------------------------------------------------------------------
-struct FastArgs {
-    const float *vec; const uint32_t *adj; const uint8_t *codes; const uint8_t *deleted;
-    const float *Q; const uint8_t *lut8; const float *lut_scale; const float *lut_offset;
-    long long N; int D, R, M;
-    long long B; int k, L, W;
-    int rerank, sqrt_out, prefetch;
-    uint32_t start;
-    int32_t *out_ids; float *out_dist; int32_t *out_hops; int32_t *out_visited;
-    int32_t *list_ids; float *list_dist; int32_t *list_len; int32_t *status;
-    u64 *counter;
-    uint32_t *ovf; uint32_t ovf_cap; uint32_t hash_cap;
-    int o_q, o_list0, o_list1, o_newk, o_newid, o_sel, o_hash;
-};
-
-__device__ __forceinline__ uint32_t lut8_word(const uint8_t *__restrict__ lut8, int m0, uint32_t w) {
-    const uint8_t *l = lut8 + (m0 << 8);
-    return (uint32_t)l[w & 0xFFu] + (uint32_t)l[256 + ((w >> 8) & 0xFFu)] + (uint32_t)l[512 + ((w >> 16) & 0xFFu)] +
-           (uint32_t)l[768 + (w >> 24)];
-}
-
-// G code rows per warp: lane l owns code word l (subspaces 4l..4l+3) and word l+32 when present; all word loads
-// are issued before any lookup.  M % 4 == 0, M <= 256.
-template <int G>
-__device__ __forceinline__ void adc_u8_group(const uint8_t *__restrict__ codes, int M, const uint8_t *__restrict__ lut8,
-                                             const uint32_t (&ids)[G], int cnt, int lane, uint32_t (&out)[G]) {
-    const int words = M >> 2;
-    if (words > 32 && words <= 48) {
-        // 33..48 code words per row (M = 192 -> 48): the upper <=16 words of TWO rows share one warp pass
-        // (lanes 0-15 row g, lanes 16-31 row g+1), so every lane does 12 lookups per pair instead of 16.
-        const int up = words - 32, hl = lane & 15;
-        uint32_t w0[G], wu[G / 2];
-        const uint32_t *rowp[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) rowp[g] = reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M);
-#pragma unroll
-        for (int g = 0; g < G; ++g) w0[g] = (g < cnt) ? __ldg(rowp[g] + lane) : 0u;
-#pragma unroll
-        for (int p = 0; p < G / 2; ++p) {
-            const uint32_t *rp = (lane < 16) ? rowp[2 * p] : rowp[2 * p + 1];
-            const int g = 2 * p + (lane >> 4);
-            wu[p] = (g < cnt && hl < up) ? __ldg(rp + 32 + hl) : 0u;
-        }
-#pragma unroll
-        for (int p = 0; p < G / 2; ++p) {
-            if (2 * p < cnt) {
-                uint32_t u = (hl < up) ? lut8_word(lut8, (32 + hl) << 2, wu[p]) : 0u;
-                uint32_t accA = lut8_word(lut8, lane << 2, w0[2 * p]) + ((lane < 16) ? u : 0u);
-                out[2 * p] = __reduce_add_sync(DR_FULL, accA);
-                if (2 * p + 1 < cnt) {
-                    uint32_t accB = lut8_word(lut8, lane << 2, w0[2 * p + 1]) + ((lane >= 16) ? u : 0u);
-                    out[2 * p + 1] = __reduce_add_sync(DR_FULL, accB);
-                }
-            }
-        }
-        return;
-    }
-    uint32_t w0[G], w1[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        w0[g] = 0u; w1[g] = 0u;
-        if (g < cnt) {
-            const uint32_t *cw = reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M);
-            if (lane < words) w0[g] = __ldg(cw + lane);
-            if (lane + 32 < words) w1[g] = __ldg(cw + lane + 32);
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        if (g < cnt) {
-            uint32_t acc = 0u;
-            if (lane < words) acc = lut8_word(lut8, lane << 2, w0[g]);
-            if (lane + 32 < words) acc += lut8_word(lut8, (lane + 32) << 2, w1[g]);
-            out[g] = __reduce_add_sync(DR_FULL, acc);
-        }
-    }
-}
-
-__device__ __forceinline__ uint32_t adc_u8_warp(const uint8_t *__restrict__ code, const uint8_t *__restrict__ lut8, int M, int lane) {
-    uint32_t acc = 0u;
-    for (int m = lane; m < M; m += 32) acc += lut8[(m << 8) + __ldg(code + m)];
-    return __reduce_add_sync(DR_FULL, acc);
-}
-
-__device__ __forceinline__ u64 make_ikey(uint32_t sum, uint32_t id) { return ((u64)sum << 32) | ((u64)id << 1); }
-
-__global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
-    uint8_t *s_lut = dr_smem;
-    float *s_q = reinterpret_cast<float *>(dr_smem + a.o_q);
-    u64 *s_list0 = reinterpret_cast<u64 *>(dr_smem + a.o_list0);
-    u64 *s_list1 = reinterpret_cast<u64 *>(dr_smem + a.o_list1);
-    u64 *s_newk = reinterpret_cast<u64 *>(dr_smem + a.o_newk);
-    uint32_t *s_newid = reinterpret_cast<uint32_t *>(dr_smem + a.o_newid);
-    uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);
-    uint32_t *s_hash = reinterpret_cast<uint32_t *>(dr_smem + a.o_hash);
-    u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_hash);
-
-    __shared__ long long s_b;
-    __shared__ __align__(8) uint64_t s_lutbar;
-    __shared__ int s_nn2[2], s_ns, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
-
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int D = a.D, R = a.R, M = a.M, L = a.L, W = a.W;
-    const uint32_t hmask = a.hash_cap - 1u, ovf_mask = a.ovf_cap - 1u;
-    const int hlimit = (int)(a.hash_cap - (a.hash_cap >> 2));
-    const int ovf_limit = (int)(a.ovf_cap - (a.ovf_cap >> 2));
-    uint32_t *my_ovf = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
-    const bool wordpath = ((M & 3) == 0) && M <= 256;
-    uint32_t lut_phase = 0;
-    if (tid == 0) { mbar_init(&s_lutbar, 1); fence_mbar_init(); }
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_b = (long long)atomicAdd(a.counter, 1ull);
-        __syncthreads();
-        const long long b = s_b;
-        if (b >= a.B) break;
-
-        if (tid == 0) {
-            mbar_expect_tx(&s_lutbar, (uint32_t)M * 256u);
-            bulk_g2s(s_lut, a.lut8 + (size_t)b * M * 256, (uint32_t)M * 256u, &s_lutbar);
-            s_hcount = 1; s_ovfcount = 0; s_ovfused = 0; s_status = 0; s_nn2[0] = 0;
-        }
-        if (a.rerank) {
-            const float *qg = a.Q + (size_t)b * D;
-            for (int i = tid; i < D; i += nt) s_q[i] = __ldg(qg + i);
-        }
-        for (uint32_t i = tid; i < a.hash_cap; i += nt) s_hash[i] = DR_EMPTY;
-        mbar_wait(&s_lutbar, lut_phase);
-        lut_phase ^= 1u;
-        __syncthreads();
-
-        if (wid == 0) {
-            uint32_t s0 = adc_u8_warp(a.codes + (size_t)a.start * M, s_lut, M, lane);
-            if (lane == 0) {
-                s_list0[0] = make_ikey(s0, a.start);
-                s_hash[hash_u32(a.start) & hmask] = a.start;
-            }
-        }
-        int cur = 0, n = 1, hops = 0, nvis = 1, step = 0;
-        __syncthreads();
-
-        for (;;) {
-            u64 *lst = cur ? s_list1 : s_list0;
-            u64 *oth = cur ? s_list0 : s_list1;
-            // (1+2) warp s finds the s-th unexpanded entry itself (no marking yet, so the scans do not race), loads
-            //       that node's adjacency row and claims its first-seen neighbours
-            int *p_nn = &s_nn2[step & 1];
-            const bool use_ovf_now = (s_hcount + W * R > hlimit);   // same value for every thread (read after the last barrier)
-            if (tid == 0) {
-                s_mvalid = 0;
-                if (use_ovf_now) s_ovfused = 1;
-            }
-            const bool ovf_full = use_ovf_now && (s_ovfcount + W * R > ovf_limit);
-            for (int s = wid; s < W; s += nw) {
-                // rank-s unexpanded entry
-                int found = 0, pos = -1;
-                const bool need_total = (s == 0);   // warp 0 also publishes how many nodes are expanded this step
-                for (int base = 0; base < n && (pos < 0 || (need_total && found < W)); base += 32) {
-                    int i = base + lane;
-                    u64 kx = (i < n) ? lst[i] : 1ull;
-                    unsigned m = __ballot_sync(DR_FULL, !(kx & 1ull));
-                    int c = __popc(m);
-                    if (pos < 0 && found + c > s) pos = base + (int)__fns(m, 0, s - found + 1);
-                    found += c;
-                }
-                if (need_total && lane == 0) {
-                    int tot = found < W ? found : W;
-                    if (ovf_full) { s_status |= DR_ST_VISITED_OVERFLOW; tot = 0; }
-                    s_ns = tot;
-                }
-                if (pos < 0 || ovf_full) continue;   // warp-uniform
-                if (lane == 0) s_sel[W + s] = (uint32_t)pos;
-                const uint32_t node = key_id(lst[pos]);
-                const uint32_t *row = a.adj + (size_t)node * R;
-                for (int j0 = 0; j0 < R; j0 += 32) {
-                    int j = j0 + lane;
-                    uint32_t nb = (j < R) ? __ldg(row + j) : DR_EMPTY;
-                    bool valid = (j < R) && ((long long)nb < a.N);
-                    if (valid && a.deleted) valid = a.deleted[nb] == 0;
-                    bool isnew = false;   // equal ids in one row (0-padding): the CAS admits exactly one of them
-                    if (valid) isnew = visited_insert(nb, s_hash, hmask, use_ovf_now, my_ovf, ovf_mask);
-                    unsigned m = __ballot_sync(DR_FULL, isnew);
-                    int cnt = __popc(m);
-                    int basepos = 0;
-                    if (cnt) {
-                        if (lane == 0) basepos = atomicAdd(p_nn, cnt);
-                        basepos = __shfl_sync(DR_FULL, basepos, 0);
-                    }
-                    if (isnew) s_newid[basepos + __popc(m & lt_mask)] = nb;
-                }
-            }
-            __syncthreads();
-            const int ns = s_ns;
-            if (ns == 0) break;
-            const bool use_ovf = use_ovf_now;
-            if (tid < ns) lst[s_sel[W + tid]] |= 1ull;        // mark the expanded entries (merge reads them after the next barrier)
-            if (tid == 0) s_nn2[(step + 1) & 1] = 0;          // next step's newcomer counter
-            ++step;
-            // (3) quantised ADC of the newcomers; the survivors are appended compactly
-            const int nn = *p_nn;
-            const bool full = (n >= L);
-            const u64 worstk = lst[n - 1] & ~1ull;
-            if (wordpath) {
-                constexpr int G = 4;
-                for (int base = wid; base < nn; base += nw * G) {
-                    uint32_t gid[G], gs[G];
-                    int cnt = 0;
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const int i = base + g * nw;
-                        gid[g] = 0u;
-                        if (i < nn) { gid[g] = s_newid[i]; cnt = g + 1; }
-                    }
-                    adc_u8_group<G>(a.codes, M, s_lut, gid, cnt, lane, gs);
-                    {   // lane g owns key g; one aggregated counter update per group
-                        uint32_t mysum = gs[0], myid = gid[0];
-#pragma unroll
-                        for (int g = 1; g < G; ++g) if (lane == g) { mysum = gs[g]; myid = gid[g]; }
-                        const u64 key = make_ikey(mysum, myid);
-                        const bool ok = lane < cnt && (!full || key < worstk);
-                        const unsigned okm = __ballot_sync(DR_FULL, ok);
-                        if (okm) {
-                            int basep = 0;
-                            if (lane == 0) basep = atomicAdd(&s_mvalid, __popc(okm));
-                            basep = __shfl_sync(DR_FULL, basep, 0);
-                            if (ok) {
-                                s_newk[basep + __popc(okm & lt_mask)] = key;
-                                if (a.prefetch) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)myid * R));
-                            }
-                        }
-                    }
-                }
-            } else {
-                for (int i = wid; i < nn; i += nw) {
-                    uint32_t id = s_newid[i];
-                    uint32_t sum = adc_u8_warp(a.codes + (size_t)id * M, s_lut, M, lane);
-                    if (lane == 0) {
-                        u64 key = make_ikey(sum, id);
-                        if (!full || key < worstk) s_newk[atomicAdd(&s_mvalid, 1)] = key;
-                    }
-                }
-            }
-            if (tid == 0) {
-                if (use_ovf) s_ovfcount += nn; else s_hcount += nn;
-            }
-            __syncthreads();
-            nvis += nn;
-            hops += ns;
-            const int mv = s_mvalid;
-            // (4) merge.  Up to 32 survivors: warp 0 sorts them in registers (bitonic, shuffles), then every item finds
-            //     its slot by binary search in the other sequence.  More than 32 (first steps only): rank counting.
-            if (mv > 0) {
-                const int total = n + mv;
-                if (mv <= 32) {
-                    if (wid == 0) {
-                        u64 key = lane < mv ? s_newk[lane] : DR_KEY_MAX;
-#pragma unroll
-                        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
-                            for (int j = k2 >> 1; j > 0; j >>= 1) {
-                                const u64 other = __shfl_xor_sync(DR_FULL, key, j);
-                                const bool up = ((lane & k2) == 0);            // ascending block
-                                const bool lower = ((lane & j) == 0);          // this lane keeps the smaller of the pair
-                                const bool take_min = (up == lower);
-                                const u64 mn = key < other ? key : other, mx = key < other ? other : key;
-                                key = take_min ? mn : mx;
-                            }
-                        }
-                        if (lane < mv) s_newk[lane] = key;
-                    }
-                    __syncthreads();
-                    for (int x = tid; x < total; x += nt) {
-                        u64 key;
-                        int pos;
-                        if (x < n) {
-                            key = lst[x];
-                            int lo = 0, hi = mv;                               // new keys smaller than this old entry
-                            while (lo < hi) {
-                                int mid = (lo + hi) >> 1;
-                                if (s_newk[mid] < key) lo = mid + 1; else hi = mid;
-                            }
-                            pos = x + lo;
-                        } else {
-                            const int j = x - n;
-                            key = s_newk[j];
-                            int lo = 0, hi = n;
-                            while (lo < hi) {
-                                int mid = (lo + hi) >> 1;
-                                if (lst[mid] < key) lo = mid + 1; else hi = mid;
-                            }
-                            pos = lo + j;
-                        }
-                        if (pos < L) oth[pos] = key;
-                    }
-                } else {
-                    for (int x = tid; x < total; x += nt) {
-                        u64 key;
-                        int pos;
-                        if (x < n) {
-                            key = lst[x];
-                            int c = 0;
-                            for (int j = 0; j < mv; ++j) c += (s_newk[j] < key) ? 1 : 0;
-                            pos = x + c;
-                        } else {
-                            key = s_newk[x - n];
-                            int c = 0;
-                            for (int j = 0; j < mv; ++j) c += (s_newk[j] < key) ? 1 : 0;
-                            int lo = 0, hi = n;
-                            while (lo < hi) {
-                                int mid = (lo + hi) >> 1;
-                                if (lst[mid] < key) lo = mid + 1; else hi = mid;
-                            }
-                            pos = lo + c;
-                        }
-                        if (pos < L) oth[pos] = key;
-                    }
-                }
-                cur ^= 1;
-                n = total < L ? total : L;
-                __syncthreads();   // the next step's scans read the merged list
-            }
-        }
-
-        const u64 *lst = cur ? s_list1 : s_list0;
-        const float sc = a.lut_scale[b], off = a.lut_offset[b];
-        if (a.list_ids) {
-            for (int i = tid; i < L; i += nt) {
-                a.list_ids[(size_t)b * L + i] = i < n ? (int32_t)key_id(lst[i]) : -1;
-                if (a.list_dist)
-                    a.list_dist[(size_t)b * L + i] = i < n ? __fmaf_rn(sc, (float)(uint32_t)(lst[i] >> 32), off) : __int_as_float(0x7f800000);
-            }
-        }
-        const int k = a.k;
-        if (a.rerank) {
-            for (int i = wid; i < n; i += 2 * nw) {
-                const int i2 = i + nw;
-                if (i2 < n) {
-                    float dA, dB;
-                    warp_l2sq_x2(a.vec + (size_t)key_id(lst[i]) * D, a.vec + (size_t)key_id(lst[i2]) * D, s_q, D, lane, dA, dB);
-                    if (lane == 0) {
-                        s_rrk[i] = ((u64)f2ord(dA + 0.0f) << 32) | (u64)i;
-                        s_rrk[i2] = ((u64)f2ord(dB + 0.0f) << 32) | (u64)i2;
-                    }
-                } else {
-                    float d2 = warp_l2sq(a.vec + (size_t)key_id(lst[i]) * D, s_q, D, lane);
-                    if (lane == 0) s_rrk[i] = ((u64)f2ord(d2 + 0.0f) << 32) | (u64)i;
-                }
-            }
-            __syncthreads();
-            for (int i = tid; i < n; i += nt) {
-                u64 key = s_rrk[i];
-                int pos = 0;
-                for (int j = 0; j < n; ++j) pos += (s_rrk[j] < key) ? 1 : 0;
-                if (pos < k) {
-                    float d2 = ord2f((uint32_t)(key >> 32));
-                    a.out_ids[(size_t)b * k + pos] = (int32_t)key_id(lst[i]);
-                    if (a.out_dist) a.out_dist[(size_t)b * k + pos] = a.sqrt_out ? sqrtf(d2) : d2;
-                }
-            }
-        } else {
-            for (int i = tid; i < n && i < k; i += nt) {
-                float d = __fmaf_rn(sc, (float)(uint32_t)(lst[i] >> 32), off);
-                a.out_ids[(size_t)b * k + i] = (int32_t)key_id(lst[i]);
-                if (a.out_dist) a.out_dist[(size_t)b * k + i] = a.sqrt_out ? sqrtf(fmaxf(d, 0.0f)) : d;
-            }
-        }
-        for (int i = n + tid; i < k; i += nt) {
-            a.out_ids[(size_t)b * k + i] = -1;
-            if (a.out_dist) a.out_dist[(size_t)b * k + i] = __int_as_float(0x7f800000);
-        }
-        if (tid == 0) {
-            if (a.out_hops) a.out_hops[b] = hops;
-            if (a.out_visited) a.out_visited[b] = nvis;
-            if (a.list_len) a.list_len[b] = n;
-            if (a.status) a.status[b] = s_status;
-        }
-        if (s_ovfused) {
-            for (uint32_t i = tid; i < a.ovf_cap; i += nt) my_ovf[i] = DR_EMPTY;
-        }
-    }
-}
-
-int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
-                        float *d_offset, float *d_mn, unsigned *d_range, cudaStream_t s);
-
-static int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, int32_t *ids, float *dist,
-                              int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist, int32_t *list_len,
-                              int32_t *status, cudaStream_t s) {
-    DR_CHECK(h->d_codes && h->d_codebook && h->M > 0, "dr_search: the u8-table mode needs PQ codes and the codebook");
-    FastArgs a;
-    memset(&a, 0, sizeof(a));
-    a.vec = h->d_vec; a.adj = h->d_adj; a.codes = h->d_codes; a.deleted = h->d_deleted;
-    a.N = h->N; a.D = h->D; a.R = h->R; a.M = h->M;
-    a.k = p->k; a.L = p->L; a.W = p->W; a.rerank = p->rerank; a.sqrt_out = p->sqrt_out; a.prefetch = p->prefetch;
-    a.start = (uint32_t)h->medoid;
-    int off = ((h->M * 256 + 15) / 16) * 16;
-    a.o_q = off; off += p->rerank ? ((h->D * 4 + 15) / 16) * 16 : 0;
-    const int LC = (p->L + 2) & ~1;
-    a.o_list0 = off; off += LC * 8;
-    a.o_list1 = off; off += LC * 8;
-    const int NC = (p->W * h->R + 1) & ~1;
-    a.o_newk = off; off += NC * 8;
-    a.o_newid = off; off += NC * 4;
-    a.o_sel = off; off += ((2 * p->W * 4 + 7) / 8) * 8;
-    a.o_hash = off;
-    const int fixed = off;
-    // visited table: enough for the typical visit count at <= 3/4 load, then whatever keeps 3 CTAs per SM
-    uint32_t hc;
-    int min_hash = 1024;
-    while (min_hash * 4 < p->L * 8) min_hash <<= 1;
-    if (p->hash_cap > 0) hc = (uint32_t)p->hash_cap;
-    else {
-        uint32_t want = 1024;
-        long long target = (long long)(p->L + 2 * p->W) * h->R;
-        while ((long long)want * 3 / 4 < target && want < 65536) want <<= 1;
-        hc = want;
-        // prefer three CTAs per SM: shrink the table down to 4096 slots to get there (the overflow table takes the tail)
-        while (hc > 4096 && fixed + (int)hc * 4 + 1024 > h->smem_optin / 3) hc >>= 1;
-        while ((int)hc > min_hash && fixed + (int)hc * 4 + 256 > h->smem_optin) hc >>= 1;
-    }
-    DR_CHECK((hc & (hc - 1)) == 0 && hc >= 64 && (int)hc * 4 >= p->L * 8 && fixed + (int)hc * 4 + 256 <= h->smem_optin,
-             "dr_search(u8): visited table of %u slots is not usable (power of two, >= 64, >= 2L, %d B of shared memory needed)",
-             hc, fixed + (int)hc * 4);
-    a.hash_cap = hc;
-    const int smem = fixed + (int)hc * 4;
-    const int nt = 256;
-    DR_CUDA(cudaFuncSetAttribute(search_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 0;
-    DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_fast_kernel, nt, smem));
-    DR_CHECK(occ >= 1, "dr_search(u8): kernel does not fit (smem %d)", smem);
-    const int max_grid = h->sms * occ;
-    a.ovf_cap = 65536;
-    size_t need = (size_t)max_grid * a.ovf_cap * 4;
-    if (h->ovf_bytes < need) {
-        if (h->d_ovf) cudaFree(h->d_ovf);
-        h->d_ovf = nullptr; h->ovf_bytes = 0;
-        DR_CUDA(cudaMalloc(&h->d_ovf, need));
-        h->ovf_bytes = need;
-        DR_CUDA(cudaMemsetAsync(h->d_ovf, 0xFF, need, s));
-    }
-    a.ovf = h->d_ovf;
-    if (!h->d_counter) DR_CUDA(cudaMalloc(&h->d_counter, sizeof(u64)));
-    a.counter = h->d_counter;
-
-    const size_t per_q = (size_t)h->M * 256;
-    int64_t cap = (int64_t)((size_t)4 << 30) / (int64_t)per_q;
-    if (p->chunk > 0) cap = p->chunk;
-    if (cap < 1) cap = 1;
-    const int64_t nchunks = (B + cap - 1) / cap;
-    const int64_t chunk = (B + nchunks - 1) / nchunks;
-    // scratch: table | scale | offset | mn | range
-    const size_t sz_tab = (size_t)chunk * per_q;
-    const size_t sz_f = ((size_t)chunk * 4 + 255) / 256 * 256;
-    const size_t sz_mn = ((size_t)chunk * h->M * 4 + 255) / 256 * 256;
-    if (dr_scratch((void **)&h->d_lut, &h->lut_bytes, sz_tab + 3 * sz_f + sz_mn)) return 1;
-    uint8_t *d_tab = reinterpret_cast<uint8_t *>(h->d_lut);
-    float *d_scale = reinterpret_cast<float *>(d_tab + sz_tab);
-    float *d_off = reinterpret_cast<float *>(d_tab + sz_tab + sz_f);
-    unsigned *d_range = reinterpret_cast<unsigned *>(d_tab + sz_tab + 2 * sz_f);
-    float *d_mn = reinterpret_cast<float *>(d_tab + sz_tab + 3 * sz_f);
-
-    for (int64_t c0 = 0; c0 < B; c0 += chunk) {
-        const int64_t cb = (B - c0 < chunk) ? (B - c0) : chunk;
-        if (launch_lut_build_u8(h->d_codebook, d_Q + (size_t)c0 * h->D, cb, h->D, h->M, d_tab, d_scale, d_off, d_mn, d_range, s)) return 1;
-        a.Q = d_Q + (size_t)c0 * h->D; a.lut8 = d_tab; a.lut_scale = d_scale; a.lut_offset = d_off; a.B = cb;
-        a.out_ids = ids + (size_t)c0 * p->k;
-        a.out_dist = dist ? dist + (size_t)c0 * p->k : nullptr;
-        a.out_hops = hops ? hops + c0 : nullptr;
-        a.out_visited = visited ? visited + c0 : nullptr;
-        a.list_ids = list_ids ? list_ids + (size_t)c0 * p->L : nullptr;
-        a.list_dist = list_dist ? list_dist + (size_t)c0 * p->L : nullptr;
-        a.list_len = list_len ? list_len + c0 : nullptr;
-        a.status = status ? status + c0 : nullptr;
-        DR_CUDA(cudaMemsetAsync(h->d_counter, 0, sizeof(u64), s));
-        int grid = (int)((cb < (int64_t)max_grid) ? cb : max_grid);
-        if (h->timing) DR_CUDA(cudaEventRecord(h->ev0, s));
-        search_fast_kernel<<<grid, nt, smem, s>>>(a);
-        DR_LAUNCHED();
-        if (h->timing) {
-            DR_CUDA(cudaEventRecord(h->ev1, s));
-            DR_CUDA(cudaEventSynchronize(h->ev1));
-            float ms = 0.f;
-            DR_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-            h->timed_ms += ms;
-            h->timed_launches += 1;
-        }
-    }
-    return 0;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // host launcher

@@ -1,0 +1,584 @@
+// search_fast.cu — K1f: the throughput form of the batched Vamana beam search (same path as search.cu:
+// greedy_search_cython + compute_query_distance, cython_utils.pyx:72-122 / vamana_graph.py:301-329, followed by
+// the exact rerank of search_engine.py:374-379), one CTA per query, W expansions per step.
+//
+// What differs from the reference-order kernel (search.cu):
+//   * the ADC table is 8-bit (pq.cu: launch_lut_build_u8): M x 256 BYTES (48 KB at M = 192 instead of 192 KB),
+//     so three CTAs share an SM; a distance is an exact integer sum of table bytes, hence independent of the
+//     summation order; keys are (sum, id) and unique, so the merge is a pure key-order merge.
+//   * shared-memory table layout is centroid-major, one 32-bit word = the entries of 4 consecutive subspaces for
+//     one centroid: lane l owns code word l of a row and its four lookups all fall into bank l whatever the code
+//     bytes are (no bank conflicts on the first 128 subspaces of a row; the tail words of two rows share a pass).
+//   * code words of 4 rows are fetched before any lookup (memory-level parallelism), survivors are compacted,
+//     small survivor sets are merged by rank counting, larger ones by per-warp bitonic sorts + binary-search ranks.
+// Restated bit-for-bit by oracle.c (dist_mode 4, orc_search_list with strict_ties = 0).
+#include "common.cuh"
+
+extern __shared__ __align__(16) unsigned char dr_smem[];
+
+struct FastArgs {
+    const float *vec; const uint32_t *adj; const uint8_t *codes; const uint8_t *deleted;
+    const float *Q; const uint8_t *lut8; const float *lut_scale; const float *lut_offset;
+    long long N; int D, R, M;
+    long long B; int k, L, W;
+    int rerank, sqrt_out, prefetch;
+    uint32_t start;
+    int32_t *out_ids; float *out_dist; int32_t *out_hops; int32_t *out_visited;
+    int32_t *list_ids; float *list_dist; int32_t *list_len; int32_t *status;
+    u64 *counter;
+    uint32_t *ovf; uint32_t ovf_cap; uint32_t hash_cap;
+    int o_q, o_list0, o_list1, o_newk, o_newid, o_sel, o_hash;
+};
+
+__device__ __forceinline__ u64 make_ikey(uint32_t sum, uint32_t id) { return ((u64)sum << 32) | ((u64)id << 1); }
+
+// ---- byte path (M % 4 != 0): table [m][c], one row per warp -------------------------------------------
+__device__ __forceinline__ uint32_t adc_u8_warp(const uint8_t *__restrict__ code, const uint8_t *__restrict__ lut8, int M, int lane) {
+    uint32_t acc = 0u;
+    for (int m = lane; m < M; m += 32) acc += lut8[(m << 8) + __ldg(code + m)];
+    return __reduce_add_sync(DR_FULL, acc);
+}
+
+// ---- word path ---------------------------------------------------------------------------------------
+// Shared-memory layout of the table for words = M / 4 code words per row, nfull = words / 32, rem = words % 32:
+//   entry (word w, centroid c, byte j) = subspace 4w + j:
+//     w <  32 nfull : (w / 32) * 32768 + c * 128     + (w % 32) * 4      + j      (bank = w % 32)
+//     w >= 32 nfull : nfull * 32768    + c * 4 * rem + (w - 32 nfull) * 4 + j
+// tb points at the lane's word of centroid 0; the four entries selected by the code word's bytes are summed.
+template <int STRIDE>
+__device__ __forceinline__ uint32_t tab_sum4(const uint8_t *__restrict__ tb, uint32_t w, int stride_rt) {
+    const int st = STRIDE ? STRIDE : stride_rt;
+    const uint32_t c0 = w & 0xFFu, c1 = (w >> 8) & 0xFFu, c2 = (w >> 16) & 0xFFu, c3 = w >> 24;
+    return (uint32_t)tb[c0 * st] + (uint32_t)tb[c1 * st + 1] + (uint32_t)tb[c2 * st + 2] + (uint32_t)tb[c3 * st + 3];
+}
+
+// G code rows per warp (G even): lane l owns word 32 k + l of every full chunk; the tail words (rem <= 16) of TWO
+// rows share one pass (lanes 0-15 row 2p, lanes 16-31 row 2p+1).  All code-word loads are issued before any lookup.
+// Every ids[g] must be a valid row (callers pad a short group by repeating an id).
+template <int WORDS, int G>
+__device__ __forceinline__ void adc_u8_rows(const uint8_t *__restrict__ codes, int M, const uint8_t *__restrict__ tab,
+                                            const uint32_t (&ids)[G], int lane, uint32_t (&out)[G]) {
+    const int words = WORDS ? WORDS : (M >> 2);
+    const int nfull = words >> 5, rem = words & 31;
+    const bool pair = rem > 0 && rem <= 16;
+    const int hl = lane & 15;
+    const uint32_t *rowp[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) rowp[g] = reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M);
+    uint32_t wf[2][G], wt[G];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (k < nfull) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) wf[k][g] = __ldg(rowp[g] + 32 * k + lane);
+        }
+    }
+    if (pair) {
+#pragma unroll
+        for (int p = 0; p < G / 2; ++p) {
+            const uint32_t *rp = (lane < 16) ? rowp[2 * p] : rowp[2 * p + 1];
+            wt[p] = (hl < rem) ? __ldg(rp + 32 * nfull + hl) : 0u;
+        }
+    } else if (rem) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) wt[g] = (lane < rem) ? __ldg(rowp[g] + 32 * nfull + lane) : 0u;
+    }
+    uint32_t acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0u;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (k < nfull) {
+            const uint8_t *tb = tab + k * 32768 + lane * 4;
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g] += tab_sum4<128>(tb, wf[k][g], 128);
+        }
+    }
+    if (pair) {
+        const uint8_t *tb = tab + nfull * 32768 + hl * 4;
+        const int st = rem * 4;
+#pragma unroll
+        for (int p = 0; p < G / 2; ++p) {
+            const uint32_t u = (hl < rem) ? tab_sum4<0>(tb, wt[p], st) : 0u;
+            acc[2 * p] += (lane < 16) ? u : 0u;
+            acc[2 * p + 1] += (lane < 16) ? 0u : u;
+        }
+    } else if (rem) {
+        const uint8_t *tb = tab + nfull * 32768 + lane * 4;
+        const int st = rem * 4;
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] += (lane < rem) ? tab_sum4<0>(tb, wt[g], st) : 0u;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) out[g] = __reduce_add_sync(DR_FULL, acc[g]);
+}
+
+// number of keys of the sorted sequence a[0..n) that are smaller than key
+__device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+#define DR_MERGE_LINEAR 8   // up to this many survivors: rank by counting, no sort
+
+// WORDS > 0: compile-time M / 4;  WORDS == 0: runtime M (M % 4 == 0, M <= 256);  WORDS < 0: byte path (any M)
+template <int WORDS>
+__global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
+    constexpr bool WP = WORDS >= 0;
+    uint8_t *s_lut = dr_smem;
+    float *s_q = reinterpret_cast<float *>(dr_smem + a.o_q);
+    u64 *s_list0 = reinterpret_cast<u64 *>(dr_smem + a.o_list0);
+    u64 *s_list1 = reinterpret_cast<u64 *>(dr_smem + a.o_list1);
+    u64 *s_newk = reinterpret_cast<u64 *>(dr_smem + a.o_newk);
+    uint32_t *s_newid = reinterpret_cast<uint32_t *>(dr_smem + a.o_newid);
+    uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);
+    uint32_t *s_hash = reinterpret_cast<uint32_t *>(dr_smem + a.o_hash);
+    u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_hash);   // rerank keys alias the (dead) visited table
+
+    __shared__ long long s_b;
+    __shared__ __align__(8) uint64_t s_lutbar;
+    __shared__ int s_nn2[2], s_ns, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int D = a.D, R = a.R, M = a.M, L = a.L, W = a.W;
+    const int words = WORDS > 0 ? WORDS : (M >> 2);
+    const uint32_t hmask = a.hash_cap - 1u, ovf_mask = a.ovf_cap - 1u;
+    const int hlimit = (int)(a.hash_cap - (a.hash_cap >> 2));
+    const int ovf_limit = (int)(a.ovf_cap - (a.ovf_cap >> 2));
+    uint32_t *my_ovf = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
+    uint32_t lut_phase = 0;
+    if (!WP && tid == 0) { mbar_init(&s_lutbar, 1); fence_mbar_init(); }
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_b = (long long)atomicAdd(a.counter, 1ull);
+        __syncthreads();
+        const long long b = s_b;
+        if (b >= a.B) break;
+
+        // ---- stage the query's table (permuting load: global [w][c][4] -> bank-per-lane layout), the query, the hash
+        if (tid == 0) { s_hcount = 1; s_ovfcount = 0; s_ovfused = 0; s_status = 0; s_nn2[0] = 0; }
+        if (WP) {
+            const int nfull = words >> 5, rem = words & 31;
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.lut8 + (size_t)b * M * 256);
+            const int total = words * 32;          // unit = 8 centroids of one code word (2 x 16 B)
+            constexpr int UB = 3;
+            for (int u0 = tid; u0 < total; u0 += nt * UB) {
+                uint4 v[UB][2];
+#pragma unroll
+                for (int i = 0; i < UB; ++i) {
+                    const int u = u0 + i * nt;
+                    if (u < total) {
+                        const int cg = u / words, w = u - cg * words;   // consecutive lanes -> consecutive words (banks)
+                        const uint4 *p = src + (w * 64 + cg * 2);
+                        v[i][0] = __ldg(p); v[i][1] = __ldg(p + 1);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < UB; ++i) {
+                    const int u = u0 + i * nt;
+                    if (u < total) {
+                        const int cg = u / words, w = u - cg * words;
+                        uint32_t *dst; int sw;
+                        if (w < nfull * 32) { dst = reinterpret_cast<uint32_t *>(s_lut + (w >> 5) * 32768) + (w & 31); sw = 32; }
+                        else { dst = reinterpret_cast<uint32_t *>(s_lut + nfull * 32768) + (w - nfull * 32); sw = rem; }
+                        dst += cg * 8 * sw;
+                        dst[0] = v[i][0].x; dst[sw] = v[i][0].y; dst[2 * sw] = v[i][0].z; dst[3 * sw] = v[i][0].w;
+                        dst[4 * sw] = v[i][1].x; dst[5 * sw] = v[i][1].y; dst[6 * sw] = v[i][1].z; dst[7 * sw] = v[i][1].w;
+                    }
+                }
+            }
+        } else if (tid == 0) {
+            mbar_expect_tx(&s_lutbar, (uint32_t)M * 256u);
+            bulk_g2s(s_lut, a.lut8 + (size_t)b * M * 256, (uint32_t)M * 256u, &s_lutbar);
+        }
+        if (a.rerank) {
+            const float *qg = a.Q + (size_t)b * D;
+            for (int i = tid; i < D; i += nt) s_q[i] = __ldg(qg + i);
+        }
+        for (uint32_t i = tid; i < a.hash_cap; i += nt) s_hash[i] = DR_EMPTY;
+        if (!WP) { mbar_wait(&s_lutbar, lut_phase); lut_phase ^= 1u; }
+        __syncthreads();
+
+        if (wid == 0) {
+            uint32_t s0;
+            if (WP) {
+                const uint32_t gid[2] = {a.start, a.start};
+                uint32_t gs[2];
+                adc_u8_rows<(WORDS > 0 ? WORDS : 0), 2>(a.codes, M, s_lut, gid, lane, gs);
+                s0 = gs[0];
+            } else {
+                s0 = adc_u8_warp(a.codes + (size_t)a.start * M, s_lut, M, lane);
+            }
+            if (lane == 0) {
+                s_list0[0] = make_ikey(s0, a.start);
+                s_hash[hash_u32(a.start) & hmask] = a.start;
+            }
+        }
+        int cur = 0, n = 1, hops = 0, nvis = 1, step = 0;
+        __syncthreads();
+
+        for (;;) {
+            u64 *lst = cur ? s_list1 : s_list0;
+            u64 *oth = cur ? s_list0 : s_list1;
+            // (1+2) warp s finds the s-th unexpanded entry itself (no marking yet, so the scans do not race), loads
+            //       that node's adjacency row and claims its first-seen neighbours
+            int *p_nn = &s_nn2[step & 1];
+            const bool use_ovf_now = (s_hcount + W * R > hlimit);   // same value for every thread (read after the last barrier)
+            if (tid == 0) {
+                s_mvalid = 0;
+                if (use_ovf_now) s_ovfused = 1;
+            }
+            const bool ovf_full = use_ovf_now && (s_ovfcount + W * R > ovf_limit);
+            for (int s = wid; s < W; s += nw) {
+                int found = 0, pos = -1;
+                const bool need_total = (s == 0);   // warp 0 also publishes how many nodes are expanded this step
+                for (int base = 0; base < n && (pos < 0 || (need_total && found < W)); base += 32) {
+                    const int i = base + lane;
+                    const bool un = (i < n) && !(lst[i] & 1ull);
+                    const unsigned m = __ballot_sync(DR_FULL, un);
+                    const int c = __popc(m);
+                    if (pos < 0 && found + c > s) {
+                        const unsigned hit = __ballot_sync(DR_FULL, un && (__popc(m & lt_mask) == s - found));
+                        pos = base + __ffs(hit) - 1;
+                    }
+                    found += c;
+                }
+                if (need_total && lane == 0) {
+                    int tot = found < W ? found : W;
+                    if (ovf_full) { s_status |= DR_ST_VISITED_OVERFLOW; tot = 0; }
+                    s_ns = tot;
+                }
+                if (pos < 0 || ovf_full) continue;   // warp-uniform
+                if (lane == 0) s_sel[W + s] = (uint32_t)pos;
+                const uint32_t node = key_id(lst[pos]);
+                const uint32_t *row = a.adj + (size_t)node * R;
+                for (int j0 = 0; j0 < R; j0 += 32) {
+                    const int j = j0 + lane;
+                    const uint32_t nb = (j < R) ? __ldg(row + j) : DR_EMPTY;
+                    bool valid = (j < R) && ((long long)nb < a.N);
+                    if (valid && a.deleted) valid = a.deleted[nb] == 0;
+                    bool isnew = false;   // equal ids in one row (0-padding): the CAS admits exactly one of them
+                    if (valid) isnew = visited_insert(nb, s_hash, hmask, use_ovf_now, my_ovf, ovf_mask);
+                    const unsigned m = __ballot_sync(DR_FULL, isnew);
+                    const int cnt = __popc(m);
+                    int basepos = 0;
+                    if (cnt) {
+                        if (lane == 0) basepos = atomicAdd(p_nn, cnt);
+                        basepos = __shfl_sync(DR_FULL, basepos, 0);
+                    }
+                    if (isnew) s_newid[basepos + __popc(m & lt_mask)] = nb;
+                }
+            }
+            __syncthreads();
+            const int ns = s_ns;
+            if (ns == 0) break;
+            const bool use_ovf = use_ovf_now;
+            if (tid < ns) lst[s_sel[W + tid]] |= 1ull;        // mark the expanded entries (merge reads them after the next barrier)
+            if (tid == 0) s_nn2[(step + 1) & 1] = 0;          // next step's newcomer counter
+            ++step;
+            // (3) quantised ADC of the newcomers; the survivors are appended compactly
+            const int nn = *p_nn;
+            const bool full = (n >= L);
+            const u64 worstk = lst[n - 1] & ~1ull;
+            if (WP) {
+                constexpr int G = 4;
+                for (int base = wid; base < nn; base += nw * G) {
+                    uint32_t gid[G], gs[G];
+                    int cnt = 1;
+                    gid[0] = s_newid[base];
+#pragma unroll
+                    for (int g = 1; g < G; ++g) {
+                        const int i = base + g * nw;
+                        gid[g] = gid[0];                        // pad a short group with a valid row
+                        if (i < nn) { gid[g] = s_newid[i]; cnt = g + 1; }
+                    }
+                    adc_u8_rows<(WORDS > 0 ? WORDS : 0), G>(a.codes, M, s_lut, gid, lane, gs);
+                    // lane g owns key g; one aggregated counter update per group
+                    uint32_t mysum = gs[0], myid = gid[0];
+#pragma unroll
+                    for (int g = 1; g < G; ++g) if (lane == g) { mysum = gs[g]; myid = gid[g]; }
+                    const u64 key = make_ikey(mysum, myid);
+                    const bool ok = lane < cnt && (!full || key < worstk);
+                    const unsigned okm = __ballot_sync(DR_FULL, ok);
+                    if (okm) {
+                        int basep = 0;
+                        if (lane == 0) basep = atomicAdd(&s_mvalid, __popc(okm));
+                        basep = __shfl_sync(DR_FULL, basep, 0);
+                        if (ok) {
+                            s_newk[basep + __popc(okm & lt_mask)] = key;
+                            if (a.prefetch) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)myid * R));
+                        }
+                    }
+                }
+            } else {
+                for (int i = wid; i < nn; i += nw) {
+                    const uint32_t id = s_newid[i];
+                    const uint32_t sum = adc_u8_warp(a.codes + (size_t)id * M, s_lut, M, lane);
+                    if (lane == 0) {
+                        const u64 key = make_ikey(sum, id);
+                        if (!full || key < worstk) s_newk[atomicAdd(&s_mvalid, 1)] = key;
+                    }
+                }
+            }
+            if (tid == 0) {
+                if (use_ovf) s_ovfcount += nn; else s_hcount += nn;
+            }
+            __syncthreads();
+            nvis += nn;
+            hops += ns;
+            const int mv = s_mvalid;
+            // (4) merge (keys are unique, so ranks are exact):
+            //     few survivors   : rank = count of smaller newcomers (no sort, no extra barrier)
+            //     up to 32 per warp: every warp bitonic-sorts one 32-key chunk in registers, then every item sums its
+            //                        binary-search ranks in the other sorted sequences
+            //     more            : rank counting over all newcomers
+            if (mv > 0) {
+                const int total = n + mv;
+                if (mv <= DR_MERGE_LINEAR) {
+                    for (int x = tid; x < total; x += nt) {
+                        u64 key;
+                        int pos;
+                        if (x < n) { key = lst[x]; pos = x; }
+                        else { key = s_newk[x - n]; pos = lower_bound_u64(lst, n, key); }
+                        for (int j = 0; j < mv; ++j) pos += (s_newk[j] < key) ? 1 : 0;
+                        if (pos < L) oth[pos] = key;
+                    }
+                } else if (mv <= 32 * nw) {
+                    const int nch = (mv + 31) >> 5;
+                    if (wid < nch) {
+                        const int idx = (wid << 5) + lane;
+                        u64 key = idx < mv ? s_newk[idx] : DR_KEY_MAX;
+#pragma unroll
+                        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                                const u64 other = __shfl_xor_sync(DR_FULL, key, j);
+                                const bool up = ((lane & k2) == 0);            // ascending block
+                                const bool lower = ((lane & j) == 0);          // this lane keeps the smaller of the pair
+                                const bool take_min = (up == lower);
+                                const u64 mn = key < other ? key : other, mx = key < other ? other : key;
+                                key = take_min ? mn : mx;
+                            }
+                        }
+                        if (idx < mv) s_newk[idx] = key;
+                    }
+                    __syncthreads();
+                    for (int x = tid; x < total; x += nt) {
+                        u64 key;
+                        int pos, own = -1;
+                        if (x < n) { key = lst[x]; pos = x; }
+                        else {
+                            const int j = x - n;
+                            key = s_newk[j];
+                            own = j >> 5;
+                            pos = (j & 31) + lower_bound_u64(lst, n, key);
+                        }
+                        for (int c = 0; c < nch; ++c) {
+                            if (c == own) continue;
+                            const int sz = (mv - (c << 5)) < 32 ? (mv - (c << 5)) : 32;
+                            pos += lower_bound_u64(s_newk + (c << 5), sz, key);
+                        }
+                        if (pos < L) oth[pos] = key;
+                    }
+                } else {
+                    for (int x = tid; x < total; x += nt) {
+                        u64 key;
+                        int pos;
+                        if (x < n) { key = lst[x]; pos = x; }
+                        else { key = s_newk[x - n]; pos = lower_bound_u64(lst, n, key); }
+                        for (int j = 0; j < mv; ++j) pos += (s_newk[j] < key) ? 1 : 0;
+                        if (pos < L) oth[pos] = key;
+                    }
+                }
+                cur ^= 1;
+                n = total < L ? total : L;
+                __syncthreads();   // the next step's scans read the merged list
+            }
+        }
+
+        const u64 *lst = cur ? s_list1 : s_list0;
+        const float sc = a.lut_scale[b], off = a.lut_offset[b];
+        if (a.list_ids) {
+            for (int i = tid; i < L; i += nt) {
+                a.list_ids[(size_t)b * L + i] = i < n ? (int32_t)key_id(lst[i]) : -1;
+                if (a.list_dist)
+                    a.list_dist[(size_t)b * L + i] = i < n ? __fmaf_rn(sc, (float)(uint32_t)(lst[i] >> 32), off) : __int_as_float(0x7f800000);
+            }
+        }
+        const int k = a.k;
+        if (a.rerank) {
+            for (int i = wid; i < n; i += 2 * nw) {
+                const int i2 = i + nw;
+                if (i2 < n) {
+                    float dA, dB;
+                    warp_l2sq_x2(a.vec + (size_t)key_id(lst[i]) * D, a.vec + (size_t)key_id(lst[i2]) * D, s_q, D, lane, dA, dB);
+                    if (lane == 0) {
+                        s_rrk[i] = ((u64)f2ord(dA + 0.0f) << 32) | (u64)i;
+                        s_rrk[i2] = ((u64)f2ord(dB + 0.0f) << 32) | (u64)i2;
+                    }
+                } else {
+                    float d2 = warp_l2sq(a.vec + (size_t)key_id(lst[i]) * D, s_q, D, lane);
+                    if (lane == 0) s_rrk[i] = ((u64)f2ord(d2 + 0.0f) << 32) | (u64)i;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += nt) {
+                u64 key = s_rrk[i];
+                int pos = 0;
+                for (int j = 0; j < n; ++j) pos += (s_rrk[j] < key) ? 1 : 0;
+                if (pos < k) {
+                    float d2 = ord2f((uint32_t)(key >> 32));
+                    a.out_ids[(size_t)b * k + pos] = (int32_t)key_id(lst[i]);
+                    if (a.out_dist) a.out_dist[(size_t)b * k + pos] = a.sqrt_out ? sqrtf(d2) : d2;
+                }
+            }
+        } else {
+            for (int i = tid; i < n && i < k; i += nt) {
+                float d = __fmaf_rn(sc, (float)(uint32_t)(lst[i] >> 32), off);
+                a.out_ids[(size_t)b * k + i] = (int32_t)key_id(lst[i]);
+                if (a.out_dist) a.out_dist[(size_t)b * k + i] = a.sqrt_out ? sqrtf(fmaxf(d, 0.0f)) : d;
+            }
+        }
+        for (int i = n + tid; i < k; i += nt) {
+            a.out_ids[(size_t)b * k + i] = -1;
+            if (a.out_dist) a.out_dist[(size_t)b * k + i] = __int_as_float(0x7f800000);
+        }
+        if (tid == 0) {
+            if (a.out_hops) a.out_hops[b] = hops;
+            if (a.out_visited) a.out_visited[b] = nvis;
+            if (a.list_len) a.list_len[b] = n;
+            if (a.status) a.status[b] = s_status;
+        }
+        if (s_ovfused) {
+            for (uint32_t i = tid; i < a.ovf_cap; i += nt) my_ovf[i] = DR_EMPTY;
+        }
+    }
+}
+
+typedef void (*fast_kernel_t)(const FastArgs);
+
+static fast_kernel_t pick_fast_kernel(int M) {
+    if ((M & 3) != 0 || M > 256) return search_fast_kernel<-1>;
+    switch (M >> 2) {
+        case 16: return search_fast_kernel<16>;   // M = 64  (the adaptive default at D = 1536, adaptive_pq.py:81-108)
+        case 32: return search_fast_kernel<32>;   // M = 128
+        case 48: return search_fast_kernel<48>;   // M = 192
+        case 64: return search_fast_kernel<64>;   // M = 256
+        default: return search_fast_kernel<0>;
+    }
+}
+
+int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, int32_t *ids, float *dist,
+                       int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist, int32_t *list_len,
+                       int32_t *status, cudaStream_t s) {
+    DR_CHECK(h->d_codes && h->d_codebook && h->M > 0, "dr_search: the u8-table mode needs PQ codes and the codebook");
+    FastArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vec = h->d_vec; a.adj = h->d_adj; a.codes = h->d_codes; a.deleted = h->d_deleted;
+    a.N = h->N; a.D = h->D; a.R = h->R; a.M = h->M;
+    a.k = p->k; a.L = p->L; a.W = p->W; a.rerank = p->rerank; a.sqrt_out = p->sqrt_out; a.prefetch = p->prefetch;
+    a.start = (uint32_t)h->medoid;
+    const bool word_layout = ((h->M & 3) == 0) && h->M <= 256;
+    fast_kernel_t kern = pick_fast_kernel(h->M);
+    int off = ((h->M * 256 + 15) / 16) * 16;
+    a.o_q = off; off += p->rerank ? ((h->D * 4 + 15) / 16) * 16 : 0;
+    const int LC = (p->L + 2) & ~1;
+    a.o_list0 = off; off += LC * 8;
+    a.o_list1 = off; off += LC * 8;
+    const int NC = (p->W * h->R + 1) & ~1;
+    a.o_newk = off; off += NC * 8;
+    a.o_newid = off; off += NC * 4;
+    a.o_sel = off; off += ((2 * p->W * 4 + 7) / 8) * 8;
+    a.o_hash = off;
+    const int fixed = off;
+    // visited table: enough for the typical visit count at <= 3/4 load, then whatever keeps 3 CTAs per SM
+    uint32_t hc;
+    int min_hash = 1024;
+    while (min_hash * 4 < p->L * 8) min_hash <<= 1;
+    if (p->hash_cap > 0) hc = (uint32_t)p->hash_cap;
+    else {
+        uint32_t want = 1024;
+        long long target = (long long)(p->L + 2 * p->W) * h->R;
+        while ((long long)want * 3 / 4 < target && want < 65536) want <<= 1;
+        hc = want;
+        // prefer three CTAs per SM: shrink the table down to 4096 slots to get there (the overflow table takes the tail)
+        while (hc > 4096 && fixed + (int)hc * 4 + 1024 > h->smem_optin / 3) hc >>= 1;
+        while ((int)hc > min_hash && fixed + (int)hc * 4 + 256 > h->smem_optin) hc >>= 1;
+    }
+    DR_CHECK((hc & (hc - 1)) == 0 && hc >= 64 && (int)hc * 4 >= p->L * 8 && fixed + (int)hc * 4 + 256 <= h->smem_optin,
+             "dr_search(u8): visited table of %u slots is not usable (power of two, >= 64, >= 2L, %d B of shared memory needed)",
+             hc, fixed + (int)hc * 4);
+    a.hash_cap = hc;
+    const int smem = fixed + (int)hc * 4;
+    const int nt = 256;
+    DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem));
+    DR_CHECK(occ >= 1, "dr_search(u8): kernel does not fit (smem %d)", smem);
+    const int max_grid = h->sms * occ;
+    a.ovf_cap = 65536;
+    size_t need = (size_t)max_grid * a.ovf_cap * 4;
+    if (h->ovf_bytes < need) {
+        if (h->d_ovf) cudaFree(h->d_ovf);
+        h->d_ovf = nullptr; h->ovf_bytes = 0;
+        DR_CUDA(cudaMalloc(&h->d_ovf, need));
+        h->ovf_bytes = need;
+        DR_CUDA(cudaMemsetAsync(h->d_ovf, 0xFF, need, s));
+    }
+    a.ovf = h->d_ovf;
+    if (!h->d_counter) DR_CUDA(cudaMalloc(&h->d_counter, sizeof(u64)));
+    a.counter = h->d_counter;
+
+    const size_t per_q = (size_t)h->M * 256;
+    int64_t cap = (int64_t)((size_t)4 << 30) / (int64_t)per_q;
+    if (p->chunk > 0) cap = p->chunk;
+    if (cap < 1) cap = 1;
+    const int64_t nchunks = (B + cap - 1) / cap;
+    const int64_t chunk = (B + nchunks - 1) / nchunks;
+    // scratch: table | scale | offset | mn | range
+    const size_t sz_tab = (size_t)chunk * per_q;
+    const size_t sz_f = ((size_t)chunk * 4 + 255) / 256 * 256;
+    const size_t sz_mn = ((size_t)chunk * h->M * 4 + 255) / 256 * 256;
+    if (dr_scratch((void **)&h->d_lut, &h->lut_bytes, sz_tab + 3 * sz_f + sz_mn)) return 1;
+    uint8_t *d_tab = reinterpret_cast<uint8_t *>(h->d_lut);
+    float *d_scale = reinterpret_cast<float *>(d_tab + sz_tab);
+    float *d_off = reinterpret_cast<float *>(d_tab + sz_tab + sz_f);
+    unsigned *d_range = reinterpret_cast<unsigned *>(d_tab + sz_tab + 2 * sz_f);
+    float *d_mn = reinterpret_cast<float *>(d_tab + sz_tab + 3 * sz_f);
+
+    for (int64_t c0 = 0; c0 < B; c0 += chunk) {
+        const int64_t cb = (B - c0 < chunk) ? (B - c0) : chunk;
+        if (launch_lut_build_u8(h->d_codebook, d_Q + (size_t)c0 * h->D, cb, h->D, h->M, d_tab, d_scale, d_off, d_mn, d_range,
+                                word_layout ? 1 : 0, s))
+            return 1;
+        a.Q = d_Q + (size_t)c0 * h->D; a.lut8 = d_tab; a.lut_scale = d_scale; a.lut_offset = d_off; a.B = cb;
+        a.out_ids = ids + (size_t)c0 * p->k;
+        a.out_dist = dist ? dist + (size_t)c0 * p->k : nullptr;
+        a.out_hops = hops ? hops + c0 : nullptr;
+        a.out_visited = visited ? visited + c0 : nullptr;
+        a.list_ids = list_ids ? list_ids + (size_t)c0 * p->L : nullptr;
+        a.list_dist = list_dist ? list_dist + (size_t)c0 * p->L : nullptr;
+        a.list_len = list_len ? list_len + c0 : nullptr;
+        a.status = status ? status + c0 : nullptr;
+        DR_CUDA(cudaMemsetAsync(h->d_counter, 0, sizeof(u64), s));
+        int grid = (int)((cb < (int64_t)max_grid) ? cb : max_grid);
+        if (h->timing) DR_CUDA(cudaEventRecord(h->ev0, s));
+        kern<<<grid, nt, smem, s>>>(a);
+        DR_LAUNCHED();
+        if (h->timing) {
+            DR_CUDA(cudaEventRecord(h->ev1, s));
+            DR_CUDA(cudaEventSynchronize(h->ev1));
+            float ms = 0.f;
+            DR_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            h->timed_ms += ms;
+            h->timed_launches += 1;
+        }
+    }
+    return 0;
+}
