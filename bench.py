@@ -203,7 +203,7 @@ def run_ours(a):
     B, k = a.queries, a.k
     Q = synth_torch(B, a.dim, seed=20242, sample_seed=1000 + rank, device=dev)     # each rank: its own query shard
     p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut,
-                           prefetch=bool(a.prefetch))
+                           prefetch=int(a.prefetch))
     ids = torch.empty((B, k), dtype=torch.int32, device=dev); dd = torch.empty((B, k), dtype=torch.float32, device=dev)
     hops = torch.empty(B, dtype=torch.int32, device=dev); vis = torch.empty(B, dtype=torch.int32, device=dev)
     llen = torch.empty(B, dtype=torch.int32, device=dev); stat = torch.empty(B, dtype=torch.int32, device=dev)

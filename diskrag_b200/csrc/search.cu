@@ -542,7 +542,7 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
         DR_CUDA(cudaMemsetAsync(h->d_ovf, 0xFF, need, s));
     }
     a.ovf = h->d_ovf;
-    if (!h->d_counter) DR_CUDA(cudaMalloc(&h->d_counter, sizeof(u64)));
+    if (!h->d_counter) DR_CUDA(cudaMalloc(&h->d_counter, 16 * sizeof(u64)));
     a.counter = h->d_counter;
 
     // chunking bounds the internal LUT buffer

@@ -45,72 +45,158 @@ __device__ __forceinline__ uint32_t adc_u8_warp(const uint8_t *__restrict__ code
 //     w <  32 nfull : (w / 32) * 32768 + c * 128     + (w % 32) * 4      + j      (bank = w % 32)
 //     w >= 32 nfull : nfull * 32768    + c * 4 * rem + (w - 32 nfull) * 4 + j
 // tb points at the lane's word of centroid 0; the four entries selected by the code word's bytes are summed.
+// tb = 32-bit shared-memory address of the lane's word of centroid 0.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int J>
+__device__ __forceinline__ uint32_t lds_u8_off(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(J));
+    return v;
+}
 template <int STRIDE>
-__device__ __forceinline__ uint32_t tab_sum4(const uint8_t *__restrict__ tb, uint32_t w, int stride_rt) {
-    const int st = STRIDE ? STRIDE : stride_rt;
-    const uint32_t c0 = w & 0xFFu, c1 = (w >> 8) & 0xFFu, c2 = (w >> 16) & 0xFFu, c3 = w >> 24;
-    return (uint32_t)tb[c0 * st] + (uint32_t)tb[c1 * st + 1] + (uint32_t)tb[c2 * st + 2] + (uint32_t)tb[c3 * st + 3];
+__device__ __forceinline__ uint32_t tab_sum4(uint32_t tb, uint32_t w, int stride_rt) {
+    const uint32_t c0 = __byte_perm(w, 0u, 0x4440), c1 = __byte_perm(w, 0u, 0x4441), c2 = __byte_perm(w, 0u, 0x4442),
+                   c3 = __byte_perm(w, 0u, 0x4443);
+    if (STRIDE == 128) {
+        return lds_u8_off<0>(tb + (c0 << 7)) + lds_u8_off<1>(tb + (c1 << 7)) + lds_u8_off<2>(tb + (c2 << 7)) +
+               lds_u8_off<3>(tb + (c3 << 7));
+    } else {
+        const uint32_t st = (uint32_t)stride_rt;
+        return lds_u8_off<0>(tb + c0 * st) + lds_u8_off<1>(tb + c1 * st) + lds_u8_off<2>(tb + c2 * st) + lds_u8_off<3>(tb + c3 * st);
+    }
 }
 
 // G code rows per warp (G even): lane l owns word 32 k + l of every full chunk; the tail words (rem <= 16) of TWO
-// rows share one pass (lanes 0-15 row 2p, lanes 16-31 row 2p+1).  All code-word loads are issued before any lookup.
+// rows share one pass (lanes 0-15 row 2p, lanes 16-31 row 2p+1).  Loading and summing are separate so that the next
+// group's code words are in flight while this group goes through the table.
 // Every ids[g] must be a valid row (callers pad a short group by repeating an id).
+template <int G>
+struct RowWords { uint32_t wf[2][G]; uint32_t wt[G]; };
+
 template <int WORDS, int G>
-__device__ __forceinline__ void adc_u8_rows(const uint8_t *__restrict__ codes, int M, const uint8_t *__restrict__ tab,
-                                            const uint32_t (&ids)[G], int lane, uint32_t (&out)[G]) {
+__device__ __forceinline__ void rows_load(const uint8_t *__restrict__ codes, int M, const uint32_t (&ids)[G], int lane,
+                                          RowWords<G> &w) {
+    const int words = WORDS ? WORDS : (M >> 2);
+    const uint32_t Mc = WORDS ? (uint32_t)(WORDS * 4) : (uint32_t)M;   // row stride in bytes
+    const int nfull = words >> 5, rem = words & 31;
+    const bool pair = rem > 0 && rem <= 16;
+    const int hl = lane & 15;
+    const uint8_t *base_lane = codes + lane * 4;                       // word `lane` of row 0
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const uint32_t *rp = reinterpret_cast<const uint32_t *>(base_lane + (size_t)ids[g] * Mc);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (k < nfull) w.wf[k][g] = __ldg(rp + 32 * k);
+    }
+    if (pair) {
+        const uint8_t *base_tail = codes + 128 * nfull + hl * 4;
+#pragma unroll
+        for (int p = 0; p < G / 2; ++p) {
+            const uint32_t id = (lane < 16) ? ids[2 * p] : ids[2 * p + 1];
+            w.wt[p] = (hl < rem) ? __ldg(reinterpret_cast<const uint32_t *>(base_tail + (size_t)id * Mc)) : 0u;
+        }
+    } else if (rem) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            w.wt[g] = (lane < rem) ? __ldg(reinterpret_cast<const uint32_t *>(base_lane + (size_t)ids[g] * Mc) + 32 * nfull) : 0u;
+    }
+}
+
+// sums of the first 2 * npairs rows (npairs is warp-uniform, 1 <= npairs <= G / 2); the other out[] are 0
+template <int WORDS, int G>
+__device__ __forceinline__ void rows_sum(int M, uint32_t tab, const RowWords<G> &w, int npairs, int lane,
+                                         uint32_t (&out)[G]) {
     const int words = WORDS ? WORDS : (M >> 2);
     const int nfull = words >> 5, rem = words & 31;
     const bool pair = rem > 0 && rem <= 16;
     const int hl = lane & 15;
-    const uint32_t *rowp[G];
+    const int st = rem * 4;
 #pragma unroll
-    for (int g = 0; g < G; ++g) rowp[g] = reinterpret_cast<const uint32_t *>(codes + (size_t)ids[g] * M);
-    uint32_t wf[2][G], wt[G];
+    for (int p = 0; p < G / 2; ++p) {
+        out[2 * p] = 0u; out[2 * p + 1] = 0u;
+        if (p < npairs) {
+            uint32_t a0 = 0u, a1 = 0u;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        if (k < nfull) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) wf[k][g] = __ldg(rowp[g] + 32 * k + lane);
+            for (int k = 0; k < 2; ++k) {
+                if (k < nfull) {
+                    const uint32_t tb = tab + k * 32768 + lane * 4;
+                    a0 += tab_sum4<128>(tb, w.wf[k][2 * p], 128);
+                    a1 += tab_sum4<128>(tb, w.wf[k][2 * p + 1], 128);
+                }
+            }
+            if (pair) {
+                const uint32_t tb = tab + nfull * 32768 + hl * 4;
+                const uint32_t u = (hl < rem) ? tab_sum4<0>(tb, w.wt[p], st) : 0u;
+                a0 += (lane < 16) ? u : 0u;
+                a1 += (lane < 16) ? 0u : u;
+            } else if (rem) {
+                const uint32_t tb = tab + nfull * 32768 + lane * 4;
+                a0 += (lane < rem) ? tab_sum4<0>(tb, w.wt[2 * p], st) : 0u;
+                a1 += (lane < rem) ? tab_sum4<0>(tb, w.wt[2 * p + 1], st) : 0u;
+            }
+            out[2 * p] = __reduce_add_sync(DR_FULL, a0);
+            out[2 * p + 1] = __reduce_add_sync(DR_FULL, a1);
         }
     }
-    if (pair) {
-#pragma unroll
-        for (int p = 0; p < G / 2; ++p) {
-            const uint32_t *rp = (lane < 16) ? rowp[2 * p] : rowp[2 * p + 1];
-            wt[p] = (hl < rem) ? __ldg(rp + 32 * nfull + hl) : 0u;
+}
+
+template <int WORDS, int G>
+__device__ __forceinline__ void adc_u8_rows(const uint8_t *__restrict__ codes, int M, const uint8_t *__restrict__ tab,
+                                            const uint32_t (&ids)[G], int lane, uint32_t (&out)[G]) {
+    RowWords<G> w;
+    rows_load<WORDS, G>(codes, M, ids, lane, w);
+    rows_sum<WORDS, G>(M, smem_u32(tab), w, G / 2, lane, out);
+}
+
+// visited set of this kernel: same open-addressing scheme as common.cuh:visited_insert, multiplicative (Fibonacci)
+// hash: the slot is the top log2(cap) bits of id * 2654435761
+__device__ __forceinline__ uint32_t fib_slot(uint32_t id, uint32_t shift) { return (id * 2654435761u) >> shift; }
+__device__ __forceinline__ bool visited_insert_fast(uint32_t nb, uint32_t *hash, uint32_t mask, uint32_t shift, bool use_ovf,
+                                                    uint32_t *ovf, uint32_t ovf_mask, uint32_t ovf_shift) {
+    uint32_t h = fib_slot(nb, shift);
+    if (!use_ovf) {
+        for (;;) {
+            const uint32_t old = atomicCAS(&hash[h], DR_EMPTY, nb);
+            if (old == DR_EMPTY) return true;
+            if (old == nb) return false;
+            h = (h + 1) & mask;
         }
-    } else if (rem) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) wt[g] = (lane < rem) ? __ldg(rowp[g] + 32 * nfull + lane) : 0u;
     }
-    uint32_t acc[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) acc[g] = 0u;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        if (k < nfull) {
-            const uint8_t *tb = tab + k * 32768 + lane * 4;
-#pragma unroll
-            for (int g = 0; g < G; ++g) acc[g] += tab_sum4<128>(tb, wf[k][g], 128);
-        }
+    for (;;) {  // shared table is frozen: look up only, then claim in the global overflow table
+        const uint32_t cur = hash[h];
+        if (cur == nb) return false;
+        if (cur == DR_EMPTY) break;
+        h = (h + 1) & mask;
     }
-    if (pair) {
-        const uint8_t *tb = tab + nfull * 32768 + hl * 4;
-        const int st = rem * 4;
-#pragma unroll
-        for (int p = 0; p < G / 2; ++p) {
-            const uint32_t u = (hl < rem) ? tab_sum4<0>(tb, wt[p], st) : 0u;
-            acc[2 * p] += (lane < 16) ? u : 0u;
-            acc[2 * p + 1] += (lane < 16) ? 0u : u;
-        }
-    } else if (rem) {
-        const uint8_t *tb = tab + nfull * 32768 + lane * 4;
-        const int st = rem * 4;
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] += (lane < rem) ? tab_sum4<0>(tb, wt[g], st) : 0u;
+    h = fib_slot(nb ^ 0x9e3779b9u, ovf_shift);
+    for (;;) {
+        const uint32_t old = atomicCAS(&ovf[h], DR_EMPTY, nb);
+        if (old == DR_EMPTY) return true;
+        if (old == nb) return false;
+        h = (h + 1) & ovf_mask;
     }
-#pragma unroll
-    for (int g = 0; g < G; ++g) out[g] = __reduce_add_sync(DR_FULL, acc[g]);
+}
+
+// One piece [e0, e1) of the canonical warp L2^2 (common.cuh:warp_l2sq: lane l owns elements base = 4 l + 128 j, fmaf in
+// increasing j), the row read from shared memory where a bulk copy staged it.  e0 is a multiple of 128.
+__device__ __forceinline__ float l2sq_piece_smem(const float *__restrict__ row, const float *__restrict__ q, int e0, int e1,
+                                                 int lane, float acc) {
+#pragma unroll 2
+    for (int base = e0 + lane * 4; base < e1; base += 128) {
+        const float4 x = *reinterpret_cast<const float4 *>(row + base);
+        const float4 y = *reinterpret_cast<const float4 *>(q + base);
+        const float d0 = __fsub_rn(x.x, y.x), d1 = __fsub_rn(x.y, y.y), d2 = __fsub_rn(x.z, y.z), d3 = __fsub_rn(x.w, y.w);
+        acc = __fmaf_rn(d0, d0, acc);
+        acc = __fmaf_rn(d1, d1, acc);
+        acc = __fmaf_rn(d2, d2, acc);
+        acc = __fmaf_rn(d3, d3, acc);
+    }
+    return acc;
 }
 
 // number of keys of the sorted sequence a[0..n) that are smaller than key
@@ -123,7 +209,14 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
     return lo;
 }
 
-#define DR_MERGE_LINEAR 8   // up to this many survivors: rank by counting, no sort
+// optional per-phase cycle accounting (build with -DDR_PHASE_TIMING; thread 0 of every CTA, summed into counter[1..8])
+#ifdef DR_PHASE_TIMING
+#define DR_PT(i) do { if (tid == 0) { const long long c__ = clock64(); pt_acc[i] += c__ - pt_last; pt_last = c__; } } while (0)
+#else
+#define DR_PT(i) do { } while (0)
+#endif
+
+#define DR_MERGE_LINEAR 12  // up to this many survivors: rank by counting, no sort
 
 // WORDS > 0: compile-time M / 4;  WORDS == 0: runtime M (M % 4 == 0, M <= 256);  WORDS < 0: byte path (any M)
 template <int WORDS>
@@ -140,24 +233,40 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
     u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_hash);   // rerank keys alias the (dead) visited table
 
     __shared__ long long s_b;
+    __shared__ u64 s_pfkey;   // prefetch == 2: a survivor below this key is among the next step's likely expansions
     __shared__ __align__(8) uint64_t s_lutbar;
-    __shared__ int s_nn2[2], s_ns, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
+    __shared__ __align__(8) uint64_t s_rrbar[16];   // rerank staging: two half-row barriers per warp
+    __shared__ int s_nn2[2], s_ns, s_p0, s_minpos, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
 
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int tid = threadIdx.x, nt = blockDim.x, nw = nt >> 5;
+    int lane = tid & 31, wid = tid >> 5;
+    asm volatile("" : "+r"(lane), "+r"(wid));    // opaque: keep them in registers instead of re-reading %tid in the loops
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t tab32 = smem_u32(s_lut);
     const int D = a.D, R = a.R, M = a.M, L = a.L, W = a.W;
     const int words = WORDS > 0 ? WORDS : (M >> 2);
     const uint32_t hmask = a.hash_cap - 1u, ovf_mask = a.ovf_cap - 1u;
+    const uint32_t hshift = 32u - (uint32_t)__popc(hmask), ovf_shift = 32u - (uint32_t)__popc(ovf_mask);
     const int hlimit = (int)(a.hash_cap - (a.hash_cap >> 2));
     const int ovf_limit = (int)(a.ovf_cap - (a.ovf_cap >> 2));
     uint32_t *my_ovf = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
     uint32_t lut_phase = 0;
-    if (!WP && tid == 0) { mbar_init(&s_lutbar, 1); fence_mbar_init(); }
+#ifdef DR_PHASE_TIMING
+    long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt_last = clock64();
+#endif
+    if (tid == 0) {
+        mbar_init(&s_lutbar, 1);
+        for (int i = 0; i < 16; ++i) mbar_init(&s_rrbar[i], 1);
+        fence_mbar_init();
+    }
+    uint32_t rr_ph0 = 0, rr_ph1 = 0;
+    const uint64_t pol_stream = l2_policy_evict_first();
 
     for (;;) {
         __syncthreads();
         if (tid == 0) s_b = (long long)atomicAdd(a.counter, 1ull);
         __syncthreads();
+        DR_PT(0);   // work fetch (and the previous query's output)
         const long long b = s_b;
         if (b >= a.B) break;
 
@@ -194,6 +303,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                 }
             }
         } else if (tid == 0) {
+            fence_proxy_async();   // the region was last touched through the generic proxy
             mbar_expect_tx(&s_lutbar, (uint32_t)M * 256u);
             bulk_g2s(s_lut, a.lut8 + (size_t)b * M * 256, (uint32_t)M * 256u, &s_lutbar);
         }
@@ -217,11 +327,13 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             }
             if (lane == 0) {
                 s_list0[0] = make_ikey(s0, a.start);
-                s_hash[hash_u32(a.start) & hmask] = a.start;
+                s_hash[fib_slot(a.start, hshift)] = a.start;
             }
         }
         int cur = 0, n = 1, hops = 0, nvis = 1, step = 0;
+        int fstart = 0;   // every list entry before fstart is expanded (scan hint, identical in all threads)
         __syncthreads();
+        DR_PT(1);   // table / query staging, start node
 
         for (;;) {
             u64 *lst = cur ? s_list1 : s_list0;
@@ -236,23 +348,35 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             }
             const bool ovf_full = use_ovf_now && (s_ovfcount + W * R > ovf_limit);
             for (int s = wid; s < W; s += nw) {
-                int found = 0, pos = -1;
+                int found = 0, pos = -1, pos2 = -1;
                 const bool need_total = (s == 0);   // warp 0 also publishes how many nodes are expanded this step
-                for (int base = 0; base < n && (pos < 0 || (need_total && found < W)); base += 32) {
+                const bool spec = (a.prefetch == 2);
+                const int t2 = s + W;               // prefetch == 2: the entry that would be expanded next step if nothing better turns up
+                for (int base = fstart & ~31;
+                     base < n && (pos < 0 || (need_total && found < W) || (spec && pos2 < 0)); base += 32) {
                     const int i = base + lane;
                     const bool un = (i < n) && !(lst[i] & 1ull);
                     const unsigned m = __ballot_sync(DR_FULL, un);
                     const int c = __popc(m);
-                    if (pos < 0 && found + c > s) {
-                        const unsigned hit = __ballot_sync(DR_FULL, un && (__popc(m & lt_mask) == s - found));
-                        pos = base + __ffs(hit) - 1;
-                    }
+                    const int myrank = found + __popc(m & lt_mask);
+                    if (pos < 0 && found + c > s) pos = base + __ffs(__ballot_sync(DR_FULL, un && myrank == s)) - 1;
+                    if (spec && pos2 < 0 && found + c > t2) pos2 = base + __ffs(__ballot_sync(DR_FULL, un && myrank == t2)) - 1;
                     found += c;
+                }
+                if (spec) {
+                    if (pos2 >= 0) {
+                        const u64 k2 = lst[pos2];
+                        if (lane * 32 < R) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(k2) * R + lane * 32));
+                        if (s == W - 1 && lane == 0) s_pfkey = k2;
+                    } else if (s == W - 1 && lane == 0) {
+                        s_pfkey = DR_KEY_MAX;
+                    }
                 }
                 if (need_total && lane == 0) {
                     int tot = found < W ? found : W;
                     if (ovf_full) { s_status |= DR_ST_VISITED_OVERFLOW; tot = 0; }
                     s_ns = tot;
+                    s_p0 = pos;
                 }
                 if (pos < 0 || ovf_full) continue;   // warp-uniform
                 if (lane == 0) s_sel[W + s] = (uint32_t)pos;
@@ -264,7 +388,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                     bool valid = (j < R) && ((long long)nb < a.N);
                     if (valid && a.deleted) valid = a.deleted[nb] == 0;
                     bool isnew = false;   // equal ids in one row (0-padding): the CAS admits exactly one of them
-                    if (valid) isnew = visited_insert(nb, s_hash, hmask, use_ovf_now, my_ovf, ovf_mask);
+                    if (valid) isnew = visited_insert_fast(nb, s_hash, hmask, hshift, use_ovf_now, my_ovf, ovf_mask, ovf_shift);
                     const unsigned m = __ballot_sync(DR_FULL, isnew);
                     const int cnt = __popc(m);
                     int basepos = 0;
@@ -276,35 +400,64 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                 }
             }
             __syncthreads();
-            const int ns = s_ns;
+            DR_PT(2);   // select + adjacency + visited
+            const int ns = s_ns, p0 = s_p0;
             if (ns == 0) break;
             const bool use_ovf = use_ovf_now;
             if (tid < ns) lst[s_sel[W + tid]] |= 1ull;        // mark the expanded entries (merge reads them after the next barrier)
-            if (tid == 0) s_nn2[(step + 1) & 1] = 0;          // next step's newcomer counter
+            if (tid == 0) { s_nn2[(step + 1) & 1] = 0; s_minpos = 0x7fffffff; }   // next step's newcomer counter; merge's first insert position
             ++step;
             // (3) quantised ADC of the newcomers; the survivors are appended compactly
             const int nn = *p_nn;
             const bool full = (n >= L);
             const u64 worstk = lst[n - 1] & ~1ull;
+            const u64 pfkey = s_pfkey;
             if (WP) {
-                constexpr int G = 4;
-                for (int base = wid; base < nn; base += nw * G) {
-                    uint32_t gid[G], gs[G];
-                    int cnt = 1;
-                    gid[0] = s_newid[base];
+                // item i of this warp = newcomer wid + nw * i; lane l owns item l of the current block of 32 items, rows go
+                // through the table four (or two) at a time, and the warp appends its survivors once per block
+                constexpr int KW = (WORDS > 0 ? WORDS : 0);
+                for (int first = wid; first < nn; first += 32 * nw) {
+                    int cntw = (nn - first + nw - 1) / nw;
+                    cntw = cntw < 32 ? cntw : 32;
+                    const uint32_t myid = lane < cntw ? s_newid[first + lane * nw] : 0u;
+                    uint32_t mysum = 0u;
+                    const int rounds = (cntw + 3) >> 2;
+                    RowWords<4> wa, wb;   // two groups of code words: one being summed, one in flight
+                    {
+                        uint32_t gid[4];
 #pragma unroll
-                    for (int g = 1; g < G; ++g) {
-                        const int i = base + g * nw;
-                        gid[g] = gid[0];                        // pad a short group with a valid row
-                        if (i < nn) { gid[g] = s_newid[i]; cnt = g + 1; }
+                        for (int g = 0; g < 4; ++g) gid[g] = __shfl_sync(DR_FULL, myid, g);    // lanes >= cntw hold row 0: valid
+                        rows_load<KW, 4>(a.codes, M, gid, lane, wa);
                     }
-                    adc_u8_rows<(WORDS > 0 ? WORDS : 0), G>(a.codes, M, s_lut, gid, lane, gs);
-                    // lane g owns key g; one aggregated counter update per group
-                    uint32_t mysum = gs[0], myid = gid[0];
+                    for (int r = 0; r < rounds; r += 2) {
+                        if (r + 1 < rounds) {
+                            uint32_t gid[4];
 #pragma unroll
-                    for (int g = 1; g < G; ++g) if (lane == g) { mysum = gs[g]; myid = gid[g]; }
+                            for (int g = 0; g < 4; ++g) gid[g] = __shfl_sync(DR_FULL, myid, (r + 1) * 4 + g);
+                            rows_load<KW, 4>(a.codes, M, gid, lane, wb);
+                        }
+                        uint32_t gs[4];
+                        rows_sum<KW, 4>(M, tab32, wa, (cntw - r * 4) > 2 ? 2 : 1, lane, gs);
+                        if ((lane >> 2) == r) {
+                            const int g = lane & 3;
+                            mysum = g == 0 ? gs[0] : (g == 1 ? gs[1] : (g == 2 ? gs[2] : gs[3]));
+                        }
+                        if (r + 1 < rounds) {
+                            if (r + 2 < rounds) {
+                                uint32_t gid[4];
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) gid[g] = __shfl_sync(DR_FULL, myid, (r + 2) * 4 + g);
+                                rows_load<KW, 4>(a.codes, M, gid, lane, wa);
+                            }
+                            rows_sum<KW, 4>(M, tab32, wb, (cntw - (r + 1) * 4) > 2 ? 2 : 1, lane, gs);
+                            if ((lane >> 2) == r + 1) {
+                                const int g = lane & 3;
+                                mysum = g == 0 ? gs[0] : (g == 1 ? gs[1] : (g == 2 ? gs[2] : gs[3]));
+                            }
+                        }
+                    }
                     const u64 key = make_ikey(mysum, myid);
-                    const bool ok = lane < cnt && (!full || key < worstk);
+                    const bool ok = lane < cntw && (!full || key < worstk);
                     const unsigned okm = __ballot_sync(DR_FULL, ok);
                     if (okm) {
                         int basep = 0;
@@ -312,7 +465,8 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                         basep = __shfl_sync(DR_FULL, basep, 0);
                         if (ok) {
                             s_newk[basep + __popc(okm & lt_mask)] = key;
-                            if (a.prefetch) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)myid * R));
+                            if (a.prefetch == 1 || (a.prefetch == 2 && key < pfkey))   // likely to be expanded next step
+                                for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)myid * R + o));
                         }
                     }
                 }
@@ -330,6 +484,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                 if (use_ovf) s_ovfcount += nn; else s_hcount += nn;
             }
             __syncthreads();
+            DR_PT(3);   // ADC
             nvis += nn;
             hops += ns;
             const int mv = s_mvalid;
@@ -347,6 +502,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                         if (x < n) { key = lst[x]; pos = x; }
                         else { key = s_newk[x - n]; pos = lower_bound_u64(lst, n, key); }
                         for (int j = 0; j < mv; ++j) pos += (s_newk[j] < key) ? 1 : 0;
+                        if (x >= n) atomicMin(&s_minpos, pos);
                         if (pos < L) oth[pos] = key;
                     }
                 } else if (mv <= 32 * nw) {
@@ -384,6 +540,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                             const int sz = (mv - (c << 5)) < 32 ? (mv - (c << 5)) : 32;
                             pos += lower_bound_u64(s_newk + (c << 5), sz, key);
                         }
+                        if (x >= n && ((x - n) & 31) == 0) atomicMin(&s_minpos, pos);   // chunk minima
                         if (pos < L) oth[pos] = key;
                     }
                 } else {
@@ -393,12 +550,18 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                         if (x < n) { key = lst[x]; pos = x; }
                         else { key = s_newk[x - n]; pos = lower_bound_u64(lst, n, key); }
                         for (int j = 0; j < mv; ++j) pos += (s_newk[j] < key) ? 1 : 0;
+                        if (x >= n) atomicMin(&s_minpos, pos);
                         if (pos < L) oth[pos] = key;
                     }
                 }
                 cur ^= 1;
                 n = total < L ? total : L;
                 __syncthreads();   // the next step's scans read the merged list
+                DR_PT(4);   // merge
+                const int mp = s_minpos;
+                fstart = (p0 + 1) < mp ? (p0 + 1) : mp;
+            } else {
+                fstart = p0 + 1;
             }
         }
 
@@ -413,21 +576,61 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
         }
         const int k = a.k;
         if (a.rerank) {
-            for (int i = wid; i < n; i += 2 * nw) {
-                const int i2 = i + nw;
-                if (i2 < n) {
-                    float dA, dB;
-                    warp_l2sq_x2(a.vec + (size_t)key_id(lst[i]) * D, a.vec + (size_t)key_id(lst[i2]) * D, s_q, D, lane, dA, dB);
-                    if (lane == 0) {
-                        s_rrk[i] = ((u64)f2ord(dA + 0.0f) << 32) | (u64)i;
-                        s_rrk[i2] = ((u64)f2ord(dB + 0.0f) << 32) | (u64)i2;
+            // Exact rerank of the whole list.  The table is dead now: its bytes stage full-precision rows, one slot per
+            // warp, filled by bulk async copies (TMA engine, evict-first in L2) in two pieces so that the second half of a
+            // row and the first half of the next one are in flight while the warp accumulates; no registers are tied up
+            // by loads in flight and 8 rows x 6 KB per CTA keep HBM busy.  Same arithmetic order as warp_l2sq.
+            const int slot = (D * 4 + 15) & ~15;
+            int nsl = (M * 256) / slot;
+            nsl = nsl < nw ? nsl : nw;
+            if (nsl >= 1 && (D & 3) == 0) {
+                if (wid < nsl) {
+                    float *buf = reinterpret_cast<float *>(s_lut + wid * slot);
+                    uint64_t *bar0 = &s_rrbar[2 * wid], *bar1 = bar0 + 1;
+                    const int e0 = (((D + 127) >> 7) >> 1) << 7;     // elements in the first piece (multiple of 128, may be 0)
+                    const uint32_t by0 = (uint32_t)e0 * 4u, by1 = (uint32_t)(D - e0) * 4u;
+                    if (lane == 0 && wid < n) {
+                        const float *row = a.vec + (size_t)key_id(lst[wid]) * D;
+                        fence_proxy_async();
+                        if (by0) { mbar_expect_tx(bar0, by0); bulk_g2s_hint(buf, row, by0, bar0, pol_stream); }
+                        mbar_expect_tx(bar1, by1); bulk_g2s_hint(buf + e0, row + e0, by1, bar1, pol_stream);
                     }
-                } else {
-                    float d2 = warp_l2sq(a.vec + (size_t)key_id(lst[i]) * D, s_q, D, lane);
-                    if (lane == 0) s_rrk[i] = ((u64)f2ord(d2 + 0.0f) << 32) | (u64)i;
+                    for (int i = wid; i < n; i += nsl) {
+                        const int inext = i + nsl;
+                        const float *rown = inext < n ? a.vec + (size_t)key_id(lst[inext]) * D : nullptr;
+                        float acc = 0.0f;
+                        if (by0) {
+                            mbar_wait(bar0, rr_ph0); rr_ph0 ^= 1u;
+                            acc = l2sq_piece_smem(buf, s_q, 0, e0, lane, acc);
+                            __syncwarp();
+                            if (lane == 0 && rown) { mbar_expect_tx(bar0, by0); bulk_g2s_hint(buf, rown, by0, bar0, pol_stream); }
+                        }
+                        mbar_wait(bar1, rr_ph1); rr_ph1 ^= 1u;
+                        acc = l2sq_piece_smem(buf, s_q, e0, D, lane, acc);
+                        __syncwarp();
+                        if (lane == 0 && rown) { mbar_expect_tx(bar1, by1); bulk_g2s_hint(buf + e0, rown + e0, by1, bar1, pol_stream); }
+                        const float d2 = warp_sum_butterfly(acc);
+                        if (lane == 0) s_rrk[i] = ((u64)f2ord(d2 + 0.0f) << 32) | (u64)i;
+                    }
+                }
+            } else {
+                for (int i = wid; i < n; i += 2 * nw) {
+                    const int i2 = i + nw;
+                    if (i2 < n) {
+                        float dA, dB;
+                        warp_l2sq_x2(a.vec + (size_t)key_id(lst[i]) * D, a.vec + (size_t)key_id(lst[i2]) * D, s_q, D, lane, dA, dB);
+                        if (lane == 0) {
+                            s_rrk[i] = ((u64)f2ord(dA + 0.0f) << 32) | (u64)i;
+                            s_rrk[i2] = ((u64)f2ord(dB + 0.0f) << 32) | (u64)i2;
+                        }
+                    } else {
+                        float d2 = warp_l2sq(a.vec + (size_t)key_id(lst[i]) * D, s_q, D, lane);
+                        if (lane == 0) s_rrk[i] = ((u64)f2ord(d2 + 0.0f) << 32) | (u64)i;
+                    }
                 }
             }
             __syncthreads();
+            DR_PT(5);   // rerank distance pass
             for (int i = tid; i < n; i += nt) {
                 u64 key = s_rrk[i];
                 int pos = 0;
@@ -459,6 +662,10 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             for (uint32_t i = tid; i < a.ovf_cap; i += nt) my_ovf[i] = DR_EMPTY;
         }
     }
+#ifdef DR_PHASE_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(a.counter + 1 + i, (u64)pt_acc[i]);
+#endif
 }
 
 typedef void (*fast_kernel_t)(const FastArgs);
@@ -532,7 +739,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
         DR_CUDA(cudaMemsetAsync(h->d_ovf, 0xFF, need, s));
     }
     a.ovf = h->d_ovf;
-    if (!h->d_counter) DR_CUDA(cudaMalloc(&h->d_counter, sizeof(u64)));
+    if (!h->d_counter) DR_CUDA(cudaMalloc(&h->d_counter, 16 * sizeof(u64)));
     a.counter = h->d_counter;
 
     const size_t per_q = (size_t)h->M * 256;
@@ -566,11 +773,28 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
         a.list_dist = list_dist ? list_dist + (size_t)c0 * p->L : nullptr;
         a.list_len = list_len ? list_len + c0 : nullptr;
         a.status = status ? status + c0 : nullptr;
+#ifdef DR_PHASE_TIMING
+        DR_CUDA(cudaMemsetAsync(h->d_counter, 0, 16 * sizeof(u64), s));
+#else
         DR_CUDA(cudaMemsetAsync(h->d_counter, 0, sizeof(u64), s));
+#endif
         int grid = (int)((cb < (int64_t)max_grid) ? cb : max_grid);
         if (h->timing) DR_CUDA(cudaEventRecord(h->ev0, s));
         kern<<<grid, nt, smem, s>>>(a);
         DR_LAUNCHED();
+#ifdef DR_PHASE_TIMING
+        {
+            u64 hc[16];
+            DR_CUDA(cudaStreamSynchronize(s));
+            DR_CUDA(cudaMemcpy(hc, h->d_counter, sizeof(hc), cudaMemcpyDeviceToHost));
+            static const char *nm[8] = {"fetch+output", "staging", "P1 select/adj/visited", "P2 adc", "merge", "rerank", "-", "-"};
+            double tot = 0;
+            for (int i = 0; i < 6; ++i) tot += (double)hc[1 + i];
+            fprintf(stderr, "[phase] %lld queries, grid %d:", (long long)cb, grid);
+            for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.1f%% (%.0f cyc/query)", nm[i], 100.0 * hc[1 + i] / tot, (double)hc[1 + i] / (double)cb);
+            fprintf(stderr, "\n");
+        }
+#endif
         if (h->timing) {
             DR_CUDA(cudaEventRecord(h->ev1, s));
             DR_CUDA(cudaEventSynchronize(h->ev1));

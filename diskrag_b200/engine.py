@@ -28,7 +28,7 @@ def make_params(k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_
                         adc_order=_lib.DR_ADC_TREE if adc_order == "tree" else _lib.DR_ADC_SEQ,
                         rerank=int(bool(rerank)), sqrt_out=int(bool(sqrt_out)), hash_cap=hash_cap, chunk=chunk,
                         threads=threads, lut_fmt=_lib.DR_LUT_U8 if lut == "u8" else _lib.DR_LUT_F32,
-                        prefetch=int(bool(prefetch)))
+                        prefetch=int(prefetch))
 
 
 class GpuIndex:
