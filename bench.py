@@ -267,7 +267,8 @@ def run_ours(a):
     tf = ROOT / "profiles" / "search_kernel_traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+            # one ncu --set full capture (scripts/profile.sh + scripts/summarize_profile.py), scaled to this launch size
+            traffic = round(json.loads(tf.read_text())["dram_bytes_per_query"] * (B * 2 / max(1, k_launches)))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
