@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--L", type=int, default=100)
     ap.add_argument("--W", type=int, default=8)
     ap.add_argument("--adc", default="tree", choices=["seq", "tree"])
-    ap.add_argument("--lut", default="u8", choices=["f32", "u8"])
+    ap.add_argument("--lut", default="u8tc", choices=["f32", "u8", "u8tc"], help="ADC table: f32 reference arithmetic, u8 exact 8-bit, u8tc 8-bit built on tensor cores")
     ap.add_argument("--prefetch", type=int, default=0)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries", type=int, default=100_000, help="queries per GPU per step")
@@ -272,7 +272,7 @@ def run_ours(a):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "kernel": "search_fast_kernel" if a.lut == "u8" else "search_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "search_fast_kernel" if a.lut != "f32" else "search_kernel",
                 "kernel_ms_per_launch": round(per_launch_ms, 3), "launches_per_step": k_launches // 2,
                 "algorithmic_bytes_per_query": round(abytes / B, 1), "kernel_share_of_step": round((k_ms / 2) / (ms_total / a.steps), 3)}
 
@@ -330,7 +330,7 @@ def cpu_baseline_port(a, X, adj, codes, cb, med, Q, ids_gpu):
     Qs = Q[:n].cpu().numpy()
     t = time.perf_counter()
     ids, d, hops, vis = O.search_batch(adjh, Xh, Qs, med, a.L, a.k, codes=ch, codebook=cbh,
-                                       dist_mode=O.DIST_ADC_U8 if a.lut == "u8" else (O.DIST_ADC_TREE if a.adc == "tree" else O.DIST_ADC_SEQ),
+                                       dist_mode=O.DIST_ADC_U8 if a.lut != "f32" else (O.DIST_ADC_TREE if a.adc == "tree" else O.DIST_ADC_SEQ),
                                        flavor=O.FLAVOR_WARP,
                                        W=a.W, rerank_=True)
     dt = time.perf_counter() - t

@@ -13,7 +13,7 @@ LIB_PATH = _HERE / "libdiskrag_b200.so"
 
 DR_DIST_PQ, DR_DIST_EXACT = 0, 1
 DR_ADC_SEQ, DR_ADC_TREE = 0, 1
-DR_LUT_F32, DR_LUT_U8 = 0, 1
+DR_LUT_F32, DR_LUT_U8, DR_LUT_U8_TC = 0, 1, 2
 DR_ST_VISITED_OVERFLOW, DR_ST_TIE_OVERFLOW = 1, 2
 
 
@@ -46,6 +46,7 @@ SIGNATURES = {
     "dr_lut_build": (C.c_int, [_vp, _vp, _i64, _vp]),
     "dr_lut_build_dev": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "dr_pq_lut": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, C.c_int]),
+    "dr_pq_lut_u8": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int]),
     "dr_pq_train": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _u64, _vp, _PP(_dbl), C.c_int]),
     "dr_pq_train_dev": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _u64, _vp, _PP(_dbl), C.c_int, _vp]),
     "dr_pq_encode": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, C.c_int]),

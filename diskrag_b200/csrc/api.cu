@@ -380,6 +380,38 @@ int dr_pq_lut(const float *codebook, const float *Q, int64_t B, int32_t D, int32
     return 0;
 }
 
+int dr_pq_lut_u8(const float *codebook, const float *Q, int64_t B, int32_t D, int32_t M, int32_t lut_fmt, uint8_t *out,
+                 float *out_scale, float *out_offset, int device) {
+    if (use_device(device)) return 3;
+    DR_CHECK(M > 0 && D % M == 0, "dr_pq_lut_u8: D=%d not divisible by M=%d", D, M);
+    DR_CHECK(lut_fmt == DR_LUT_U8 || lut_fmt == DR_LUT_U8_TC, "dr_pq_lut_u8: lut_fmt must be DR_LUT_U8 or DR_LUT_U8_TC");
+    DevBuf cb, q, o, o2, sc, of, mn, rg;
+    if (cb.alloc((size_t)256 * D * 4) || q.alloc((size_t)B * D * 4) || o.alloc((size_t)B * M * 256) || o2.alloc((size_t)B * M * 256) ||
+        sc.alloc((size_t)B * 4) || of.alloc((size_t)B * 4) || mn.alloc((size_t)B * M * 4) || rg.alloc((size_t)B * 4))
+        return 1;
+    DR_CUDA(cudaMemcpy(cb.p, codebook, (size_t)256 * D * 4, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(q.p, Q, (size_t)B * D * 4, cudaMemcpyHostToDevice));
+    const bool words = (M & 3) == 0;
+    if (lut_fmt == DR_LUT_U8_TC) {
+        int sms = 0;
+        DR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        if (launch_lut_build_u8_tc(cb.as<float>(), q.as<float>(), B, D, M, o.as<uint8_t>(), sc.as<float>(), of.as<float>(), mn.as<float>(), rg.as<unsigned>(), sms, 0))
+            return 1;
+    } else if (launch_lut_build_u8(cb.as<float>(), q.as<float>(), B, D, M, o.as<uint8_t>(), sc.as<float>(), of.as<float>(), mn.as<float>(),
+                                   rg.as<unsigned>(), words ? 1 : 0, 0)) {
+        return 1;
+    }
+    const uint8_t *plain = o.as<uint8_t>();
+    if (words) {
+        if (launch_lut_u8_unpermute(o.as<uint8_t>(), B, M, o2.as<uint8_t>(), 0)) return 1;
+        plain = o2.as<uint8_t>();
+    }
+    DR_CUDA(cudaMemcpy(out, plain, (size_t)B * M * 256, cudaMemcpyDeviceToHost));
+    DR_CUDA(cudaMemcpy(out_scale, sc.p, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    DR_CUDA(cudaMemcpy(out_offset, of.p, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int dr_pq_train_dev(const float *d_X, int64_t N, int32_t D, int32_t M, int32_t iters, uint64_t seed, float *d_out_codebook,
                     double *out_mse, int device, void *stream) {
     if (use_device(device)) return 3;

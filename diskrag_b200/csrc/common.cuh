@@ -82,6 +82,9 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
                        int32_t *status, cudaStream_t s);   // search_fast.cu: u8-table throughput kernel
 int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
                         float *d_offset, float *d_mn, unsigned *d_range, int word_layout, cudaStream_t s);  // pq.cu
+int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
+                           float *d_offset, float *d_mn, unsigned *d_range, int sms, cudaStream_t s);   // lut_tc.cu (tcgen05)
+int launch_lut_u8_unpermute(const uint8_t *d_words, int64_t B, int M, uint8_t *d_plain, cudaStream_t s);  // pq.cu
 
 // ---------------------------------------------------------------------------------------------
 // device side

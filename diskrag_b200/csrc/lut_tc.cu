@@ -1,0 +1,293 @@
+// lut_tc.cu — K2 on the 5th-generation tensor cores: the 8-bit ADC table of the throughput search, built with
+// tcgen05.mma (kind::tf32, accumulators in TMEM) instead of CUDA-core FMA chains.
+//
+// Replaces DiskANNPQ.compute_distance_table (pydiskann/pq/fast_pq.py:294-318) for the u8 table of search_fast.cu:
+//   t[b][m][c]   = ||C[m][c]||^2 - 2 q_b,m . C[m][c]                 (the ||q_m||^2 term goes into the per-query offset)
+//   lo[b][m]     = min_c t,   scale[b] = max_m (max_c t - lo) / 255,  offset[b] = sum_m lo[b][m] + ||q_b||^2
+//   out[b][m][c] = sat_u8(rint((t - lo[b][m]) / scale[b]))
+// which is the contract of pq.cu:launch_lut_build_u8 (restated by oracle.c:orc_lut_u8), here with the inner products
+// in TF32 (10-bit mantissa inputs, fp32 accumulation): an entry may differ from the exact table by one unit
+// (tests/test_lut_tc_gpu.py bounds it); traversal quality is unchanged (recall checked in the same test).
+//
+// Shape: queries x centroids is a genuine dense contraction, one per subspace: [128 queries x ds] . [ds x 256].
+// One CTA = one 128-query tile; a "stage" = one code word (4 subspaces) x one quarter of the centroids (64):
+// four MMAs D_j[128 x 64] (+)= A_j[128 x 8] . B_j[64 x 8]^T per K-step write 4 x 64 = 256 TMEM columns, and the 128
+// threads (thread = TMEM lane = query) read them back with tcgen05.ld.  The affine part of the map is folded into
+// one extra K-step so that the epilogue is a bare convert-and-pack:
+//   phase 1 (statistics):  A = [-2 q | 1, 1, 0..],            B = [c | cn_hi, cn_lo, 0..]          -> D = t
+//   phase 2 (quantise)  :  A = [-2 inv q | inv_hi, inv_hi, inv_lo, k_hi, k_lo, 0..],
+//                          B = [c | cn_hi, cn_lo, cn_hi, 1, 1, 0..]                                -> D = t * inv + k
+//   with inv = 1 / scale[b], k = -lo[b][m] * inv, and x_hi / x_lo the exact two-term TF32 split of x.
+// Operands are staged in shared memory in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B), the
+// descriptors say LBO = 128 B (next K chunk), SBO = 256 B (next 8-row group).  Two CTAs share an SM (256 TMEM columns
+// each), so one CTA's staging + MMA round trip hides behind the other's epilogue.
+#include "common.cuh"
+
+#define TC_ROWS 128      // queries per CTA tile = TMEM lanes
+#ifndef TC_NQ
+#define TC_NQ 32         // centroids per stage
+#endif
+#define TC_COLS (4 * TC_NQ)   // TMEM columns per CTA (4 subspaces x TC_NQ centroids)
+#define TC_CTAS (512 / TC_COLS)   // CTAs per SM: together they own the SM's 512 TMEM columns
+
+namespace {
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, both operands K-major, TF32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, no swizzle, version 1 (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = 64
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int Mdim, int Ndim) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ndim >> 3) << 17) | ((uint32_t)(Mdim >> 4) << 24);
+}
+
+// exact two-term TF32 split: hi has 10 explicit mantissa bits, lo = x - hi (its own rounding is second order)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits: a biased error)
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32_rna4(float4 v) { return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)); }
+
+// byte offset of (row r, 16-byte K chunk c) inside one K-step block of the canonical layout
+__device__ __forceinline__ uint32_t core_off(int r, int c) { return (uint32_t)((r >> 3) * 256 + c * 128 + (r & 7) * 16); }
+
+struct LutTcArgs {
+    const float *codebook; const float *Q; long long B; int D, M, ds;
+    uint32_t *out32;      // [B][M/4][256] packed words (search_fast.cu's global layout)
+    const float *scale;   // phase 2: per-query scale written by lut_u8_finalize_kernel
+    float *lo;            // [B][M] per-subspace minima (phase 1 writes, phase 2 reads)
+    unsigned *range_bits; // [B] max range as float bits (phase 1, atomicMax)
+    int words_per_cta;
+};
+
+// One stage: operands are in shared memory; thread 0 issues 4 x (nks + 1) MMAs and commits; everybody waits.
+__device__ __forceinline__ void stage_mma(uint32_t tmem, uint32_t a_base, uint32_t b_base, int nks1, uint64_t *bar, uint32_t &phase,
+                                          int tid) {
+    fence_proxy_async();          // this thread's generic-proxy operand writes -> visible to the tensor core (async proxy)
+    tc_fence_before();            // this thread's TMEM reads of the previous stage are ordered before the barrier
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc_tf32(TC_ROWS, TC_NQ);
+        for (int j = 0; j < 4; ++j)
+            for (int ks = 0; ks < nks1; ++ks)
+                umma_tf32(tmem + (uint32_t)(j * TC_NQ), umma_desc(a_base + (uint32_t)((j * nks1 + ks) * (TC_ROWS * 32))),
+                          umma_desc(b_base + (uint32_t)((j * nks1 + ks) * (TC_NQ * 32))), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+}
+
+// Stage the B operand of one stage: centroids [c0, c0 + TC_NQ) of the word's four subspaces (warp j stages subspace
+// 4 w + j), rounded to TF32, plus the extra K-step [cn_hi, cn_lo, cn_hi, 1 | 1, 0, 0, 0] with cn = ||c||^2 in fp32.
+__device__ __forceinline__ void stage_B(const float *__restrict__ codebook, int w, int c0, int ds, int nks, unsigned char *sB,
+                                        int wid, int lane) {
+    const int nks1 = nks + 1, j = wid;
+    for (int rr = 0; rr < TC_NQ / 32; ++rr) {
+        const int r = lane * (TC_NQ / 32) + rr;
+        const float *src = codebook + ((size_t)(4 * w + j) * 256 + c0 + r) * ds;
+        float cn = 0.0f;
+        for (int kc = 0; kc < (ds >> 2); ++kc) {
+            const float4 v = ldg_f4(src + kc * 4);
+            cn = __fmaf_rn(v.x, v.x, cn); cn = __fmaf_rn(v.y, v.y, cn); cn = __fmaf_rn(v.z, v.z, cn); cn = __fmaf_rn(v.w, v.w, cn);
+            *reinterpret_cast<float4 *>(sB + (j * nks1 + (kc >> 1)) * (TC_NQ * 32) + core_off(r, kc & 1)) = tf32_rna4(v);
+        }
+        const float ch = tf32_hi(cn);
+        unsigned char *x = sB + (j * nks1 + nks) * (TC_NQ * 32);
+        *reinterpret_cast<float4 *>(x + core_off(r, 0)) = make_float4(ch, cn - ch, ch, 1.0f);
+        *reinterpret_cast<float4 *>(x + core_off(r, 1)) = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+// grid (query tiles, word groups), 128 threads (thread = query = TMEM lane).
+// PHASE 1: lo[b][m] = min_c t and range_bits[b] = max(range_bits[b], max_c t - lo)        (then lut_u8_finalize_kernel)
+// PHASE 2: out32[b][w][c] = the four subspaces' quantised entries, packed
+// Dynamic shared memory: A blocks 4 * (nks+1) * 4 KB, then B blocks 4 * (nks+1) * TC_NQ * 32 B.
+template <int PHASE>
+__global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTcArgs a) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ds = a.ds, nks = ds >> 3, nks1 = nks + 1, words = a.M >> 2, D = a.D, M = a.M;
+    unsigned char *sA = tc_smem;
+    unsigned char *sB = tc_smem + 4 * nks1 * (TC_ROWS * 32);
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+
+    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    if (wid == 0) tmem_alloc(&s_tmem, TC_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t tlane = tmem + ((uint32_t)(wid * 32) << 16);    // this warp's 32-lane quarter of TMEM
+    uint32_t phase = 0;
+
+    const long long b0 = (long long)blockIdx.x * TC_ROWS;
+    const long long b = b0 + tid;
+    const bool live = b < a.B;
+    const float *qrow = a.Q + (size_t)(live ? b : b0) * D;     // dead rows recompute row b0 and are never stored
+    const int w_begin = blockIdx.y * a.words_per_cta;
+    const int w_end = (w_begin + a.words_per_cta < words) ? (w_begin + a.words_per_cta) : words;
+
+    float mul = -2.0f, inv = 1.0f, inv_hi = 1.0f, inv_lo = 0.0f;
+    if (PHASE == 2) {
+        inv = __fdiv_rn(1.0f, a.scale[live ? b : b0]);
+        inv_hi = tf32_hi(inv); inv_lo = inv - inv_hi; mul = -2.0f * inv;
+    }
+    float rmax = 0.0f;
+    for (int w = w_begin; w < w_end; ++w) {
+        // A for this word: the row's 4 * ds query elements times -2 (phase 2: -2 inv), then the extra K-step
+        for (int j = 0; j < 4; ++j) {
+            const float *src = qrow + (size_t)(4 * w + j) * ds;
+            for (int kc = 0; kc < (ds >> 2); ++kc) {
+                float4 v = ldg_f4(src + kc * 4);
+                v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+                *reinterpret_cast<float4 *>(sA + (j * nks1 + (kc >> 1)) * (TC_ROWS * 32) + core_off(tid, kc & 1)) = tf32_rna4(v);
+            }
+            unsigned char *x = sA + (j * nks1 + nks) * (TC_ROWS * 32);
+            if (PHASE == 1) {
+                *reinterpret_cast<float4 *>(x + core_off(tid, 0)) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+                *reinterpret_cast<float4 *>(x + core_off(tid, 1)) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            } else {
+                const float k0 = -__fmul_rn(a.lo[(size_t)(live ? b : b0) * M + 4 * w + j], inv);
+                const float kh = tf32_hi(k0);
+                *reinterpret_cast<float4 *>(x + core_off(tid, 0)) = make_float4(inv_hi, inv_hi, inv_lo, kh);
+                *reinterpret_cast<float4 *>(x + core_off(tid, 1)) = make_float4(k0 - kh, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        float lo[4], hi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { lo[j] = __int_as_float(0x7f800000); hi[j] = -__int_as_float(0x7f800000); }
+        for (int c0 = 0; c0 < 256; c0 += TC_NQ) {
+            stage_B(a.codebook, w, c0, ds, nks, sB, wid, lane);
+            stage_mma(tmem, a_base, b_base, nks1, &s_bar, phase, tid);
+            if (PHASE == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int ch = 0; ch < TC_NQ / 16; ++ch) {
+                        float v[16];
+                        tmem_ld16(tlane + (uint32_t)(j * TC_NQ + ch * 16), v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { lo[j] = fminf(lo[j], v[i]); hi[j] = fmaxf(hi[j], v[i]); }
+                    }
+                }
+            } else {
+                uint32_t *orow = a.out32 + ((size_t)(live ? b : b0) * words + w) * 256 + c0;
+#pragma unroll
+                for (int ch = 0; ch < TC_NQ / 16; ++ch) {
+                    float v0[16], v1[16], v2[16], v3[16];
+                    tmem_ld16(tlane + (uint32_t)(0 * TC_NQ + ch * 16), v0);
+                    tmem_ld16(tlane + (uint32_t)(1 * TC_NQ + ch * 16), v1);
+                    tmem_ld16(tlane + (uint32_t)(2 * TC_NQ + ch * 16), v2);
+                    tmem_ld16(tlane + (uint32_t)(3 * TC_NQ + ch * 16), v3);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        uint32_t q0, q1, q2, q3;
+                        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q0) : "f"(v0[i]));
+                        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q1) : "f"(v1[i]));
+                        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q2) : "f"(v2[i]));
+                        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q3) : "f"(v3[i]));
+                        pk[i] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+                    }
+                    if (live) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<uint4 *>(orow + ch * 16 + i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+                    }
+                }
+            }
+        }
+        if (PHASE == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                rmax = fmaxf(rmax, hi[j] - lo[j]);
+                if (live) a.lo[(size_t)b * M + 4 * w + j] = lo[j];
+            }
+        }
+    }
+    if (PHASE == 1 && live) atomicMax(a.range_bits + b, __float_as_uint(rmax));   // a non-negative float orders like its bits
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 0) tmem_dealloc(tmem, TC_COLS);
+}
+
+}  // namespace
+
+// Same contract as launch_lut_build_u8(..., word_layout = 1): needs M % 4 == 0 and (D / M) % 8 == 0.
+// d_mn f32[B][M] and d_range u32[B] are scratch.  Three launches: statistics (tensor cores), finalize (pq.cu), quantise
+// (tensor cores); the two tensor-core launches are parallel over (128-query tile, group of code words).
+int launch_lut_u8_finalize(const float *d_lo, const unsigned *d_range, const float *d_Q, int64_t B, int D, int M, float *d_scale,
+                           float *d_offset, cudaStream_t s);   // pq.cu
+
+int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
+                           float *d_offset, float *d_mn, unsigned *d_range, int sms, cudaStream_t s) {
+    DR_CHECK(M > 0 && D % M == 0 && (M & 3) == 0 && ((D / M) & 7) == 0,
+             "dr_lut_build(u8, tensor cores): needs M %% 4 == 0 and a sub-dimension that is a multiple of 8 (D=%d M=%d)", D, M);
+    if (B == 0) return 0;
+    const int ds = D / M, nks1 = ds / 8 + 1, words = M / 4;
+    const int smem = 4 * nks1 * (TC_ROWS * 32) + 4 * nks1 * (TC_NQ * 32);
+    DR_CHECK(smem <= 200 * 1024, "dr_lut_build(u8, tensor cores): sub-dimension %d too large", ds);   // fewer CTAs per SM when large
+    DR_CUDA(cudaFuncSetAttribute(lut_u8_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DR_CUDA(cudaFuncSetAttribute(lut_u8_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LutTcArgs a;
+    a.codebook = d_codebook; a.Q = d_Q; a.B = B; a.D = D; a.M = M; a.ds = ds;
+    a.out32 = reinterpret_cast<uint32_t *>(d_out8); a.scale = d_scale; a.lo = d_mn; a.range_bits = d_range;
+    const long long tiles = (B + TC_ROWS - 1) / TC_ROWS;
+    // enough CTAs for >= 4 waves of the whole chip, a word group no smaller than 2 words (the A operand is staged per word)
+    int groups = (int)((4LL * TC_CTAS * sms + tiles - 1) / tiles);
+    if (groups > words / 2) groups = words / 2;
+    if (groups < 1) groups = 1;
+    a.words_per_cta = (words + groups - 1) / groups;
+    groups = (words + a.words_per_cta - 1) / a.words_per_cta;
+    DR_CHECK(tiles <= 2147483647LL, "dr_lut_build(u8, tensor cores): batch too large");
+    dim3 grid((unsigned)tiles, (unsigned)groups);
+    DR_CUDA(cudaMemsetAsync(d_range, 0, (size_t)B * 4, s));
+    lut_u8_tc_kernel<1><<<grid, TC_ROWS, smem, s>>>(a);
+    DR_LAUNCHED();
+    if (launch_lut_u8_finalize(d_mn, d_range, d_Q, B, D, M, d_scale, d_offset, s)) return 1;
+    lut_u8_tc_kernel<2><<<grid, TC_ROWS, smem, s>>>(a);
+    DR_LAUNCHED();
+    return 0;
+}

@@ -262,6 +262,14 @@ __global__ void __launch_bounds__(256) lut_u8_quant_kernel(const float *__restri
     }
 }
 
+int launch_lut_u8_finalize(const float *d_lo, const unsigned *d_range, const float *d_Q, int64_t B, int D, int M, float *d_scale,
+                           float *d_offset, cudaStream_t s) {
+    if (B == 0) return 0;
+    lut_u8_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(d_lo, d_range, d_Q, B, D, M, d_scale, d_offset);
+    DR_LAUNCHED();
+    return 0;
+}
+
 // Word layout for the bank-per-lane search table (search_fast.cu): out8[b][w][c][j] = entry of subspace 4w + j,
 // centroid c.  Block = (code word w, 64-query tile); thread c computes the four subspaces' entries of its centroid
 // and stores one packed 32-bit word per query: a warp writes 128 contiguous bytes.  Same arithmetic, entry for
@@ -360,6 +368,24 @@ int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, in
     }
     dr_set_error("dr_search(u8): sub-dimension %d is not instantiated (1-6, 8, 12, 16, 24, 32)", D / M);
     return 2;
+}
+
+// word layout [b][w][c][4] -> plain [b][m][c] (tests only)
+__global__ void lut_u8_unpermute_kernel(const uint8_t *__restrict__ in, long long total, int M, uint8_t *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 255);
+        const long long bm = i >> 8;
+        const int m = (int)(bm % M);
+        const long long b = bm / M;
+        out[i] = in[((b * (M >> 2) + (m >> 2)) * 256 + c) * 4 + (m & 3)];
+    }
+}
+int launch_lut_u8_unpermute(const uint8_t *d_words, int64_t B, int M, uint8_t *d_plain, cudaStream_t s) {
+    if (B == 0) return 0;
+    const long long total = (long long)B * M * 256;
+    lut_u8_unpermute_kernel<<<(unsigned)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535), 256, 0, s>>>(d_words, total, M, d_plain);
+    DR_LAUNCHED();
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------

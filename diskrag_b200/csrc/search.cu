@@ -469,7 +469,7 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
     if (pq) DR_CHECK(h->d_codes && h->M > 0, "dr_search: index has no PQ codes");
     DR_CHECK(h->medoid >= 0 && h->medoid < h->N, "dr_search: medoid out of range");
     if (B == 0) return 0;
-    if (p->lut_fmt == DR_LUT_U8) {
+    if (p->lut_fmt == DR_LUT_U8 || p->lut_fmt == DR_LUT_U8_TC) {
         DR_CHECK(pq && !d_lut && !trace && !qmap && !h->d_deg, "dr_search: the u8-table mode is PQ-only, builds its own tables and has no trace");
         return launch_search_fast(h, d_Q, B, p, ids, dist, hops, visited, list_ids, list_dist, list_len, status, s);
     }

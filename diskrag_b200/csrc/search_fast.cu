@@ -692,6 +692,8 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     a.k = p->k; a.L = p->L; a.W = p->W; a.rerank = p->rerank; a.sqrt_out = p->sqrt_out; a.prefetch = p->prefetch;
     a.start = (uint32_t)h->medoid;
     const bool word_layout = ((h->M & 3) == 0) && h->M <= 256;
+    DR_CHECK(p->lut_fmt != DR_LUT_U8_TC || (word_layout && ((h->D / h->M) & 7) == 0),
+             "dr_search: DR_LUT_U8_TC needs M %% 4 == 0, M <= 256 and (D / M) %% 8 == 0 (D=%d M=%d)", h->D, h->M);
     fast_kernel_t kern = pick_fast_kernel(h->M);
     int off = ((h->M * 256 + 15) / 16) * 16;
     a.o_q = off; off += p->rerank ? ((h->D * 4 + 15) / 16) * 16 : 0;
@@ -761,9 +763,13 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
 
     for (int64_t c0 = 0; c0 < B; c0 += chunk) {
         const int64_t cb = (B - c0 < chunk) ? (B - c0) : chunk;
-        if (launch_lut_build_u8(h->d_codebook, d_Q + (size_t)c0 * h->D, cb, h->D, h->M, d_tab, d_scale, d_off, d_mn, d_range,
-                                word_layout ? 1 : 0, s))
+        if (p->lut_fmt == DR_LUT_U8_TC) {
+            if (launch_lut_build_u8_tc(h->d_codebook, d_Q + (size_t)c0 * h->D, cb, h->D, h->M, d_tab, d_scale, d_off, d_mn, d_range, h->sms, s))
+                return 1;
+        } else if (launch_lut_build_u8(h->d_codebook, d_Q + (size_t)c0 * h->D, cb, h->D, h->M, d_tab, d_scale, d_off, d_mn, d_range,
+                                       word_layout ? 1 : 0, s)) {
             return 1;
+        }
         a.Q = d_Q + (size_t)c0 * h->D; a.lut8 = d_tab; a.lut_scale = d_scale; a.lut_offset = d_off; a.B = cb;
         a.out_ids = ids + (size_t)c0 * p->k;
         a.out_dist = dist ? dist + (size_t)c0 * p->k : nullptr;

@@ -27,7 +27,7 @@ def make_params(k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_
     return SearchParams(k=k, L=L, W=W, dist=_lib.DR_DIST_PQ if dist == "pq" else _lib.DR_DIST_EXACT,
                         adc_order=_lib.DR_ADC_TREE if adc_order == "tree" else _lib.DR_ADC_SEQ,
                         rerank=int(bool(rerank)), sqrt_out=int(bool(sqrt_out)), hash_cap=hash_cap, chunk=chunk,
-                        threads=threads, lut_fmt=_lib.DR_LUT_U8 if lut == "u8" else _lib.DR_LUT_F32,
+                        threads=threads, lut_fmt={"u8": _lib.DR_LUT_U8, "u8tc": _lib.DR_LUT_U8_TC}.get(lut, _lib.DR_LUT_F32),
                         prefetch=int(prefetch))
 
 

@@ -68,3 +68,19 @@ def topk_merge(ids_t, dist_t, stream=None):
     check(lib().dr_topk_merge_dev(ids_t.data_ptr(), dist_t.data_ptr(), G, B, k, oi.data_ptr(), od.data_ptr(),
                                   ids_t.device.index or 0, st), "dr_topk_merge_dev")
     return oi, od
+
+
+def pq_lut_u8(codebook, Q, fmt="u8", device=0):
+    """The throughput search's 8-bit ADC table (pq.cu / lut_tc.cu) in plain order:
+    -> (table u8[B, M, 256], scale f32[B], offset f32[B]) with ADC^2 ~= offset + scale * sum_m table[b, m, code_m].
+    fmt "u8" = CUDA-core build (restated bit-for-bit by oracle.c:orc_lut_u8), "u8tc" = tensor-core build (TF32 products)."""
+    from . import _lib
+    codebook = as_f32(codebook); Q = as_f32(np.atleast_2d(Q))
+    M, _, ds = codebook.shape
+    B, D = Q.shape
+    if D != M * ds:
+        raise ValueError(f"query dimension {D} != M * ds = {M * ds}")
+    tab = np.empty((B, M, 256), np.uint8); sc = np.empty(B, np.float32); off = np.empty(B, np.float32)
+    check(lib().dr_pq_lut_u8(ptr(codebook), ptr(Q), B, D, M, _lib.DR_LUT_U8_TC if fmt == "u8tc" else _lib.DR_LUT_U8,
+                             ptr(tab), ptr(sc), ptr(off), device), "dr_pq_lut_u8")
+    return tab, sc, off

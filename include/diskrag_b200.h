@@ -40,6 +40,8 @@ typedef struct dr_index dr_index; /* opaque device-resident index (vectors, adja
 /* ADC table format held in shared memory */
 #define DR_LUT_F32 0 /* M x 256 fp32, bit-identical to DiskANNPQ.compute_distance_table */
 #define DR_LUT_U8 1  /* M x 256 bytes: q = rint((T - min_m) / scale), scale = max range / 255; exact integer sums */
+#define DR_LUT_U8_TC 2 /* the same table built on the tensor cores (tcgen05, TF32 products): entries within one unit of DR_LUT_U8;
+                          needs M % 4 == 0 and (D / M) % 8 == 0 */
 
 /* per-query status bits written to out_status */
 #define DR_ST_OK 0
@@ -131,6 +133,10 @@ int dr_lut_build(dr_index *h, const float *Q, int64_t B, float *out);
 int dr_lut_build_dev(dr_index *h, const float *d_Q, int64_t B, float *d_out, void *stream);
 /* same without an index: codebook f32[M,256,D/M] on the host (the DiskANNPQ object's own method) */
 int dr_pq_lut(const float *codebook, const float *Q, int64_t B, int32_t D, int32_t M, float *out, int device);
+/* The throughput search's 8-bit table (DR_LUT_U8 / DR_LUT_U8_TC), exposed for tests: out u8[B, M, 256] in plain
+ * (subspace, centroid) order, out_scale / out_offset f32[B]: ADC^2 ~= offset + scale * sum_m out[b][m][code_m]. */
+int dr_pq_lut_u8(const float *codebook, const float *Q, int64_t B, int32_t D, int32_t M, int32_t lut_fmt, uint8_t *out,
+                 float *out_scale, float *out_offset, int device);
 /* dr_pq_train replaces DiskANNPQ.fit (fast_pq.py:197-243; M x KMeans(256)): X f32[N,D] -> codebook
  *   f32[M,256,D/M].  Lloyd iterations on the device; not bit-comparable with sklearn's k-means++
  *    — judged by quantisation error.  out_mse (may be NULL) = mean squared error. */
