@@ -7,7 +7,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libdiskrag_b200.so"
-SOURCES = ["api.cu", "search.cu", "search_fast.cu", "lut_tc.cu", "pq.cu", "distance.cu", "build.cu"]
+SOURCES = ["api.cu", "search.cu", "search_fast.cu", "lut_tc.cu", "kmeans_tc.cu", "pq.cu", "distance.cu", "build.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # FMAs only where written explicitly: the summation orders are part of the contract
@@ -26,7 +26,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", HERE.parent / "include" / "diskrag_b200.h"]
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", CSRC / "tc_common.cuh", HERE.parent / "include" / "diskrag_b200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

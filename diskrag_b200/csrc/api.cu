@@ -412,6 +412,11 @@ int dr_pq_lut_u8(const float *codebook, const float *Q, int64_t B, int32_t D, in
     return 0;
 }
 
+int dr_pq_train_tensor_cores(int enable) {
+    pq_train_set_tensor_cores(enable);
+    return 0;
+}
+
 int dr_pq_train_dev(const float *d_X, int64_t N, int32_t D, int32_t M, int32_t iters, uint64_t seed, float *d_out_codebook,
                     double *out_mse, int device, void *stream) {
     if (use_device(device)) return 3;

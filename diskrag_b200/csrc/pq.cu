@@ -517,6 +517,11 @@ int launch_pq_encode(const float *d_codebook, const float *d_X, int64_t N, int D
     return 0;
 }
 
+int launch_kmeans_assign_tc(const float *d_X, long long N, int D, int M, long long stride, const float *d_codebook, float *d_sums,
+                            int *d_counts, double *d_sse, cudaStream_t s);   // kmeans_tc.cu (tcgen05)
+static std::atomic<int> g_kmeans_tc{1};
+void pq_train_set_tensor_cores(int enable) { g_kmeans_tc.store(enable ? 1 : 0); }
+
 int launch_pq_train(const float *d_X, int64_t N, int D, int M, int iters, uint64_t seed, float *d_codebook,
                     double *out_mse, cudaStream_t s) {
     DR_CHECK(M > 0 && D % M == 0, "dr_pq_train: D=%d not divisible by M=%d", D, M);
@@ -537,12 +542,19 @@ int launch_pq_train(const float *d_X, int64_t N, int D, int M, int iters, uint64
     size_t smem = assign_smem(ds, true);
     DR_CUDA(cudaFuncSetAttribute(assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((ntrain + 255) / 256), M);
+    const bool use_tc = g_kmeans_tc.load() != 0 && (ds & 7) == 0 && ds <= 64;
     for (int it = 0; it < iters; ++it) {
         DR_CUDA(cudaMemsetAsync(d_sums, 0, (size_t)M * 256 * ds * 4, s));
         DR_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)M * 256 * 4, s));
         DR_CUDA(cudaMemsetAsync(d_sse, 0, 8, s));
-        assign_kernel<true><<<grid, 256, smem, s>>>(d_X, ntrain, D, M, stride, 0, d_codebook, nullptr, d_sums, d_counts, d_sse);
-        DR_LAUNCHED();
+        // assignment: tensor cores (TF32 contraction rows x centroids) when the sub-dimension allows, else CUDA cores;
+        // the last pass, which only measures the error of the final codebook, is always exact
+        if (use_tc && it + 1 < iters) {
+            if (launch_kmeans_assign_tc(d_X, ntrain, D, M, stride, d_codebook, d_sums, d_counts, d_sse, s)) return 1;
+        } else {
+            assign_kernel<true><<<grid, 256, smem, s>>>(d_X, ntrain, D, M, stride, 0, d_codebook, nullptr, d_sums, d_counts, d_sse);
+            DR_LAUNCHED();
+        }
         if (it + 1 < iters) {  // the last pass only measures the error of the final codebook
             update_kernel<<<M * 256, 32, 0, s>>>(d_codebook, d_sums, d_counts, d_X, N, D, M, seed, it);
             DR_LAUNCHED();

@@ -27,7 +27,7 @@ struct FastArgs {
     int32_t *list_ids; float *list_dist; int32_t *list_len; int32_t *status;
     u64 *counter;
     uint32_t *ovf; uint32_t ovf_cap; uint32_t hash_cap;
-    int o_q, o_list0, o_list1, o_newk, o_newid, o_sel, o_hash;
+    int o_q, o_list0, o_list1, o_ur0, o_ur1, o_newk, o_newid, o_sel, o_hash;
 };
 
 __device__ __forceinline__ u64 make_ikey(uint32_t sum, uint32_t id) { return ((u64)sum << 32) | ((u64)id << 1); }
@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
     float *s_q = reinterpret_cast<float *>(dr_smem + a.o_q);
     u64 *s_list0 = reinterpret_cast<u64 *>(dr_smem + a.o_list0);
     u64 *s_list1 = reinterpret_cast<u64 *>(dr_smem + a.o_list1);
+    uint16_t *s_ur0 = reinterpret_cast<uint16_t *>(dr_smem + a.o_ur0);   // per list entry: unexpanded entries before it
+    uint16_t *s_ur1 = reinterpret_cast<uint16_t *>(dr_smem + a.o_ur1);
     u64 *s_newk = reinterpret_cast<u64 *>(dr_smem + a.o_newk);
     uint32_t *s_newid = reinterpret_cast<uint32_t *>(dr_smem + a.o_newid);
     uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
     __shared__ u64 s_pfkey;   // prefetch == 2: a survivor below this key is among the next step's likely expansions
     __shared__ __align__(8) uint64_t s_lutbar;
     __shared__ __align__(8) uint64_t s_rrbar[16];   // rerank staging: two half-row barriers per warp
-    __shared__ int s_nn2[2], s_ns, s_p0, s_minpos, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
+    __shared__ int s_nn2[2], s_ns, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
 
     const int tid = threadIdx.x, nt = blockDim.x, nw = nt >> 5;
     int lane = tid & 31, wid = tid >> 5;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
     uint32_t *my_ovf = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
     uint32_t lut_phase = 0;
 #ifdef DR_PHASE_TIMING
-    long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt_last = clock64();
+    long long pt_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt_last = clock64();
 #endif
     if (tid == 0) {
         mbar_init(&s_lutbar, 1);
@@ -307,10 +309,6 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             mbar_expect_tx(&s_lutbar, (uint32_t)M * 256u);
             bulk_g2s(s_lut, a.lut8 + (size_t)b * M * 256, (uint32_t)M * 256u, &s_lutbar);
         }
-        if (a.rerank) {
-            const float *qg = a.Q + (size_t)b * D;
-            for (int i = tid; i < D; i += nt) s_q[i] = __ldg(qg + i);
-        }
         for (uint32_t i = tid; i < a.hash_cap; i += nt) s_hash[i] = DR_EMPTY;
         if (!WP) { mbar_wait(&s_lutbar, lut_phase); lut_phase ^= 1u; }
         __syncthreads();
@@ -328,64 +326,49 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             if (lane == 0) {
                 s_list0[0] = make_ikey(s0, a.start);
                 s_hash[fib_slot(a.start, hshift)] = a.start;
+                s_ur0[0] = 0; s_ur0[1] = 1;      // one unexpanded entry
+                s_sel[W] = 0u; s_ns = 1;         // the first step expands list position 0
+                s_pfkey = DR_KEY_MAX;
             }
         }
         int cur = 0, n = 1, hops = 0, nvis = 1, step = 0;
-        int fstart = 0;   // every list entry before fstart is expanded (scan hint, identical in all threads)
+        int ubase = 0;    // entries marked expanded since the ur[] array of the current list was written
         __syncthreads();
         DR_PT(1);   // table / query staging, start node
 
         for (;;) {
             u64 *lst = cur ? s_list1 : s_list0;
             u64 *oth = cur ? s_list0 : s_list1;
-            // (1+2) warp s finds the s-th unexpanded entry itself (no marking yet, so the scans do not race), loads
-            //       that node's adjacency row and claims its first-seen neighbours
+            // (1+2) The selection (list positions of the first W unexpanded entries, s_sel / s_ns) was produced by the
+            //       previous step's merge: warp s loads that node's adjacency row and claims its first-seen neighbours.
+            uint16_t *ur_old = cur ? s_ur1 : s_ur0;
+            uint16_t *ur_new = cur ? s_ur0 : s_ur1;
             int *p_nn = &s_nn2[step & 1];
+            const int ns = s_ns;
+            if (ns == 0) break;
             const bool use_ovf_now = (s_hcount + W * R > hlimit);   // same value for every thread (read after the last barrier)
+            if (use_ovf_now && (s_ovfcount + W * R > ovf_limit)) {
+                if (tid == 0) s_status |= DR_ST_VISITED_OVERFLOW;
+                break;
+            }
             if (tid == 0) {
                 s_mvalid = 0;
                 if (use_ovf_now) s_ovfused = 1;
             }
-            const bool ovf_full = use_ovf_now && (s_ovfcount + W * R > ovf_limit);
-            for (int s = wid; s < W; s += nw) {
-                int found = 0, pos = -1, pos2 = -1;
-                const bool need_total = (s == 0);   // warp 0 also publishes how many nodes are expanded this step
-                const bool spec = (a.prefetch == 2);
-                const int t2 = s + W;               // prefetch == 2: the entry that would be expanded next step if nothing better turns up
-                for (int base = fstart & ~31;
-                     base < n && (pos < 0 || (need_total && found < W) || (spec && pos2 < 0)); base += 32) {
-                    const int i = base + lane;
-                    const bool un = (i < n) && !(lst[i] & 1ull);
-                    const unsigned m = __ballot_sync(DR_FULL, un);
-                    const int c = __popc(m);
-                    const int myrank = found + __popc(m & lt_mask);
-                    if (pos < 0 && found + c > s) pos = base + __ffs(__ballot_sync(DR_FULL, un && myrank == s)) - 1;
-                    if (spec && pos2 < 0 && found + c > t2) pos2 = base + __ffs(__ballot_sync(DR_FULL, un && myrank == t2)) - 1;
-                    found += c;
-                }
-                if (spec) {
-                    if (pos2 >= 0) {
-                        const u64 k2 = lst[pos2];
-                        if (lane * 32 < R) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(k2) * R + lane * 32));
-                        if (s == W - 1 && lane == 0) s_pfkey = k2;
-                    } else if (s == W - 1 && lane == 0) {
-                        s_pfkey = DR_KEY_MAX;
-                    }
-                }
-                if (need_total && lane == 0) {
-                    int tot = found < W ? found : W;
-                    if (ovf_full) { s_status |= DR_ST_VISITED_OVERFLOW; tot = 0; }
-                    s_ns = tot;
-                    s_p0 = pos;
-                }
-                if (pos < 0 || ovf_full) continue;   // warp-uniform
-                if (lane == 0) s_sel[W + s] = (uint32_t)pos;
+            const bool spec = (a.prefetch == 2);
+            for (int s = wid; s < ns; s += nw) {
+                const int pos = (int)s_sel[W + s];
+                DR_PT(6);   // (timing build) selection read
                 const uint32_t node = key_id(lst[pos]);
                 const uint32_t *row = a.adj + (size_t)node * R;
                 for (int j0 = 0; j0 < R; j0 += 32) {
                     const int j = j0 + lane;
                     const uint32_t nb = (j < R) ? __ldg(row + j) : DR_EMPTY;
                     bool valid = (j < R) && ((long long)nb < a.N);
+#ifdef DR_PHASE_TIMING
+                    asm volatile("" ::"r"(nb));
+                    DR_PT(7);   // (timing build) adjacency row arrived
+#endif
                     if (valid && a.deleted) valid = a.deleted[nb] == 0;
                     bool isnew = false;   // equal ids in one row (0-padding): the CAS admits exactly one of them
                     if (valid) isnew = visited_insert_fast(nb, s_hash, hmask, hshift, use_ovf_now, my_ovf, ovf_mask, ovf_shift);
@@ -401,11 +384,10 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             }
             __syncthreads();
             DR_PT(2);   // select + adjacency + visited
-            const int ns = s_ns, p0 = s_p0;
-            if (ns == 0) break;
             const bool use_ovf = use_ovf_now;
             if (tid < ns) lst[s_sel[W + tid]] |= 1ull;        // mark the expanded entries (merge reads them after the next barrier)
-            if (tid == 0) { s_nn2[(step + 1) & 1] = 0; s_minpos = 0x7fffffff; }   // next step's newcomer counter; merge's first insert position
+            ubase += ns;
+            if (tid == 0) s_nn2[(step + 1) & 1] = 0;          // next step's newcomer counter
             ++step;
             // (3) quantised ADC of the newcomers; the survivors are appended compactly
             const int nn = *p_nn;
@@ -438,6 +420,9 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                         }
                         uint32_t gs[4];
                         rows_sum<KW, 4>(M, tab32, wa, (cntw - r * 4) > 2 ? 2 : 1, lane, gs);
+#ifdef DR_PHASE_TIMING
+                        if (r == 0) { asm volatile("" ::"r"(gs[0])); DR_PT(8); }   // (timing build) first group of code rows summed
+#endif
                         if ((lane >> 2) == r) {
                             const int g = lane & 3;
                             mysum = g == 0 ? gs[0] : (g == 1 ? gs[1] : (g == 2 ? gs[2] : gs[3]));
@@ -493,19 +478,43 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             //     up to 32 per warp: every warp bitonic-sorts one 32-key chunk in registers, then every item sums its
             //                        binary-search ranks in the other sorted sequences
             //     more            : rank counting over all newcomers
+            //     Every placed element also gets its unexpanded rank (unexpanded old entries before it, from ur_old, plus
+            //     the newcomers before it): ranks < W are the next step's selection, so no step ever scans the list.
+            const int total = n + mv;
+            const int nnew = total < L ? total : L;
+            auto place = [&](u64 key, int pos, int from, bool isnew) {
+                if (pos >= L) return;
+                const int ub = (int)ur_old[from] - ubase;
+                const int rank = (ub > 0 ? ub : 0) + (pos - from);
+                const bool un = isnew || !(key & 1ull);
+                oth[pos] = key;
+                ur_new[pos] = (uint16_t)rank;
+                if (un) {
+                    if (rank < W) s_sel[W + rank] = (uint32_t)pos;
+                    else if (spec && rank < 2 * W) {     // next in line: likely to be expanded in two steps
+                        for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(key) * R + o));
+                        if (rank == 2 * W - 1) s_pfkey = key;
+                    }
+                }
+                if (pos == nnew - 1) {
+                    const int tot = rank + (un ? 1 : 0);
+                    ur_new[nnew] = (uint16_t)tot;
+                    s_ns = tot < W ? tot : W;
+                    if (spec && tot < 2 * W) s_pfkey = DR_KEY_MAX;
+                }
+            };
             if (mv > 0) {
-                const int total = n + mv;
-                if (mv <= DR_MERGE_LINEAR) {
+                if (mv <= DR_MERGE_LINEAR || mv > 32 * nw) {
                     for (int x = tid; x < total; x += nt) {
                         u64 key;
-                        int pos;
-                        if (x < n) { key = lst[x]; pos = x; }
-                        else { key = s_newk[x - n]; pos = lower_bound_u64(lst, n, key); }
+                        int pos, from;
+                        if (x < n) { key = lst[x]; from = x; }
+                        else { key = s_newk[x - n]; from = lower_bound_u64(lst, n, key); }
+                        pos = from;
                         for (int j = 0; j < mv; ++j) pos += (s_newk[j] < key) ? 1 : 0;
-                        if (x >= n) atomicMin(&s_minpos, pos);
-                        if (pos < L) oth[pos] = key;
+                        place(key, pos, from, x >= n);
                     }
-                } else if (mv <= 32 * nw) {
+                } else {
                     const int nch = (mv + 31) >> 5;
                     if (wid < nch) {
                         const int idx = (wid << 5) + lane;
@@ -527,41 +536,48 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                     __syncthreads();
                     for (int x = tid; x < total; x += nt) {
                         u64 key;
-                        int pos, own = -1;
-                        if (x < n) { key = lst[x]; pos = x; }
+                        int pos, from, own = -1;
+                        if (x < n) { key = lst[x]; from = x; pos = x; }
                         else {
                             const int j = x - n;
                             key = s_newk[j];
                             own = j >> 5;
-                            pos = (j & 31) + lower_bound_u64(lst, n, key);
+                            from = lower_bound_u64(lst, n, key);
+                            pos = (j & 31) + from;
                         }
                         for (int c = 0; c < nch; ++c) {
                             if (c == own) continue;
                             const int sz = (mv - (c << 5)) < 32 ? (mv - (c << 5)) : 32;
                             pos += lower_bound_u64(s_newk + (c << 5), sz, key);
                         }
-                        if (x >= n && ((x - n) & 31) == 0) atomicMin(&s_minpos, pos);   // chunk minima
-                        if (pos < L) oth[pos] = key;
-                    }
-                } else {
-                    for (int x = tid; x < total; x += nt) {
-                        u64 key;
-                        int pos;
-                        if (x < n) { key = lst[x]; pos = x; }
-                        else { key = s_newk[x - n]; pos = lower_bound_u64(lst, n, key); }
-                        for (int j = 0; j < mv; ++j) pos += (s_newk[j] < key) ? 1 : 0;
-                        if (x >= n) atomicMin(&s_minpos, pos);
-                        if (pos < L) oth[pos] = key;
+                        place(key, pos, from, x >= n);
                     }
                 }
                 cur ^= 1;
-                n = total < L ? total : L;
-                __syncthreads();   // the next step's scans read the merged list
+                n = nnew;
+                ubase = 0;
+                __syncthreads();   // the next step reads the merged list and its selection
                 DR_PT(4);   // merge
-                const int mp = s_minpos;
-                fstart = (p0 + 1) < mp ? (p0 + 1) : mp;
             } else {
-                fstart = p0 + 1;
+                // nothing survived: the list stays, the selection moves on by the ns entries just expanded
+                for (int x = tid; x < n; x += nt) {
+                    const int r = (int)ur_old[x] - ubase;
+                    if (!(lst[x] & 1ull)) {
+                        if (r < W) s_sel[W + r] = (uint32_t)x;
+                        else if (spec && r < 2 * W) {
+                            for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(lst[x]) * R + o));
+                            if (r == 2 * W - 1) s_pfkey = lst[x];
+                        }
+                    }
+                }
+                if (tid == 0) {
+                    int tot = (int)ur_old[n] - ubase;
+                    tot = tot > 0 ? tot : 0;
+                    s_ns = tot < W ? tot : W;
+                    if (spec && tot < 2 * W) s_pfkey = DR_KEY_MAX;
+                }
+                __syncthreads();
+                DR_PT(4);
             }
         }
 
@@ -583,18 +599,24 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
             const int slot = (D * 4 + 15) & ~15;
             int nsl = (M * 256) / slot;
             nsl = nsl < nw ? nsl : nw;
-            if (nsl >= 1 && (D & 3) == 0) {
+            const bool staged = nsl >= 1 && (D & 3) == 0;
+            float *buf = reinterpret_cast<float *>(s_lut + wid * slot);
+            uint64_t *bar0 = &s_rrbar[2 * (wid & 7)], *bar1 = bar0 + 1;
+            const int e0 = (((D + 127) >> 7) >> 1) << 7;     // elements in the first piece (multiple of 128, may be 0)
+            const uint32_t by0 = (uint32_t)e0 * 4u, by1 = (uint32_t)(D - e0) * 4u;
+            if (staged && wid < nsl && lane == 0 && wid < n) {   // first rows in flight before anything else
+                const float *row = a.vec + (size_t)key_id(lst[wid]) * D;
+                fence_proxy_async();
+                if (by0) { mbar_expect_tx(bar0, by0); bulk_g2s_hint(buf, row, by0, bar0, pol_stream); }
+                mbar_expect_tx(bar1, by1); bulk_g2s_hint(buf + e0, row + e0, by1, bar1, pol_stream);
+            }
+            {   // the query vector goes where the (dead) visited table was
+                const float *qg = a.Q + (size_t)b * D;
+                for (int i = tid; i < D; i += nt) s_q[i] = __ldg(qg + i);
+            }
+            __syncthreads();
+            if (staged) {
                 if (wid < nsl) {
-                    float *buf = reinterpret_cast<float *>(s_lut + wid * slot);
-                    uint64_t *bar0 = &s_rrbar[2 * wid], *bar1 = bar0 + 1;
-                    const int e0 = (((D + 127) >> 7) >> 1) << 7;     // elements in the first piece (multiple of 128, may be 0)
-                    const uint32_t by0 = (uint32_t)e0 * 4u, by1 = (uint32_t)(D - e0) * 4u;
-                    if (lane == 0 && wid < n) {
-                        const float *row = a.vec + (size_t)key_id(lst[wid]) * D;
-                        fence_proxy_async();
-                        if (by0) { mbar_expect_tx(bar0, by0); bulk_g2s_hint(buf, row, by0, bar0, pol_stream); }
-                        mbar_expect_tx(bar1, by1); bulk_g2s_hint(buf + e0, row + e0, by1, bar1, pol_stream);
-                    }
                     for (int i = wid; i < n; i += nsl) {
                         const int inext = i + nsl;
                         const float *rown = inext < n ? a.vec + (size_t)key_id(lst[inext]) * D : nullptr;
@@ -664,7 +686,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
     }
 #ifdef DR_PHASE_TIMING
     if (tid == 0)
-        for (int i = 0; i < 8; ++i) atomicAdd(a.counter + 1 + i, (u64)pt_acc[i]);
+        for (int i = 0; i < 12; ++i) atomicAdd(a.counter + 1 + i, (u64)pt_acc[i]);
 #endif
 }
 
@@ -696,16 +718,22 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
              "dr_search: DR_LUT_U8_TC needs M %% 4 == 0, M <= 256 and (D / M) %% 8 == 0 (D=%d M=%d)", h->D, h->M);
     fast_kernel_t kern = pick_fast_kernel(h->M);
     int off = ((h->M * 256 + 15) / 16) * 16;
-    a.o_q = off; off += p->rerank ? ((h->D * 4 + 15) / 16) * 16 : 0;
     const int LC = (p->L + 2) & ~1;
     a.o_list0 = off; off += LC * 8;
     a.o_list1 = off; off += LC * 8;
+    a.o_ur0 = off; off += ((LC + 2) * 2 + 7) / 8 * 8;
+    a.o_ur1 = off; off += ((LC + 2) * 2 + 7) / 8 * 8;
     const int NC = (p->W * h->R + 1) & ~1;
     a.o_newk = off; off += NC * 8;
     a.o_newid = off; off += NC * 4;
     a.o_sel = off; off += ((2 * p->W * 4 + 7) / 8) * 8;
+    off = (off + 15) / 16 * 16;
     a.o_hash = off;
     const int fixed = off;
+    // The query vector (rerank only) lives in the visited table's bytes once the traversal is over, behind the rerank
+    // keys; a table too small for that (tests force small ones) gets a region of its own after it.
+    const int q_in_hash = ((p->L * 8 + 15) / 16) * 16;
+    const int q_bytes = p->rerank ? ((h->D * 4 + 15) / 16) * 16 : 0;
     // visited table: enough for the typical visit count at <= 3/4 load, then whatever keeps 3 CTAs per SM
     uint32_t hc;
     int min_hash = 1024;
@@ -720,11 +748,14 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
         while (hc > 4096 && fixed + (int)hc * 4 + 1024 > h->smem_optin / 3) hc >>= 1;
         while ((int)hc > min_hash && fixed + (int)hc * 4 + 256 > h->smem_optin) hc >>= 1;
     }
-    DR_CHECK((hc & (hc - 1)) == 0 && hc >= 64 && (int)hc * 4 >= p->L * 8 && fixed + (int)hc * 4 + 256 <= h->smem_optin,
+    int q_extra = 0;
+    if (q_bytes && (int)hc * 4 < q_in_hash + q_bytes) { a.o_q = fixed + (int)hc * 4; q_extra = q_bytes; }
+    else a.o_q = a.o_hash + q_in_hash;
+    DR_CHECK((hc & (hc - 1)) == 0 && hc >= 64 && (int)hc * 4 >= p->L * 8 && fixed + (int)hc * 4 + q_extra + 512 <= h->smem_optin,
              "dr_search(u8): visited table of %u slots is not usable (power of two, >= 64, >= 2L, %d B of shared memory needed)",
-             hc, fixed + (int)hc * 4);
+             hc, fixed + (int)hc * 4 + q_extra);
     a.hash_cap = hc;
-    const int smem = fixed + (int)hc * 4;
+    const int smem = fixed + (int)hc * 4 + q_extra;
     const int nt = 256;
     DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
@@ -793,11 +824,11 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
             u64 hc[16];
             DR_CUDA(cudaStreamSynchronize(s));
             DR_CUDA(cudaMemcpy(hc, h->d_counter, sizeof(hc), cudaMemcpyDeviceToHost));
-            static const char *nm[8] = {"fetch+output", "staging", "P1 select/adj/visited", "P2 adc", "merge", "rerank", "-", "-"};
+            static const char *nm[12] = {"fetch+output", "staging", "P1 visited+barrier", "P2 rest+barrier", "merge", "rerank", "P1 scan", "P1 adj wait", "P2 first group", "-", "-", "-"};
             double tot = 0;
-            for (int i = 0; i < 6; ++i) tot += (double)hc[1 + i];
+            for (int i = 0; i < 9; ++i) tot += (double)hc[1 + i];
             fprintf(stderr, "[phase] %lld queries, grid %d:", (long long)cb, grid);
-            for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.1f%% (%.0f cyc/query)", nm[i], 100.0 * hc[1 + i] / tot, (double)hc[1 + i] / (double)cb);
+            for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.1f%% (%.0f cyc/query)", nm[i], 100.0 * hc[1 + i] / tot, (double)hc[1 + i] / (double)cb);
             fprintf(stderr, "\n");
         }
 #endif

@@ -140,6 +140,9 @@ int dr_pq_lut_u8(const float *codebook, const float *Q, int64_t B, int32_t D, in
 /* dr_pq_train replaces DiskANNPQ.fit (fast_pq.py:197-243; M x KMeans(256)): X f32[N,D] -> codebook
  *   f32[M,256,D/M].  Lloyd iterations on the device; not bit-comparable with sklearn's k-means++
  *    — judged by quantisation error.  out_mse (may be NULL) = mean squared error. */
+/* k-means assignment on the tensor cores (tcgen05, TF32) when D / M is a multiple of 8: on by default; 0 forces the exact
+ * fp32 CUDA-core assignment (tests compare the two by quantisation error).  The final encode is always exact. */
+int dr_pq_train_tensor_cores(int enable);
 int dr_pq_train(const float *X, int64_t N, int32_t D, int32_t M, int32_t iters, uint64_t seed,
                 float *out_codebook, double *out_mse, int device);
 int dr_pq_train_dev(const float *d_X, int64_t N, int32_t D, int32_t M, int32_t iters, uint64_t seed,

@@ -68,3 +68,24 @@ def test_search_with_tensor_core_table_keeps_recall():
     rec = lambda ids: np.mean([len(set(ids[i]) & set(gt[i])) / 10 for i in range(len(gt))])
     assert abs(rec(r0.ids) - rec(r1.ids)) <= 0.005
     assert np.mean(np.all(r0.ids == r1.ids, axis=1)) >= 0.9
+
+
+@pytest.mark.parametrize("D,M", [(64, 8), (256, 16), (384, 16)])
+def test_kmeans_tensor_core_assignment_quality(D, M):
+    """K3: the tcgen05 (TF32) assignment step against the exact fp32 one, same seed and iteration count: judged by the
+    quantisation error of the trained codebook (final pass and encode are exact in both)."""
+    from diskrag_b200._lib import lib
+    from diskrag_b200.pq.fast_pq import DiskANNPQ
+    from diskrag_b200.synth import synth_numpy
+    X = synth_numpy(20000, D, seed=9)
+    try:
+        lib().dr_pq_train_tensor_cores(0)
+        p0 = DiskANNPQ(M); p0.fit(X)
+        lib().dr_pq_train_tensor_cores(1)
+        p1 = DiskANNPQ(M); p1.fit(X)
+    finally:
+        lib().dr_pq_train_tensor_cores(1)
+    assert p1.train_mse_ <= 1.02 * p0.train_mse_, (p1.train_mse_, p0.train_mse_)
+    c1 = p1.encode(X)
+    mse1 = float(((p1.decode(c1) - X) ** 2).mean())
+    assert abs(mse1 - p1.train_mse_) <= 0.05 * mse1
