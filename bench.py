@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--W", type=int, default=8)
     ap.add_argument("--adc", default="tree", choices=["seq", "tree"])
     ap.add_argument("--lut", default="u8tc", choices=["f32", "u8", "u8tc"], help="ADC table: f32 reference arithmetic, u8 exact 8-bit, u8tc 8-bit built on tensor cores")
-    ap.add_argument("--prefetch", type=int, default=0)
+    ap.add_argument("--prefetch", type=int, default=5, help="L2 prefetch bit mask of the throughput kernel (include/diskrag_b200.h); results are unchanged")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries", type=int, default=100_000, help="queries per GPU per step")
     ap.add_argument("--gt-queries", type=int, default=1000)

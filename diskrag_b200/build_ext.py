@@ -12,7 +12,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # FMAs only where written explicitly: the summation orders are part of the contract
     "-Xcompiler", "-fPIC", "-shared",
-] + (["-DDR_PHASE_TIMING"] if os.environ.get("DR_PHASE_TIMING") else [])   # debug: per-phase cycle accounting in the search kernel
+] + (["-DDR_PHASE_TIMING"] if os.environ.get("DR_PHASE_TIMING") else []) + (
+    ["-DDR_FAST_NT=" + os.environ["DR_FAST_NT"]] if os.environ.get("DR_FAST_NT") else [])   # debug: per-phase cycle accounting in the search kernel
 
 
 def _nvcc():

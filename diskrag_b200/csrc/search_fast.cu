@@ -216,11 +216,14 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #define DR_PT(i) do { } while (0)
 #endif
 
+#ifndef DR_FAST_NT
+#define DR_FAST_NT 256   // threads per CTA of the throughput kernel (three CTAs per SM)
+#endif
 #define DR_MERGE_LINEAR 12  // up to this many survivors: rank by counting, no sort
 
 // WORDS > 0: compile-time M / 4;  WORDS == 0: runtime M (M % 4 == 0, M <= 256);  WORDS < 0: byte path (any M)
 template <int WORDS>
-__global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
+__global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastArgs a) {
     constexpr bool WP = WORDS >= 0;
     uint8_t *s_lut = dr_smem;
     float *s_q = reinterpret_cast<float *>(dr_smem + a.o_q);
@@ -264,12 +267,11 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
     uint32_t rr_ph0 = 0, rr_ph1 = 0;
     const uint64_t pol_stream = l2_policy_evict_first();
 
+    if (tid == 0) s_b = (long long)atomicAdd(a.counter, 1ull);
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_b = (long long)atomicAdd(a.counter, 1ull);
-        __syncthreads();
-        DR_PT(0);   // work fetch (and the previous query's output)
-        const long long b = s_b;
+        DR_PT(0);   // the previous query's output
+        const long long b = s_b;      // fetched during the previous query (its table is already on its way to L2)
         if (b >= a.B) break;
 
         // ---- stage the query's table (permuting load: global [w][c][4] -> bank-per-lane layout), the query, the hash
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                 s_mvalid = 0;
                 if (use_ovf_now) s_ovfused = 1;
             }
-            const bool spec = (a.prefetch == 2);
+            const bool spec = (a.prefetch & 2) != 0;
             for (int s = wid; s < ns; s += nw) {
                 const int pos = (int)s_sel[W + s];
                 DR_PT(6);   // (timing build) selection read
@@ -379,7 +381,14 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                         if (lane == 0) basepos = atomicAdd(p_nn, cnt);
                         basepos = __shfl_sync(DR_FULL, basepos, 0);
                     }
-                    if (isnew) s_newid[basepos + __popc(m & lt_mask)] = nb;
+                    if (isnew) {
+                        s_newid[basepos + __popc(m & lt_mask)] = nb;
+                        if (a.prefetch & 4) {   // the code row is needed right after the barrier: start its trip now
+                            const uint8_t *cr = a.codes + (size_t)nb * M;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(cr));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(cr + (M > 128 ? 128 : M - 1)));
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -450,7 +459,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                         basep = __shfl_sync(DR_FULL, basep, 0);
                         if (ok) {
                             s_newk[basep + __popc(okm & lt_mask)] = key;
-                            if (a.prefetch == 1 || (a.prefetch == 2 && key < pfkey))   // likely to be expanded next step
+                            if ((a.prefetch & 1) || ((a.prefetch & 2) && key < pfkey))   // likely to be expanded next step
                                 for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)myid * R + o));
                         }
                     }
@@ -583,6 +592,7 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
 
         const u64 *lst = cur ? s_list1 : s_list0;
         const float sc = a.lut_scale[b], off = a.lut_offset[b];
+        if (tid == 0) s_b = (long long)atomicAdd(a.counter, 1ull);   // next query (every thread holds b in a register by now)
         if (a.list_ids) {
             for (int i = tid; i < L; i += nt) {
                 a.list_ids[(size_t)b * L + i] = i < n ? (int32_t)key_id(lst[i]) : -1;
@@ -615,6 +625,13 @@ __global__ void __launch_bounds__(256, 3) search_fast_kernel(const FastArgs a) {
                 for (int i = tid; i < D; i += nt) s_q[i] = __ldg(qg + i);
             }
             __syncthreads();
+            {   // start the next query's table on its trip to L2: the staging loop of the next iteration hits there
+                const long long bn = s_b;
+                if (bn < a.B) {
+                    const uint8_t *tn = a.lut8 + (size_t)bn * M * 256;
+                    for (int o = tid * 128; o < M * 256; o += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tn + o));
+                }
+            }
             if (staged) {
                 if (wid < nsl) {
                     for (int i = wid; i < n; i += nsl) {
@@ -756,7 +773,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
              hc, fixed + (int)hc * 4 + q_extra);
     a.hash_cap = hc;
     const int smem = fixed + (int)hc * 4 + q_extra;
-    const int nt = 256;
+    const int nt = DR_FAST_NT;
     DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
     DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem));

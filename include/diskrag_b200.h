@@ -60,8 +60,9 @@ typedef struct dr_search_params {
     int32_t chunk;     /* 0 = auto; queries per launch (bounds the device LUT buffer) */
     int32_t threads;   /* 0 = auto; CTA size (multiple of 32) */
     int32_t lut_fmt;   /* DR_LUT_F32 (reference arithmetic) | DR_LUT_U8 (throughput: 8-bit table, integer sums) */
-    int32_t prefetch;  /* DR_LUT_U8 only, results unchanged: 1 = L2-prefetch the adjacency row of every accepted candidate;
-                          2 = speculative: the rows of the W entries next in line and of accepted candidates ranking before them */
+    int32_t prefetch;  /* DR_LUT_U8 only, results unchanged; bit mask of L2 prefetches: 1 = the adjacency row of every accepted
+                          candidate; 2 = speculative: the rows of the W entries next in line and of accepted candidates ranking
+                          before them; 4 = the PQ code row of a neighbour as soon as it is first seen */
 } dr_search_params;
 
 /* ---- library ---- */
