@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--queries", type=int, default=100_000, help="queries per GPU per step")
     ap.add_argument("--gt-queries", type=int, default=1000)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--hash-cap", type=int, default=0, help="force the visited-table size (occupancy experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-profile", action="store_true", help="wrap one extra step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -202,7 +203,7 @@ def run_ours(a):
                                            med, local, keepalive=(X, adj, codes, cb))
     B, k = a.queries, a.k
     Q = synth_torch(B, a.dim, seed=20242, sample_seed=1000 + rank, device=dev)     # each rank: its own query shard
-    p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut,
+    p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut, hash_cap=a.hash_cap,
                            prefetch=int(a.prefetch))
     ids = torch.empty((B, k), dtype=torch.int32, device=dev); dd = torch.empty((B, k), dtype=torch.float32, device=dev)
     hops = torch.empty(B, dtype=torch.int32, device=dev); vis = torch.empty(B, dtype=torch.int32, device=dev)

@@ -9,7 +9,9 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libdiskrag_b200.so"
+import os as _os
+# DISKRAG_B200_LIB: load another build of the same library (A/B runs of kernel variants, scripts/build_variants.py)
+LIB_PATH = Path(_os.environ["DISKRAG_B200_LIB"]) if _os.environ.get("DISKRAG_B200_LIB") else _HERE / "libdiskrag_b200.so"
 
 DR_DIST_PQ, DR_DIST_EXACT = 0, 1
 DR_ADC_SEQ, DR_ADC_TREE = 0, 1

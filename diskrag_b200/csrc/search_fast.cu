@@ -219,7 +219,9 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #ifndef DR_FAST_NT
 #define DR_FAST_NT 256   // threads per CTA of the throughput kernel (three CTAs per SM)
 #endif
-#define DR_MERGE_LINEAR 12  // up to this many survivors: rank by counting, no sort
+#ifndef DR_MERGE_LINEAR
+#define DR_MERGE_LINEAR 32
+#endif  // up to this many survivors: rank by counting, no sort
 
 // WORDS > 0: compile-time M / 4;  WORDS == 0: runtime M (M % 4 == 0, M <= 256);  WORDS < 0: byte path (any M)
 template <int WORDS>
