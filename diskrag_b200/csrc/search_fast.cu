@@ -27,7 +27,8 @@ struct FastArgs {
     int32_t *list_ids; float *list_dist; int32_t *list_len; int32_t *status;
     u64 *counter;
     uint32_t *ovf; uint32_t ovf_cap; uint32_t hash_cap;
-    int o_q, o_list0, o_list1, o_ur0, o_ur1, o_newk, o_newid, o_sel, o_hash;
+    int o_q, o_rrk, o_list0, o_list1, o_ur0, o_ur1, o_newk, o_newid, o_sel, o_hash;
+    int rr_slots;   // rerank staging slots available in the table region (the query vector may occupy the last one)
 };
 
 __device__ __forceinline__ u64 make_ikey(uint32_t sum, uint32_t id) { return ((u64)sum << 32) | ((u64)id << 1); }
@@ -157,8 +158,10 @@ __device__ __forceinline__ void adc_u8_rows(const uint8_t *__restrict__ codes, i
 // hash: the slot is the top log2(cap) bits of id * 2654435761
 __device__ __forceinline__ uint32_t fib_slot(uint32_t id, uint32_t shift) { return (id * 2654435761u) >> shift; }
 __device__ __forceinline__ bool visited_insert_fast(uint32_t nb, uint32_t *hash, uint32_t mask, uint32_t shift, bool use_ovf,
-                                                    uint32_t *ovf, uint32_t ovf_mask, uint32_t ovf_shift) {
-    uint32_t h = fib_slot(nb, shift);
+                                                    uint32_t *ovf, uint32_t ovf_mask, uint32_t ovf_shift, bool no_smem) {
+    uint32_t h;
+    if (no_smem) goto global_table;   // the whole visited set lives in the CTA's global (L2-resident) table
+    h = fib_slot(nb, shift);
     if (!use_ovf) {
         for (;;) {
             const uint32_t old = atomicCAS(&hash[h], DR_EMPTY, nb);
@@ -173,6 +176,7 @@ __device__ __forceinline__ bool visited_insert_fast(uint32_t nb, uint32_t *hash,
         if (cur == DR_EMPTY) break;
         h = (h + 1) & mask;
     }
+global_table:
     h = fib_slot(nb ^ 0x9e3779b9u, ovf_shift);
     for (;;) {
         const uint32_t old = atomicCAS(&ovf[h], DR_EMPTY, nb);
@@ -224,8 +228,10 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #endif  // up to this many survivors: rank by counting, no sort
 
 // WORDS > 0: compile-time M / 4;  WORDS == 0: runtime M (M % 4 == 0, M <= 256);  WORDS < 0: byte path (any M)
-template <int WORDS>
-__global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastArgs a) {
+// MINB = CTAs per SM the register budget is cut for (3: 80 registers; 4: 64 registers, used when the visited set moves out
+// of shared memory so that a fourth CTA fits)
+template <int WORDS, int MINB>
+__global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const FastArgs a) {
     constexpr bool WP = WORDS >= 0;
     uint8_t *s_lut = dr_smem;
     float *s_q = reinterpret_cast<float *>(dr_smem + a.o_q);
@@ -237,7 +243,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastAr
     uint32_t *s_newid = reinterpret_cast<uint32_t *>(dr_smem + a.o_newid);
     uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);
     uint32_t *s_hash = reinterpret_cast<uint32_t *>(dr_smem + a.o_hash);
-    u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_hash);   // rerank keys alias the (dead) visited table
+    u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_rrk);    // rerank keys alias a region that is dead after the traversal
+    const bool no_smem_hash = (a.hash_cap == 0);
 
     __shared__ long long s_b;
     __shared__ u64 s_pfkey;   // prefetch == 2: a survivor below this key is among the next step's likely expansions
@@ -245,16 +252,17 @@ __global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastAr
     __shared__ __align__(8) uint64_t s_rrbar[16];   // rerank staging: two half-row barriers per warp
     __shared__ int s_nn2[2], s_ns, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
 
-    const int tid = threadIdx.x, nt = blockDim.x, nw = nt >> 5;
+    const int tid = threadIdx.x;
+    constexpr int nt = DR_FAST_NT, nw = DR_FAST_NT / 32;   // the launcher always uses DR_FAST_NT threads
     int lane = tid & 31, wid = tid >> 5;
     asm volatile("" : "+r"(lane), "+r"(wid));    // opaque: keep them in registers instead of re-reading %tid in the loops
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tab32 = smem_u32(s_lut);
     const int D = a.D, R = a.R, M = a.M, L = a.L, W = a.W;
     const int words = WORDS > 0 ? WORDS : (M >> 2);
-    const uint32_t hmask = a.hash_cap - 1u, ovf_mask = a.ovf_cap - 1u;
+    const uint32_t hmask = a.hash_cap ? a.hash_cap - 1u : 0u, ovf_mask = a.ovf_cap - 1u;
     const uint32_t hshift = 32u - (uint32_t)__popc(hmask), ovf_shift = 32u - (uint32_t)__popc(ovf_mask);
-    const int hlimit = (int)(a.hash_cap - (a.hash_cap >> 2));
+    const int hlimit = a.hash_cap ? (int)(a.hash_cap - (a.hash_cap >> 2)) : -1;   // no table: "full" from the start
     const int ovf_limit = (int)(a.ovf_cap - (a.ovf_cap >> 2));
     uint32_t *my_ovf = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
     uint32_t lut_phase = 0;
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastAr
         if (b >= a.B) break;
 
         // ---- stage the query's table (permuting load: global [w][c][4] -> bank-per-lane layout), the query, the hash
-        if (tid == 0) { s_hcount = 1; s_ovfcount = 0; s_ovfused = 0; s_status = 0; s_nn2[0] = 0; }
+        if (tid == 0) { s_hcount = 1; s_ovfcount = no_smem_hash ? 1 : 0; s_ovfused = no_smem_hash ? 1 : 0; s_status = 0; s_nn2[0] = 0; }
         if (WP) {
             const int nfull = words >> 5, rem = words & 31;
             const uint4 *src = reinterpret_cast<const uint4 *>(a.lut8 + (size_t)b * M * 256);
@@ -329,7 +337,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastAr
             }
             if (lane == 0) {
                 s_list0[0] = make_ikey(s0, a.start);
-                s_hash[fib_slot(a.start, hshift)] = a.start;
+                if (no_smem_hash) my_ovf[fib_slot(a.start ^ 0x9e3779b9u, ovf_shift)] = a.start;
+                else s_hash[fib_slot(a.start, hshift)] = a.start;
                 s_ur0[0] = 0; s_ur0[1] = 1;      // one unexpanded entry
                 s_sel[W] = 0u; s_ns = 1;         // the first step expands list position 0
                 s_pfkey = DR_KEY_MAX;
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastAr
 #endif
                     if (valid && a.deleted) valid = a.deleted[nb] == 0;
                     bool isnew = false;   // equal ids in one row (0-padding): the CAS admits exactly one of them
-                    if (valid) isnew = visited_insert_fast(nb, s_hash, hmask, hshift, use_ovf_now, my_ovf, ovf_mask, ovf_shift);
+                    if (valid) isnew = visited_insert_fast(nb, s_hash, hmask, hshift, use_ovf_now, my_ovf, ovf_mask, ovf_shift, no_smem_hash);
                     const unsigned m = __ballot_sync(DR_FULL, isnew);
                     const int cnt = __popc(m);
                     int basepos = 0;
@@ -609,7 +618,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastAr
             // row and the first half of the next one are in flight while the warp accumulates; no registers are tied up
             // by loads in flight and 8 rows x 6 KB per CTA keep HBM busy.  Same arithmetic order as warp_l2sq.
             const int slot = (D * 4 + 15) & ~15;
-            int nsl = (M * 256) / slot;
+            int nsl = a.rr_slots;
             nsl = nsl < nw ? nsl : nw;
             const bool staged = nsl >= 1 && (D & 3) == 0;
             float *buf = reinterpret_cast<float *>(s_lut + wid * slot);
@@ -711,16 +720,18 @@ __global__ void __launch_bounds__(DR_FAST_NT, 3) search_fast_kernel(const FastAr
 
 typedef void (*fast_kernel_t)(const FastArgs);
 
-static fast_kernel_t pick_fast_kernel(int M) {
-    if ((M & 3) != 0 || M > 256) return search_fast_kernel<-1>;
+template <int MINB>
+static fast_kernel_t pick_fast_kernel_b(int M) {
+    if ((M & 3) != 0 || M > 256) return search_fast_kernel<-1, MINB>;
     switch (M >> 2) {
-        case 16: return search_fast_kernel<16>;   // M = 64  (the adaptive default at D = 1536, adaptive_pq.py:81-108)
-        case 32: return search_fast_kernel<32>;   // M = 128
-        case 48: return search_fast_kernel<48>;   // M = 192
-        case 64: return search_fast_kernel<64>;   // M = 256
-        default: return search_fast_kernel<0>;
+        case 16: return search_fast_kernel<16, MINB>;   // M = 64  (the adaptive default at D = 1536, adaptive_pq.py:81-108)
+        case 32: return search_fast_kernel<32, MINB>;   // M = 128
+        case 48: return search_fast_kernel<48, MINB>;   // M = 192
+        case 64: return search_fast_kernel<64, MINB>;   // M = 256
+        default: return search_fast_kernel<0, MINB>;
     }
 }
+static fast_kernel_t pick_fast_kernel(int M, int minb) { return minb >= 4 ? pick_fast_kernel_b<4>(M) : pick_fast_kernel_b<3>(M); }
 
 int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, int32_t *ids, float *dist,
                        int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist, int32_t *list_len,
@@ -735,7 +746,10 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     const bool word_layout = ((h->M & 3) == 0) && h->M <= 256;
     DR_CHECK(p->lut_fmt != DR_LUT_U8_TC || (word_layout && ((h->D / h->M) & 7) == 0),
              "dr_search: DR_LUT_U8_TC needs M %% 4 == 0, M <= 256 and (D / M) %% 8 == 0 (D=%d M=%d)", h->D, h->M);
-    fast_kernel_t kern = pick_fast_kernel(h->M);
+    // hash_cap < 0: the visited set lives entirely in the CTA's global table (L2-resident, 32 KB per CTA): no shared-memory
+    // hash, so a fourth CTA fits on the SM next to three 48 KB tables (the kernel is bound by resident queries)
+    const bool l2_visited = p->hash_cap < 0;
+    fast_kernel_t kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3);
     int off = ((h->M * 256 + 15) / 16) * 16;
     const int LC = (p->L + 2) & ~1;
     a.o_list0 = off; off += LC * 8;
@@ -754,10 +768,21 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     const int q_in_hash = ((p->L * 8 + 15) / 16) * 16;
     const int q_bytes = p->rerank ? ((h->D * 4 + 15) / 16) * 16 : 0;
     // visited table: enough for the typical visit count at <= 3/4 load, then whatever keeps 3 CTAs per SM
-    uint32_t hc;
+    uint32_t hc = 0;
     int min_hash = 1024;
     while (min_hash * 4 < p->L * 8) min_hash <<= 1;
-    if (p->hash_cap > 0) hc = (uint32_t)p->hash_cap;
+    const int slot_bytes = (h->D * 4 + 15) & ~15;
+    a.rr_slots = (h->M * 256) / slot_bytes;
+    int q_extra = 0;
+    if (l2_visited) {
+        // rerank keys reuse the newcomer keys' bytes, the query vector takes the last staging slot of the table region
+        a.o_rrk = a.o_newk;
+        if (p->L > NC) { a.o_rrk = fixed; q_extra += ((p->L * 8 + 15) / 16) * 16; }
+        if (q_bytes) {
+            if (a.rr_slots >= 2) { a.rr_slots -= 1; a.o_q = a.rr_slots * slot_bytes; }
+            else { a.o_q = fixed + q_extra; q_extra += q_bytes; a.rr_slots = 0; }   // rows come straight from global memory
+        }
+    } else if (p->hash_cap > 0) hc = (uint32_t)p->hash_cap;
     else {
         uint32_t want = 1024;
         long long target = (long long)(p->L + 2 * p->W) * h->R;
@@ -767,12 +792,16 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
         while (hc > 4096 && fixed + (int)hc * 4 + 1024 > h->smem_optin / 3) hc >>= 1;
         while ((int)hc > min_hash && fixed + (int)hc * 4 + 256 > h->smem_optin) hc >>= 1;
     }
-    int q_extra = 0;
-    if (q_bytes && (int)hc * 4 < q_in_hash + q_bytes) { a.o_q = fixed + (int)hc * 4; q_extra = q_bytes; }
-    else a.o_q = a.o_hash + q_in_hash;
-    DR_CHECK((hc & (hc - 1)) == 0 && hc >= 64 && (int)hc * 4 >= p->L * 8 && fixed + (int)hc * 4 + q_extra + 512 <= h->smem_optin,
-             "dr_search(u8): visited table of %u slots is not usable (power of two, >= 64, >= 2L, %d B of shared memory needed)",
-             hc, fixed + (int)hc * 4 + q_extra);
+    if (!l2_visited) {
+        a.o_rrk = a.o_hash;
+        if (q_bytes && (int)hc * 4 < q_in_hash + q_bytes) { a.o_q = fixed + (int)hc * 4; q_extra = q_bytes; }
+        else a.o_q = a.o_hash + q_in_hash;
+        DR_CHECK((hc & (hc - 1)) == 0 && hc >= 64 && (int)hc * 4 >= p->L * 8 && fixed + (int)hc * 4 + q_extra + 512 <= h->smem_optin,
+                 "dr_search(u8): visited table of %u slots is not usable (power of two, >= 64, >= 2L, %d B of shared memory needed)",
+                 hc, fixed + (int)hc * 4 + q_extra);
+    } else {
+        DR_CHECK(fixed + q_extra + 512 <= h->smem_optin, "dr_search(u8): %d B of shared memory needed", fixed + q_extra);
+    }
     a.hash_cap = hc;
     const int smem = fixed + (int)hc * 4 + q_extra;
     const int nt = DR_FAST_NT;
@@ -782,6 +811,11 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     DR_CHECK(occ >= 1, "dr_search(u8): kernel does not fit (smem %d)", smem);
     const int max_grid = h->sms * occ;
     a.ovf_cap = 65536;
+    if (l2_visited) {   // sized for the visit count (<= 1/2 load), small enough that all CTAs' tables stay in L2
+        uint32_t want = 8192;
+        while ((long long)want / 2 < (long long)(p->L + 2 * p->W) * h->R && want < 65536) want <<= 1;
+        a.ovf_cap = want;
+    }
     size_t need = (size_t)max_grid * a.ovf_cap * 4;
     if (h->ovf_bytes < need) {
         if (h->d_ovf) cudaFree(h->d_ovf);

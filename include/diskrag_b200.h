@@ -56,7 +56,8 @@ typedef struct dr_search_params {
     int32_t adc_order; /* DR_ADC_SEQ | DR_ADC_TREE (DR_DIST_PQ only) */
     int32_t rerank;    /* 1: exact fp32 L2^2 rerank of the final list (search_engine.py:374-379), stable */
     int32_t sqrt_out;  /* 1: report sqrt(d2) like np.linalg.norm (vamana_graph.py:726,743) */
-    int32_t hash_cap;  /* 0 = auto; else forces the shared-memory visited table size (power of two; tests) */
+    int32_t hash_cap;  /* 0 = auto; > 0 forces the shared-memory visited table size (power of two; tests);
+                          < 0 (DR_LUT_U8*) keeps the visited set in a per-CTA global table (L2-resident) instead */
     int32_t chunk;     /* 0 = auto; queries per launch (bounds the device LUT buffer) */
     int32_t threads;   /* 0 = auto; CTA size (multiple of 32) */
     int32_t lut_fmt;   /* DR_LUT_F32 (reference arithmetic) | DR_LUT_U8 (throughput: 8-bit table, integer sums) */

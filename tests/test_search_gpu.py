@@ -149,6 +149,11 @@ def test_u8_table_mode_vs_oracle(case, orc, W):
     L = 48
     r = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=(W == 4))
     r2 = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=False, lut_fmt="u8", hash_cap=256)
+    # visited set kept in the CTA's global (L2-resident) table, four CTAs per SM: same answers, with and without rerank
+    r3 = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", hash_cap=-1, prefetch=5)
+    r4 = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=False, lut_fmt="u8", hash_cap=-1)
+    assert np.array_equal(r3.ids, r.ids) and np.array_equal(r3.dists, r.dists) and np.array_equal(r3.list_ids, r.list_ids)
+    assert np.array_equal(r3.hops, r.hops) and np.array_equal(r3.visited, r.visited) and np.array_equal(r4.ids, r2.ids)
     for qi in range(c["Q"].shape[0]):
         t8, sc, off = orc.lut_u8(c["codebook"], c["Q"][qi])
         l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False)
