@@ -230,7 +230,8 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 // WORDS > 0: compile-time M / 4;  WORDS == 0: runtime M (M % 4 == 0, M <= 256);  WORDS < 0: byte path (any M)
 // MINB = CTAs per SM the register budget is cut for (3: 80 registers; 4: 64 registers, used when the visited set moves out
 // of shared memory so that a fourth CTA fits)
-template <int WORDS, int MINB>
+// RW8 = 1: R == 32 and W == 8 are compile-time (the bench / default serving shape)
+template <int WORDS, int MINB, int RW8>
 __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const FastArgs a) {
     constexpr bool WP = WORDS >= 0;
     uint8_t *s_lut = dr_smem;
@@ -258,7 +259,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     asm volatile("" : "+r"(lane), "+r"(wid));    // opaque: keep them in registers instead of re-reading %tid in the loops
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tab32 = smem_u32(s_lut);
-    const int D = a.D, R = a.R, M = a.M, L = a.L, W = a.W;
+    const int D = a.D, M = a.M, L = a.L;
+    const int R = RW8 ? 32 : a.R, W = RW8 ? 8 : a.W;
     const int words = WORDS > 0 ? WORDS : (M >> 2);
     const uint32_t hmask = a.hash_cap ? a.hash_cap - 1u : 0u, ovf_mask = a.ovf_cap - 1u;
     const uint32_t hshift = 32u - (uint32_t)__popc(hmask), ovf_shift = 32u - (uint32_t)__popc(ovf_mask);
@@ -720,18 +722,21 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
 
 typedef void (*fast_kernel_t)(const FastArgs);
 
-template <int MINB>
+template <int MINB, int RW8>
 static fast_kernel_t pick_fast_kernel_b(int M) {
-    if ((M & 3) != 0 || M > 256) return search_fast_kernel<-1, MINB>;
+    if ((M & 3) != 0 || M > 256) return search_fast_kernel<-1, MINB, RW8>;
     switch (M >> 2) {
-        case 16: return search_fast_kernel<16, MINB>;   // M = 64  (the adaptive default at D = 1536, adaptive_pq.py:81-108)
-        case 32: return search_fast_kernel<32, MINB>;   // M = 128
-        case 48: return search_fast_kernel<48, MINB>;   // M = 192
-        case 64: return search_fast_kernel<64, MINB>;   // M = 256
-        default: return search_fast_kernel<0, MINB>;
+        case 16: return search_fast_kernel<16, MINB, RW8>;   // M = 64  (the adaptive default at D = 1536, adaptive_pq.py:81-108)
+        case 32: return search_fast_kernel<32, MINB, RW8>;   // M = 128
+        case 48: return search_fast_kernel<48, MINB, RW8>;   // M = 192
+        case 64: return search_fast_kernel<64, MINB, RW8>;   // M = 256
+        default: return search_fast_kernel<0, MINB, RW8>;
     }
 }
-static fast_kernel_t pick_fast_kernel(int M, int minb) { return minb >= 4 ? pick_fast_kernel_b<4>(M) : pick_fast_kernel_b<3>(M); }
+static fast_kernel_t pick_fast_kernel(int M, int minb, bool rw8) {
+    if (rw8) return minb >= 4 ? pick_fast_kernel_b<4, 1>(M) : pick_fast_kernel_b<3, 1>(M);
+    return minb >= 4 ? pick_fast_kernel_b<4, 0>(M) : pick_fast_kernel_b<3, 0>(M);
+}
 
 int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, int32_t *ids, float *dist,
                        int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist, int32_t *list_len,
@@ -749,7 +754,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     // hash_cap < 0: the visited set lives entirely in the CTA's global table (L2-resident, 32 KB per CTA): no shared-memory
     // hash, so a fourth CTA fits on the SM next to three 48 KB tables (the kernel is bound by resident queries)
     const bool l2_visited = p->hash_cap < 0;
-    fast_kernel_t kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3);
+    fast_kernel_t kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3, h->R == 32 && p->W == 8);
     int off = ((h->M * 256 + 15) / 16) * 16;
     const int LC = (p->L + 2) & ~1;
     a.o_list0 = off; off += LC * 8;
