@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     asm volatile("" : "+r"(lane), "+r"(wid));    // opaque: keep them in registers instead of re-reading %tid in the loops
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tab32 = smem_u32(s_lut);
-    const int D = a.D, M = a.M, L = a.L;
+    const int D = RW8 == 2 ? 1536 : a.D, M = a.M, L = a.L;      // RW8 == 2: additionally D == 1536 (text-embedding-3-small)
     const int R = RW8 ? 32 : a.R, W = RW8 ? 8 : a.W;
     const int words = WORDS > 0 ? WORDS : (M >> 2);
     const uint32_t hmask = a.hash_cap ? a.hash_cap - 1u : 0u, ovf_mask = a.ovf_cap - 1u;
@@ -733,7 +733,8 @@ static fast_kernel_t pick_fast_kernel_b(int M) {
         default: return search_fast_kernel<0, MINB, RW8>;
     }
 }
-static fast_kernel_t pick_fast_kernel(int M, int minb, bool rw8) {
+static fast_kernel_t pick_fast_kernel(int M, int minb, int rw8) {
+    if (rw8 == 2) return minb >= 4 ? pick_fast_kernel_b<4, 2>(M) : pick_fast_kernel_b<3, 2>(M);
     if (rw8) return minb >= 4 ? pick_fast_kernel_b<4, 1>(M) : pick_fast_kernel_b<3, 1>(M);
     return minb >= 4 ? pick_fast_kernel_b<4, 0>(M) : pick_fast_kernel_b<3, 0>(M);
 }
@@ -754,7 +755,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     // hash_cap < 0: the visited set lives entirely in the CTA's global table (L2-resident, 32 KB per CTA): no shared-memory
     // hash, so a fourth CTA fits on the SM next to three 48 KB tables (the kernel is bound by resident queries)
     const bool l2_visited = p->hash_cap < 0;
-    fast_kernel_t kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3, h->R == 32 && p->W == 8);
+    fast_kernel_t kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3, (h->R == 32 && p->W == 8) ? (h->D == 1536 ? 2 : 1) : 0);
     int off = ((h->M * 256 + 15) / 16) * 16;
     const int LC = (p->L + 2) & ~1;
     a.o_list0 = off; off += LC * 8;
