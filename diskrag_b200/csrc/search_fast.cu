@@ -230,7 +230,8 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 // WORDS > 0: compile-time M / 4;  WORDS == 0: runtime M (M % 4 == 0, M <= 256);  WORDS < 0: byte path (any M)
 // MINB = CTAs per SM the register budget is cut for (3: 80 registers; 4: 64 registers, used when the visited set moves out
 // of shared memory so that a fourth CTA fits)
-// RW8 = 1: R == 32 and W == 8 are compile-time (the bench / default serving shape)
+// RW8 = 1: R == 32 and W == 8 are compile-time; RW8 = 2: also D == 1536; RW8 = 3: also L == 100 and a 4096-slot visited table
+// (the bench / default serving shape: text-embedding-3-small vectors, beam 100)
 template <int WORDS, int MINB, int RW8>
 __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const FastArgs a) {
     constexpr bool WP = WORDS >= 0;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);
     uint32_t *s_hash = reinterpret_cast<uint32_t *>(dr_smem + a.o_hash);
     u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_rrk);    // rerank keys alias a region that is dead after the traversal
-    const bool no_smem_hash = (a.hash_cap == 0);
+    const bool no_smem_hash = RW8 == 3 ? false : (a.hash_cap == 0);
 
     __shared__ long long s_b;
     __shared__ u64 s_pfkey;   // prefetch == 2: a survivor below this key is among the next step's likely expansions
@@ -259,14 +260,16 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     asm volatile("" : "+r"(lane), "+r"(wid));    // opaque: keep them in registers instead of re-reading %tid in the loops
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tab32 = smem_u32(s_lut);
-    const int D = RW8 == 2 ? 1536 : a.D, M = a.M, L = a.L;      // RW8 == 2: additionally D == 1536 (text-embedding-3-small)
+    const int D = RW8 >= 2 ? 1536 : a.D, M = a.M, L = RW8 == 3 ? 100 : a.L;
+    const uint32_t hcap = RW8 == 3 ? 4096u : a.hash_cap;
     const int R = RW8 ? 32 : a.R, W = RW8 ? 8 : a.W;
     const int words = WORDS > 0 ? WORDS : (M >> 2);
-    const uint32_t hmask = a.hash_cap ? a.hash_cap - 1u : 0u, ovf_mask = a.ovf_cap - 1u;
+    const uint32_t hmask = hcap ? hcap - 1u : 0u, ovf_mask = a.ovf_cap - 1u;
     const uint32_t hshift = 32u - (uint32_t)__popc(hmask), ovf_shift = 32u - (uint32_t)__popc(ovf_mask);
-    const int hlimit = a.hash_cap ? (int)(a.hash_cap - (a.hash_cap >> 2)) : -1;   // no table: "full" from the start
+    const int hlimit = hcap ? (int)(hcap - (hcap >> 2)) : -1;   // no table: "full" from the start
     const int ovf_limit = (int)(a.ovf_cap - (a.ovf_cap >> 2));
     uint32_t *my_ovf = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
+    const uint32_t n32 = a.N > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)a.N;   // ids are 32-bit; DR_EMPTY is never valid
     uint32_t lut_phase = 0;
 #ifdef DR_PHASE_TIMING
     long long pt_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt_last = clock64();
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             mbar_expect_tx(&s_lutbar, (uint32_t)M * 256u);
             bulk_g2s(s_lut, a.lut8 + (size_t)b * M * 256, (uint32_t)M * 256u, &s_lutbar);
         }
-        for (uint32_t i = tid; i < a.hash_cap; i += nt) s_hash[i] = DR_EMPTY;
+        for (uint32_t i = tid; i < hcap; i += nt) s_hash[i] = DR_EMPTY;
         if (!WP) { mbar_wait(&s_lutbar, lut_phase); lut_phase ^= 1u; }
         __syncthreads();
 
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 for (int j0 = 0; j0 < R; j0 += 32) {
                     const int j = j0 + lane;
                     const uint32_t nb = (j < R) ? __ldg(row + j) : DR_EMPTY;
-                    bool valid = (j < R) && ((long long)nb < a.N);
+                    bool valid = (j < R) && (nb < n32);
 #ifdef DR_PHASE_TIMING
                     asm volatile("" ::"r"(nb));
                     DR_PT(7);   // (timing build) adjacency row arrived
@@ -734,7 +737,8 @@ static fast_kernel_t pick_fast_kernel_b(int M) {
     }
 }
 static fast_kernel_t pick_fast_kernel(int M, int minb, int rw8) {
-    if (rw8 == 2) return minb >= 4 ? pick_fast_kernel_b<4, 2>(M) : pick_fast_kernel_b<3, 2>(M);
+    if (rw8 == 3 && minb < 4) return pick_fast_kernel_b<3, 3>(M);
+    if (rw8 >= 2) return minb >= 4 ? pick_fast_kernel_b<4, 2>(M) : pick_fast_kernel_b<3, 2>(M);
     if (rw8) return minb >= 4 ? pick_fast_kernel_b<4, 1>(M) : pick_fast_kernel_b<3, 1>(M);
     return minb >= 4 ? pick_fast_kernel_b<4, 0>(M) : pick_fast_kernel_b<3, 0>(M);
 }
@@ -755,7 +759,9 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     // hash_cap < 0: the visited set lives entirely in the CTA's global table (L2-resident, 32 KB per CTA): no shared-memory
     // hash, so a fourth CTA fits on the SM next to three 48 KB tables (the kernel is bound by resident queries)
     const bool l2_visited = p->hash_cap < 0;
-    fast_kernel_t kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3, (h->R == 32 && p->W == 8) ? (h->D == 1536 ? 2 : 1) : 0);
+    int shape = (h->R == 32 && p->W == 8) ? (h->D == 1536 ? 2 : 1) : 0;
+    if (shape == 2 && p->L == 100 && p->hash_cap == 0) shape = 3;   // confirmed below once the table size is known
+    fast_kernel_t kern = nullptr;
     int off = ((h->M * 256 + 15) / 16) * 16;
     const int LC = (p->L + 2) & ~1;
     a.o_list0 = off; off += LC * 8;
@@ -809,6 +815,8 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
         DR_CHECK(fixed + q_extra + 512 <= h->smem_optin, "dr_search(u8): %d B of shared memory needed", fixed + q_extra);
     }
     a.hash_cap = hc;
+    if (shape == 3 && hc != 4096) shape = 2;
+    kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3, shape);
     const int smem = fixed + (int)hc * 4 + q_extra;
     const int nt = DR_FAST_NT;
     DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
