@@ -231,7 +231,8 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 // MINB = CTAs per SM the register budget is cut for (3: 80 registers; 4: 64 registers, used when the visited set moves out
 // of shared memory so that a fourth CTA fits)
 // RW8 = 1: R == 32 and W == 8 are compile-time; RW8 = 2: also D == 1536; RW8 = 3: also L == 100 and a 4096-slot visited table
-// (the bench / default serving shape: text-embedding-3-small vectors, beam 100)
+// (the bench / default serving shape: text-embedding-3-small vectors, beam 100); RW8 = 4: also prefetch mask 5, no
+// lazy-delete mask, rerank on
 template <int WORDS, int MINB, int RW8>
 __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const FastArgs a) {
     constexpr bool WP = WORDS >= 0;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);
     uint32_t *s_hash = reinterpret_cast<uint32_t *>(dr_smem + a.o_hash);
     u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_rrk);    // rerank keys alias a region that is dead after the traversal
-    const bool no_smem_hash = RW8 == 3 ? false : (a.hash_cap == 0);
+    const bool no_smem_hash = RW8 >= 3 ? false : (a.hash_cap == 0);
 
     __shared__ long long s_b;
     __shared__ u64 s_pfkey;   // prefetch == 2: a survivor below this key is among the next step's likely expansions
@@ -260,8 +261,11 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     asm volatile("" : "+r"(lane), "+r"(wid));    // opaque: keep them in registers instead of re-reading %tid in the loops
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tab32 = smem_u32(s_lut);
-    const int D = RW8 >= 2 ? 1536 : a.D, M = a.M, L = RW8 == 3 ? 100 : a.L;
-    const uint32_t hcap = RW8 == 3 ? 4096u : a.hash_cap;
+    const int D = RW8 >= 2 ? 1536 : a.D, M = a.M, L = RW8 >= 3 ? 100 : a.L;
+    const uint32_t hcap = RW8 >= 3 ? 4096u : a.hash_cap;
+    const int pf = RW8 == 4 ? 5 : a.prefetch;
+    const uint8_t *deleted = RW8 == 4 ? nullptr : a.deleted;
+    const bool do_rerank = RW8 == 4 ? true : (a.rerank != 0);
     const int R = RW8 ? 32 : a.R, W = RW8 ? 8 : a.W;
     const int words = WORDS > 0 ? WORDS : (M >> 2);
     const uint32_t hmask = hcap ? hcap - 1u : 0u, ovf_mask = a.ovf_cap - 1u;
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 s_mvalid = 0;
                 if (use_ovf_now) s_ovfused = 1;
             }
-            const bool spec = (a.prefetch & 2) != 0;
+            const bool spec = (pf & 2) != 0;
             for (int s = wid; s < ns; s += nw) {
                 const int pos = (int)s_sel[W + s];
                 DR_PT(6);   // (timing build) selection read
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     asm volatile("" ::"r"(nb));
                     DR_PT(7);   // (timing build) adjacency row arrived
 #endif
-                    if (valid && a.deleted) valid = a.deleted[nb] == 0;
+                    if (valid && deleted) valid = deleted[nb] == 0;
                     bool isnew = false;   // equal ids in one row (0-padding): the CAS admits exactly one of them
                     if (valid) isnew = visited_insert_fast(nb, s_hash, hmask, hshift, use_ovf_now, my_ovf, ovf_mask, ovf_shift, no_smem_hash);
                     const unsigned m = __ballot_sync(DR_FULL, isnew);
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     }
                     if (isnew) {
                         s_newid[basepos + __popc(m & lt_mask)] = nb;
-                        if (a.prefetch & 4) {   // the code row is needed right after the barrier: start its trip now
+                        if (pf & 4) {   // the code row is needed right after the barrier: start its trip now
                             const uint8_t *cr = a.codes + (size_t)nb * M;
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(cr));
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(cr + (M > 128 ? 128 : M - 1)));
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                         basep = __shfl_sync(DR_FULL, basep, 0);
                         if (ok) {
                             s_newk[basep + __popc(okm & lt_mask)] = key;
-                            if ((a.prefetch & 1) || ((a.prefetch & 2) && key < pfkey))   // likely to be expanded next step
+                            if ((pf & 1) || ((pf & 2) && key < pfkey))   // likely to be expanded next step
                                 for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)myid * R + o));
                         }
                     }
@@ -617,7 +621,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             }
         }
         const int k = a.k;
-        if (a.rerank) {
+        if (do_rerank) {
             // Exact rerank of the whole list.  The table is dead now: its bytes stage full-precision rows, one slot per
             // warp, filled by bulk async copies (TMA engine, evict-first in L2) in two pieces so that the second half of a
             // row and the first half of the next one are in flight while the warp accumulates; no registers are tied up
@@ -737,7 +741,8 @@ static fast_kernel_t pick_fast_kernel_b(int M) {
     }
 }
 static fast_kernel_t pick_fast_kernel(int M, int minb, int rw8) {
-    if (rw8 == 3 && minb < 4) return pick_fast_kernel_b<3, 3>(M);
+    if (rw8 == 4 && minb < 4) return pick_fast_kernel_b<3, 4>(M);
+    if (rw8 >= 3 && minb < 4) return pick_fast_kernel_b<3, 3>(M);
     if (rw8 >= 2) return minb >= 4 ? pick_fast_kernel_b<4, 2>(M) : pick_fast_kernel_b<3, 2>(M);
     if (rw8) return minb >= 4 ? pick_fast_kernel_b<4, 1>(M) : pick_fast_kernel_b<3, 1>(M);
     return minb >= 4 ? pick_fast_kernel_b<4, 0>(M) : pick_fast_kernel_b<3, 0>(M);
@@ -816,6 +821,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     }
     a.hash_cap = hc;
     if (shape == 3 && hc != 4096) shape = 2;
+    if (shape == 3 && p->prefetch == 5 && !h->d_deleted && p->rerank) shape = 4;
     kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3, shape);
     const int smem = fixed + (int)hc * 4 + q_extra;
     const int nt = DR_FAST_NT;
