@@ -205,3 +205,25 @@ def test_edge_cases(case):
 
 def test_export_records_roundtrip(golden, gidx):
     assert np.array_equal(gidx.export_records(), golden["records"])
+
+
+def test_bench_shape_specialisation_vs_oracle(orc):
+    """The compile-time-specialised instantiation the bench runs (D = 1536, M = 192, R = 32, W = 8, L = 100, 4096-slot visited
+    table, prefetch mask 5, rerank): bit-for-bit against the restatement with the exact 8-bit table, and the same ids with
+    the tensor-core table on all but near-tie queries."""
+    from diskrag_b200.engine import GpuIndex
+    c = make_case(orc, 2500, 1536, 192, 32, 48, 31, nq=16)
+    L, W = 100, 8
+    with GpuIndex.from_arrays(c["X"], c["adj"], c["codes"], c["codebook"], c["medoid"]) as idx:
+        r = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=False, lut_fmt="u8", prefetch=5)
+        rl = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5)   # generic flags path
+        rt = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8tc", prefetch=5)
+    assert np.array_equal(r.ids, rl.ids) and np.array_equal(r.dists, rl.dists) and np.array_equal(r.hops, rl.hops)
+    for qi in range(c["Q"].shape[0]):
+        t8, sc, off = orc.lut_u8(c["codebook"], c["Q"][qi])
+        l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False)
+        assert (r.hops[qi], r.visited[qi]) == (l["hops"], l["visited"])
+        assert np.array_equal(l["ids"], rl.list_ids[qi, :rl.list_len[qi]])
+        oi, od = orc.rerank(c["X"], c["Q"][qi], l["ids"], 10, flavor=orc.FLAVOR_WARP)
+        assert np.array_equal(oi, r.ids[qi, :len(oi)]) and np.array_equal(od, r.dists[qi, :len(od)])
+    assert np.mean(np.all(rt.ids == r.ids, axis=1)) >= 0.8
