@@ -314,16 +314,24 @@ int dr_search_batch(dr_index *h, const float *Q, int64_t B, const dr_search_para
             DR_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
         }
     }
-    int64_t piece = B;
+    // piece sizes: a short ramp (2k, 4k, 8k queries) so that the first search starts after ~0.2 ms of copying instead of a
+    // full piece, then equal pieces of about 16k queries (at most DR_PIPE_EVENTS pieces in all)
+    int64_t sizes[DR_PIPE_EVENTS];
+    int npieces = 0;
     if (!lut && !trace && B >= 8192) {
-        int64_t np = (B + 16383) / 16384;
-        if (np > DR_PIPE_EVENTS) np = DR_PIPE_EVENTS;
-        piece = (B + np - 1) / np;
+        int64_t left = B;
+        for (int64_t r = 2048; r <= 8192 && left > 4 * r && npieces < 3; r *= 2) { sizes[npieces++] = r; left -= r; }
+        int64_t np = (left + 16383) / 16384;
+        if (np > DR_PIPE_EVENTS - npieces) np = DR_PIPE_EVENTS - npieces;
+        const int64_t each = (left + np - 1) / np;
+        while (left > 0) { const int64_t c = left < each ? left : each; sizes[npieces++] = c; left -= c; }
+    } else {
+        sizes[npieces++] = B;
     }
     if (trace) DR_CUDA(cudaMemsetAsync(dTrace, 0xFF, (size_t)B * trace_cap * 4, h->s_comp));
-    int pi = 0;
-    for (int64_t c0 = 0; c0 < B; c0 += piece, ++pi) {
-        const int64_t cb = (B - c0 < piece) ? (B - c0) : piece;
+    int64_t c0 = 0;
+    for (int pi = 0; pi < npieces; c0 += sizes[pi], ++pi) {
+        const int64_t cb = sizes[pi];
         DR_CUDA(cudaMemcpyAsync(dQ + (size_t)c0 * h->D, Q + (size_t)c0 * h->D, (size_t)cb * h->D * 4, cudaMemcpyHostToDevice, h->s_in));
         if (lut) DR_CUDA(cudaMemcpyAsync(dLut, lut, (size_t)B * h->M * 1024, cudaMemcpyHostToDevice, h->s_in));
         DR_CUDA(cudaEventRecord(h->ev_in[pi], h->s_in));
