@@ -35,7 +35,7 @@ namespace {
 struct LutTcArgs {
     const float *codebook; const float *Q; long long B; int D, M, ds;
     uint32_t *out32;      // [B][M/4][256] packed words (search_fast.cu's global layout)
-    const float *scale;   // phase 2: per-query scale written by lut_u8_finalize_kernel
+    float *scale, *offset; // phase 2 derives them from lo / range_bits (pq.cu:lut_u8_finalize_kernel's formulas) and stores them
     float *lo;            // [B][M] per-subspace minima (phase 1 writes, phase 2 reads)
     unsigned *range_bits; // [B] max range as float bits (phase 1, atomicMax)
     int words_per_cta;
@@ -115,8 +115,20 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
 
     float mul = -2.0f, inv = 1.0f, inv_hi = 1.0f, inv_lo = 0.0f;
     if (PHASE == 2) {
-        inv = __fdiv_rn(1.0f, a.scale[live ? b : b0]);
+        // scale[b] = max range / 255 (1 if 0): every CTA of the tile recomputes it from the statistics pass; the CTAs of the
+        // first word group also publish scale[b] and offset[b] = sum_m lo[b][m] + ||q_b||^2 (same operation order as
+        // lut_u8_finalize_kernel), so no separate finalize launch is needed
+        const float range = __uint_as_float(a.range_bits[live ? b : b0]);
+        const float scale = range > 0.0f ? __fdiv_rn(range, 255.0f) : 1.0f;
+        inv = __fdiv_rn(1.0f, scale);
         inv_hi = tf32_hi(inv); inv_lo = inv - inv_hi; mul = -2.0f * inv;
+        if (blockIdx.y == 0 && live) {
+            float acc = 0.0f, qn = 0.0f;
+            for (int m = 0; m < M; ++m) acc = __fadd_rn(acc, a.lo[(size_t)b * M + m]);
+            for (int j = 0; j < D; ++j) { const float v = qrow[j]; qn = __fmaf_rn(v, v, qn); }
+            a.scale[b] = scale;
+            a.offset[b] = __fadd_rn(acc, qn);
+        }
     }
     float rmax = 0.0f;
     for (int w = w_begin; w < w_end; ++w) {
@@ -202,8 +214,8 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
 }  // namespace
 
 // Same contract as launch_lut_build_u8(..., word_layout = 1): needs M % 4 == 0 and (D / M) % 8 == 0.
-// d_mn f32[B][M] and d_range u32[B] are scratch.  Three launches: statistics (tensor cores), finalize (pq.cu), quantise
-// (tensor cores); the two tensor-core launches are parallel over (128-query tile, group of code words).
+// d_mn f32[B][M] and d_range u32[B] are scratch.  Two launches, both on the tensor cores and parallel over (128-query tile,
+// group of code words): statistics, then quantise (which also publishes the per-query scale / offset).
 int launch_lut_u8_finalize(const float *d_lo, const unsigned *d_range, const float *d_Q, int64_t B, int D, int M, float *d_scale,
                            float *d_offset, cudaStream_t s);   // pq.cu
 
@@ -219,7 +231,7 @@ int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B,
     DR_CUDA(cudaFuncSetAttribute(lut_u8_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LutTcArgs a;
     a.codebook = d_codebook; a.Q = d_Q; a.B = B; a.D = D; a.M = M; a.ds = ds;
-    a.out32 = reinterpret_cast<uint32_t *>(d_out8); a.scale = d_scale; a.lo = d_mn; a.range_bits = d_range;
+    a.out32 = reinterpret_cast<uint32_t *>(d_out8); a.scale = d_scale; a.offset = d_offset; a.lo = d_mn; a.range_bits = d_range;
     const long long tiles = (B + TC_ROWS - 1) / TC_ROWS;
     // enough CTAs for >= 4 waves of the whole chip, a word group no smaller than 2 words (the A operand is staged per word)
     int groups = (int)((4LL * TC_CTAS * sms + tiles - 1) / tiles);
@@ -232,7 +244,6 @@ int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B,
     DR_CUDA(cudaMemsetAsync(d_range, 0, (size_t)B * 4, s));
     lut_u8_tc_kernel<1><<<grid, TC_ROWS, smem, s>>>(a);
     DR_LAUNCHED();
-    if (launch_lut_u8_finalize(d_mn, d_range, d_Q, B, D, M, d_scale, d_offset, s)) return 1;
     lut_u8_tc_kernel<2><<<grid, TC_ROWS, smem, s>>>(a);
     DR_LAUNCHED();
     return 0;
