@@ -13,7 +13,7 @@ import os as _os
 # DISKRAG_B200_LIB: load another build of the same library (A/B runs of kernel variants, scripts/build_variants.py)
 LIB_PATH = Path(_os.environ["DISKRAG_B200_LIB"]) if _os.environ.get("DISKRAG_B200_LIB") else _HERE / "libdiskrag_b200.so"
 
-DR_DIST_PQ, DR_DIST_EXACT = 0, 1
+DR_DIST_PQ, DR_DIST_EXACT, DR_DIST_COSINE = 0, 1, 2
 DR_ADC_SEQ, DR_ADC_TREE = 0, 1
 DR_LUT_F32, DR_LUT_U8, DR_LUT_U8_TC = 0, 1, 2
 DR_ST_VISITED_OVERFLOW, DR_ST_TIE_OVERFLOW = 1, 2

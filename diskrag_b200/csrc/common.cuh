@@ -147,6 +147,34 @@ __device__ __forceinline__ float warp_l2sq(const float *__restrict__ row, const 
     return warp_sum_butterfly(acc);
 }
 
+// Canonical cosine DISTANCE 1 - cos (cosine_similarity_cython, cython_utils.pyx:53-70; 0.0 when a norm is 0) of one row
+// against the query in shared memory, one warp per row: the three sums (x.q, x.x, q.q) use the lane / fmaf / butterfly
+// order of distance.cu:rowdist_kernel (op 2), the final division is done in double like the reference (np.sqrt of a
+// Python float).  Restated by oracle.c:orc_cosine_warp.
+__device__ __forceinline__ float warp_cosdist(const float *__restrict__ row, const float *__restrict__ q, int D, int lane) {
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+    if ((D & 3) == 0) {
+#pragma unroll 4
+        for (int base = lane * 4; base < D; base += 128) {
+            const float4 x = ldg_f4(row + base);
+            const float4 y = *reinterpret_cast<const float4 *>(q + base);
+            const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s0 = __fmaf_rn(xs[c], ys[c], s0); s1 = __fmaf_rn(xs[c], xs[c], s1); s2 = __fmaf_rn(ys[c], ys[c], s2);
+            }
+        }
+    } else {
+        for (int i = lane; i < D; i += 32) {
+            const float x = __ldg(row + i), y = q[i];
+            s0 = __fmaf_rn(x, y, s0); s1 = __fmaf_rn(x, x, s1); s2 = __fmaf_rn(y, y, s2);
+        }
+    }
+    s0 = warp_sum_butterfly(s0); s1 = warp_sum_butterfly(s1); s2 = warp_sum_butterfly(s2);
+    if (s1 == 0.0f || s2 == 0.0f) return 0.0f;
+    return (float)(1.0 - ((double)s0 / (sqrt((double)s1) * sqrt((double)s2))));
+}
+
 // two rows at once (twice the loads in flight per lane); each row keeps the canonical order of warp_l2sq
 __device__ __forceinline__ void warp_l2sq_x2(const float *__restrict__ rowA, const float *__restrict__ rowB,
                                              const float *__restrict__ q, int D, int lane, float &dA, float &dB) {

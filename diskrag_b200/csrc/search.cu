@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
     const int ovf_limit = (int)(a.ovf_cap - (a.ovf_cap >> 2));
     uint32_t *my_ovf = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
     const bool pq = (a.dist == DR_DIST_PQ);
+    const bool cosine = (a.dist == DR_DIST_COSINE);
     const bool strict = a.strict != 0;
     uint32_t lut_phase = 0;
     if (tid == 0) { mbar_init(&s_lutbar, 1); fence_mbar_init(); }
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
                 if (a.adc_tree) d0 = adc_tree_warp(a.codes + (size_t)a.start * M, s_lut, M, lane);
                 else d0 = adc_seq(a.codes + (size_t)a.start * M, s_lut, M);  // every lane computes the same value
             } else {
-                d0 = warp_l2sq(a.vec + (size_t)a.start * D, s_q, D, lane);
+                d0 = cosine ? warp_cosdist(a.vec + (size_t)a.start * D, s_q, D, lane) : warp_l2sq(a.vec + (size_t)a.start * D, s_q, D, lane);
             }
             if (lane == 0) {
                 s_list0[0] = make_key(d0, a.start);
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
                 for (int i = wid; i < nn; i += nw) {
                     uint32_t id = s_newid[i];
                     float d = pq ? adc_tree_warp(a.codes + (size_t)id * M, s_lut, M, lane)
-                                 : warp_l2sq(a.vec + (size_t)id * D, s_q, D, lane);
+                                 : (cosine ? warp_cosdist(a.vec + (size_t)id * D, s_q, D, lane) : warp_l2sq(a.vec + (size_t)id * D, s_q, D, lane));
                     if (lane == 0) {
                         u64 key = make_key(d, id);
                         bool ok = !full || (strict ? (key_dbits(key) < worst_db) : (key < worstk));
@@ -465,7 +466,8 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
     DR_CHECK(p->k >= 1 && p->L >= 1 && p->L <= 512 && p->k <= p->L, "dr_search: need 1 <= k <= L <= 512 (k=%d L=%d)", p->k, p->L);
     DR_CHECK(p->W >= 1 && p->W <= 32, "dr_search: W must be in 1..32 (got %d)", p->W);
     const bool pq = p->dist == DR_DIST_PQ;
-    DR_CHECK(p->dist == DR_DIST_PQ || p->dist == DR_DIST_EXACT, "dr_search: unknown dist %d", p->dist);
+    DR_CHECK(p->dist == DR_DIST_PQ || p->dist == DR_DIST_EXACT || p->dist == DR_DIST_COSINE, "dr_search: unknown dist %d", p->dist);
+    DR_CHECK(p->dist != DR_DIST_COSINE || !p->rerank, "dr_search: the rerank is a squared-L2 rerank; DR_DIST_COSINE returns the traversal's own order");
     if (pq) DR_CHECK(h->d_codes && h->M > 0, "dr_search: index has no PQ codes");
     DR_CHECK(h->medoid >= 0 && h->medoid < h->N, "dr_search: medoid out of range");
     if (B == 0) return 0;

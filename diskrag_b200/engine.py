@@ -24,7 +24,7 @@ class SearchResult:
 
 def make_params(k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_out=False, hash_cap=0, chunk=0,
                 threads=0, lut="f32", prefetch=False) -> SearchParams:
-    return SearchParams(k=k, L=L, W=W, dist=_lib.DR_DIST_PQ if dist == "pq" else _lib.DR_DIST_EXACT,
+    return SearchParams(k=k, L=L, W=W, dist={"pq": _lib.DR_DIST_PQ, "cosine": _lib.DR_DIST_COSINE}.get(dist, _lib.DR_DIST_EXACT),
                         adc_order=_lib.DR_ADC_TREE if adc_order == "tree" else _lib.DR_ADC_SEQ,
                         rerank=int(bool(rerank)), sqrt_out=int(bool(sqrt_out)), hash_cap=hash_cap, chunk=chunk,
                         threads=threads, lut_fmt={"u8": _lib.DR_LUT_U8, "u8tc": _lib.DR_LUT_U8_TC}.get(lut, _lib.DR_LUT_F32),

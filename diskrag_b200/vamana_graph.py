@@ -407,14 +407,16 @@ def _live_start(g, start_idx):
 def _graph_search(graph, start_idx, q, L):
     """greedy_search_cython semantics: <= L ids, ascending traversal distance."""
     g = _as_graph(graph)
-    if g.distance_metric != 'l2' and not _pq_on(g):
-        raise NotImplementedError("cosine traversal is not implemented on the GPU path; unit-normalise and use l2")
+    if g.distance_metric not in ('l2', 'cosine') and not _pq_on(g):
+        raise ValueError(f"unknown distance_metric {g.distance_metric!r}")
     start = _live_start(g, start_idx)
     if start is None:
         return []
     idx = g.gpu_index()
     check(lib().dr_index_set_start(idx._h, start))
-    r = idx.search(q[None, :], k=1, L=L, W=1, dist="pq" if _pq_on(g) else "exact", rerank=False, want_list=True)
+    # compute_query_distance (:301-329): ADC when PQ search is enabled, else 1 - cos for 'cosine', else squared L2
+    dist = "pq" if _pq_on(g) else ("cosine" if g.distance_metric == 'cosine' else "exact")
+    r = idx.search(q[None, :], k=1, L=L, W=1, dist=dist, rerank=False, want_list=True)
     n = int(r.list_len[0])
     return [int(x) for x in r.list_ids[0, :n]]
 

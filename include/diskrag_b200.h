@@ -33,6 +33,7 @@ typedef struct dr_index dr_index; /* opaque device-resident index (vectors, adja
 /* traversal distance */
 #define DR_DIST_PQ 0    /* ADC over PQ codes: vamana_graph.py:301-329 compute_query_distance + fast_pq.py:320-328 */
 #define DR_DIST_EXACT 1 /* fp32 squared L2 on the full vectors: vamana_graph.py:719-760, :607-640 */
+#define DR_DIST_COSINE 2 /* exact traversal with 1 - cos(x, q) (distance_metric='cosine', vamana_graph.py:301-329 -> cython_utils.pyx:53-70) */
 /* ADC summation order */
 #define DR_ADC_SEQ 0  /* m = 0..M-1 sequential fp32 adds: bit-identical to fast_pq.py:320-328 */
 #define DR_ADC_TREE 1 /* lane-strided partial sums + butterfly: throughput mode, not a reference order */

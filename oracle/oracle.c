@@ -123,6 +123,34 @@ float orc_l2sq_warp(const float *v, const float *q, int n) {
     return lane[0];
 }
 
+/* The GPU's canonical cosine distance (diskrag_b200/csrc/common.cuh:warp_cosdist, distance.cu:rowdist_kernel op 2):
+ * the three sums in the lane / fmaf / xor-butterfly order of orc_l2sq_warp, the final division in double as
+ * cosine_similarity_cython does (cython_utils.pyx:53-70); 0.0 when a norm is zero. */
+static float warp_sum3(const float *a, const float *b, int n, int which) {
+    float lane[32];
+    int vw = (n % 4 == 0) ? 4 : 1;
+    for (int l = 0; l < 32; ++l) {
+        float acc = 0.0f;
+        for (int base = l * vw; base < n; base += 32 * vw)
+            for (int c = 0; c < vw; ++c) {
+                float x = a[base + c], y = b[base + c];
+                acc = which == 0 ? fmaf(x, y, acc) : (which == 1 ? fmaf(x, x, acc) : fmaf(y, y, acc));
+            }
+        lane[l] = acc;
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        float t[32];
+        for (int l = 0; l < 32; ++l) t[l] = lane[l] + lane[l ^ off];
+        memcpy(lane, t, sizeof(t));
+    }
+    return lane[0];
+}
+float orc_cosine_warp(const float *v, const float *q, int n) {
+    float s0 = warp_sum3(v, q, n, 0), s1 = warp_sum3(v, q, n, 1), s2 = warp_sum3(v, q, n, 2);
+    if (s1 == 0.0f || s2 == 0.0f) return 0.0f;
+    return (float)(1.0 - ((double)s0 / (sqrt((double)s1) * sqrt((double)s2))));
+}
+
 /* flavor: 0 = double accumulation rounded once (stand-in for BLAS sdot inside np.linalg.norm,
  * vamana_graph.py:726,743), 1 = numpy pairwise, 2 = GPU warp order, 3 = sequential fp32. */
 static float l2sq_flavor(const float *v, const float *q, int n, int flavor) {
@@ -356,7 +384,8 @@ static void stable_sort_by_dist(ent_t *a, int n) { /* insertion sort: stable, n 
 /*   B: vamana_graph.py:607-640 greedy_search (exact np.linalg.norm)                            */
 /*   D: vamana_graph.py:719-760 beam_search_from_disk (exact, frontier truncated to beam_width) */
 /* dist_mode: 0 = ADC sequential (needs codes+lut), 1 = sqrt(exact L2^2 flavor) as B/D,         */
-/*            2 = exact L2^2 flavor (squared, as cython l2 callback), 3 = ADC tree (GPU fast).  */
+/*            2 = exact L2^2 flavor (squared, as cython l2 callback), 3 = ADC tree (GPU fast),  */
+/*            4 = u8 table, 5 = cosine distance 1 - cos (distance_metric='cosine').             */
 /* truncate_frontier: D's `if len(beam) > beam_width: beam = nsmallest(beam_width, beam)`.      */
 /* Outputs: out_ids/out_d = the whole result list in the reference's output order (<= L);       */
 /*          trace (optional) = ids in the order their distance was computed (visited order).    */
@@ -380,6 +409,9 @@ static inline float node_dist(const sctx_t *c, long id) {
         return (float)acc;
     }
     case 1: return sqrtf(l2sq_flavor(c->vec + (size_t)id * c->D, c->q, c->D, c->flavor));
+    case 5: /* distance_metric == 'cosine' (vamana_graph.py:325-326): flavor 2 = GPU warp order, else the reference's loop */
+        return c->flavor == 2 ? orc_cosine_warp(c->vec + (size_t)id * c->D, c->q, c->D)
+                              : (float)orc_cosine_dist(c->vec + (size_t)id * c->D, c->q, c->D);
     default: return l2sq_flavor(c->vec + (size_t)id * c->D, c->q, c->D, c->flavor);
     }
 }

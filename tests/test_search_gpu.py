@@ -227,3 +227,51 @@ def test_bench_shape_specialisation_vs_oracle(orc):
         oi, od = orc.rerank(c["X"], c["Q"][qi], l["ids"], 10, flavor=orc.FLAVOR_WARP)
         assert np.array_equal(oi, r.ids[qi, :len(oi)]) and np.array_equal(od, r.dists[qi, :len(od)])
     assert np.mean(np.all(rt.ids == r.ids, axis=1)) >= 0.8
+
+
+def test_cosine_traversal_vs_oracle_and_reference(case, orc):
+    """distance_metric='cosine' (compute_query_distance, vamana_graph.py:301-329 -> cosine_similarity_cython,
+    cython_utils.pyx:53-70: the distance is 1 - cos): the GPU traversal is bit-for-bit the restatement in the GPU's summation
+    order, and agrees with the REAL reference's greedy_search_cython on the same graph up to near-ties (the reference sums
+    sequentially in fp32 under -ffast-math, so only a tolerance comparison is meaningful: distances within 1e-5)."""
+    import sys
+    from pathlib import Path
+    c = case
+    L = 40
+    r = c["idx"].search(c["Q"], k=10, L=L, W=1, dist="cosine", rerank=False, want_list=True)
+    for qi in range(c["Q"].shape[0]):
+        h = orc.search_heap(c["adj"], c["medoid"], L, vec=c["X"], q=c["Q"][qi], dist_mode=orc.DIST_COSINE, flavor=orc.FLAVOR_WARP)
+        n = r.list_len[qi]
+        ei, ed = canon(h["ids"], h["dists"])
+        gi, gd = canon(r.list_ids[qi, :n], r.list_dists[qi, :n])
+        assert np.array_equal(ei, gi) and np.array_equal(ed, gd), qi
+        assert (r.hops[qi], r.visited[qi]) == (h["hops"], h["visited"])
+    with pytest.raises(ValueError):
+        c["idx"].search(c["Q"][:1], k=5, L=L, dist="cosine", rerank=True)        # the fused rerank is a squared-L2 rerank
+    # the shim: a graph object with distance_metric='cosine' searches through the same kernel
+    from diskrag_b200.vamana_graph import VamanaGraphWithPQ, greedy_search
+    g = VamanaGraphWithPQ.from_arrays(c["X"], c["adj"], medoid_idx=c["medoid"], distance_metric='cosine')
+    ids = greedy_search(g, c["medoid"], c["Q"][0], L)
+    assert ids == [int(x) for x in r.list_ids[0, :r.list_len[0]]]
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built")
+    ref = ref_loader.load()
+    vg, cu = ref["vamana_graph"], ref["cython_utils"]
+    rg = vg.VamanaGraphWithPQ(c["R"], None, distance_metric='cosine')
+    for i in range(c["N"]):
+        node = vg.Node(i, c["X"][i], None)
+        node.neighbors = [int(x) for x in c["adj"][i]]
+        rg.nodes[i] = node
+    rg.medoid_idx = c["medoid"]
+    same, overlap = 0, []
+    for qi in range(8):
+        rid = cu.greedy_search_cython(rg, c["medoid"], c["Q"][qi], L, vg.compute_query_distance)
+        mine = [int(x) for x in r.list_ids[qi, :r.list_len[qi]]]
+        same += (set(rid) == set(mine))            # order inside an exact tie group is heap-layout dependent in the reference
+        overlap.append(len(set(rid) & set(mine)) / max(1, len(rid)))
+        dref = np.array([orc.cosine_dist(c["X"][i], c["Q"][qi]) for i in rid], np.float64)
+        dgpu = np.sort(r.list_dists[qi, :r.list_len[qi]].astype(np.float64))
+        np.testing.assert_allclose(np.sort(dref), dgpu, atol=1e-5)
+    assert same >= 5 and np.mean(overlap) >= 0.95, (same, overlap)
