@@ -1,0 +1,30 @@
+"""BASELINE configs[1] input: a REFERENCE-EQUIVALENT Vamana graph over 100k x 1536 synthetic vectors, built on the CPU by
+oracle/oracle.c:orc_vamana_build — the restatement of build_vamana_index_cython (cython_utils.pyx:269-492) that
+tests/test_golden_oracle.py pins row for row against the real reference build.  Sequential by nature (~30 min on one
+core); the adjacency (N x R u32, 0-padded like DiskANNPersist.save_index) is cached under .cache/ and the vectors are
+regenerated from the seed wherever it is used (scripts/parity_config2.py).
+usage: python scripts/build_config2_graph.py [N]"""
+import sys, time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
+import numpy as np
+import oracle as O
+from diskrag_b200.synth import synth_numpy
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+D, R, L, ALPHA, SEED = 1536, 32, 64, 1.2, 20241
+O.build()
+X = synth_numpy(N, D, seed=SEED)
+rng = np.random.default_rng(SEED)
+s0 = rng.permutation(N).astype(np.int32); s1 = rng.permutation(N).astype(np.int32)
+med = O.medoid(X, rng.choice(N, 1000, replace=False).astype(np.int32))
+t = time.time()
+rows = O.vamana_build(X, R, L, ALPHA, med, s0, s1)
+adj = np.zeros((N, R), np.uint32)
+for i, row in enumerate(rows):
+    adj[i, :len(row)] = row[:R]
+out = ROOT / ".cache" / f"config2_adj_{N}.npz"
+np.savez_compressed(out, adj=adj, medoid=np.int64(med), N=N, D=D, R=R, L=L, alpha=ALPHA, seed=SEED,
+                    deg=np.array([len(r) for r in rows], np.int32), build_s=time.time() - t)
+print(out, "built in", round(time.time() - t, 1), "s; mean degree", float(np.mean([len(r) for r in rows])))

@@ -1,0 +1,122 @@
+"""BASELINE configs[1]: reference-equivalent graph (sequential 2-pass Vamana, scripts/build_config2_graph.py) over
+N x 1536 synthetic vectors, written in the pydiskann/io layout, loaded from the index directory, searched as ONE
+10k-query batch on the GPU and compared with the CPU oracle (the literal two-heap form of the reference's searches).
+Run on the GPU box; prints one JSON summary (kept in profiles/).
+
+  variant D  beam_search_from_disk (vamana_graph.py:719-760): exact traversal, L = beam_width = 100
+             ids + hops + visited bit-exact against the oracle in the GPU's summation order; against the oracle in the
+             reference-like (double-accumulated, BLAS stand-in) order: ids on all but near-tie queries, distances <= 1e-4 rel
+  variant A  greedy_search_cython + ADC callback (cython_utils.pyx:72-122): sequential-order ADC over the f32 table
+             ids, ADC distances (bit-equal), hops, visited
+  throughput u8 table, W = 8, fused rerank: ids / distances bit-equal to the list-form restatement
+"""
+import json
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
+
+
+def main():
+    import oracle as O
+    from diskrag_b200.engine import GpuIndex
+    from diskrag_b200.io.diskann_persist import DiskANNPersist
+    from diskrag_b200.pq.fast_pq import DiskANNPQ
+    from diskrag_b200.synth import synth_numpy
+    O.build()
+    nq_exact = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000
+    nq_oracle = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000          # queries the CPU oracle re-runs per variant
+    cached = sorted((ROOT / ".cache").glob("config2_adj_*.npz"), key=lambda p: int(p.stem.split("_")[-1]))
+    if cached:
+        z = np.load(cached[-1])
+        adj, med, N, D, R, seed = z["adj"], int(z["medoid"]), int(z["N"]), int(z["D"]), int(z["R"]), int(z["seed"])
+        X = synth_numpy(N, D, seed=seed)
+        built = f"oracle sequential build, {float(z['build_s']):.0f} s on one CPU core"
+    else:                                                                 # no cached graph on this box: a small one, same recipe
+        N, D, R, seed = 4000, 1536, 32, 20241
+        X = synth_numpy(N, D, seed=seed)
+        rng = np.random.default_rng(seed)
+        s0 = rng.permutation(N).astype(np.int32); s1 = rng.permutation(N).astype(np.int32)
+        med = O.medoid(X, rng.choice(N, 1000, replace=False).astype(np.int32))
+        rows = O.vamana_build(X, R, 64, 1.2, med, s0, s1)
+        adj = np.zeros((N, R), np.uint32)
+        for i, row in enumerate(rows):
+            adj[i, :len(row)] = row[:R]
+        built = "oracle sequential build (fallback size)"
+    Q = synth_numpy(nq_exact, D, seed=seed, sample_seed=1000)
+    M, L, k = 192, 100, 10
+    out = {"config": f"{N}x{D}, R={R}, reference-equivalent graph ({built}), PQ M={M}, {nq_exact}-query batch, L={L}, k={k}",
+           "oracle_queries_per_variant": nq_oracle}
+    with tempfile.TemporaryDirectory() as tmp:
+        d = Path(tmp)
+        pq = DiskANNPQ(M, 256); pq.fit(X)
+        codes = pq.encode(X)
+        persist = DiskANNPersist(dim=D, R=R)
+        persist.save_arrays(d / "index.dat", X, adj)                      # the byte layout of DiskANNPersist.save_index
+        persist.save_pq_codes(str(d / "pq_codes.bin"), codes)
+        persist.save_pq_codebook(str(d / "pq_model.pkl"), pq)
+        persist.save_meta(str(d / "meta.json"), {"D": D, "R": R, "L": 64, "alpha": 1.2, "N": N, "medoid_idx": med,
+                                                  "n_subvectors": M, "pq_centroids": 256, "use_pq": True})
+        assert (d / "index.dat").stat().st_size == N * 4 * (D + R)
+        idx = GpuIndex.from_dir(d)                                        # pydiskann/io layout -> device arrays
+    cb = np.stack([km.cluster_centers_ for km in pq.kmeans_list]).astype(np.float32)
+    with idx:
+        # ---- variant D ---------------------------------------------------------------------------------------
+        t = time.time()
+        rD = idx.search(Q, k=k, L=L, W=1, dist="exact", rerank=False, sqrt_out=True, want_list=True)
+        tD = time.time() - t
+        same_w = same_ids_d = 0; maxrel = 0.0; hv = 0
+        for qi in range(nq_oracle):
+            hw = O.search_heap(adj, med, L, vec=X, q=Q[qi], dist_mode=O.DIST_L2_SQ, flavor=O.FLAVOR_WARP, truncate_frontier=True)
+            n = rD.list_len[qi]
+            o = np.lexsort((hw["ids"], hw["dists"]))
+            ok = np.array_equal(hw["ids"][o], rD.list_ids[qi, :n]) and np.array_equal(hw["dists"][o], rD.list_dists[qi, :n])
+            same_w += ok
+            hv += (rD.hops[qi], rD.visited[qi]) == (hw["hops"], hw["visited"])
+            hd = O.search_heap(adj, med, L, vec=X, q=Q[qi], dist_mode=O.DIST_L2_SQRT, flavor=O.FLAVOR_DOUBLE, truncate_frontier=True)
+            od = np.lexsort((hd["ids"], hd["dists"]))
+            topd = hd["ids"][od][:k]
+            if set(topd.tolist()) == set(rD.ids[qi].tolist()):
+                same_ids_d += 1
+                rel = np.abs(np.sort(hd["dists"][od][:k]) - np.sort(rD.dists[qi])) / np.maximum(np.sort(hd["dists"][od][:k]), 1e-12)
+                maxrel = max(maxrel, float(rel.max()))
+        out["variant_D_exact"] = {"gpu_batch_seconds": round(tD, 3), "lists_bit_equal_to_oracle_gpu_order": f"{same_w}/{nq_oracle}",
+                                  "hops_and_visited_equal": f"{hv}/{nq_oracle}",
+                                  "top_k_id_sets_equal_to_reference_like_order": f"{same_ids_d}/{nq_oracle}",
+                                  "max_rel_distance_diff_on_those": maxrel}
+        # ---- variant A ---------------------------------------------------------------------------------------
+        t = time.time()
+        rA = idx.search(Q, k=k, L=L, W=1, dist="pq", adc_order="seq", rerank=False, want_list=True)
+        tA = time.time() - t
+        okA = 0
+        for qi in range(nq_oracle):
+            T = O.lut(cb, Q[qi])                                          # numpy-order table == the GPU's f32 table (tests)
+            h = O.search_heap(adj, med, L, codes=codes, lut_=T, dist_mode=O.DIST_ADC_SEQ)
+            n = rA.list_len[qi]
+            o = np.lexsort((h["ids"], h["dists"]))
+            okA += (np.array_equal(h["ids"][o], rA.list_ids[qi, :n]) and np.array_equal(h["dists"][o], rA.list_dists[qi, :n])
+                    and (rA.hops[qi], rA.visited[qi]) == (h["hops"], h["visited"]))
+        out["variant_A_pq"] = {"gpu_batch_seconds": round(tA, 3), "ids_adc_distances_hops_visited_bit_equal": f"{okA}/{nq_oracle}"}
+        # ---- throughput mode ---------------------------------------------------------------------------------
+        t = time.time()
+        rT = idx.search(Q, k=k, L=L, W=8, dist="pq", rerank=True, lut_fmt="u8", prefetch=5)
+        tT = time.time() - t
+        oi, od, oh, ov = O.search_batch(adj, X, Q[:nq_oracle], med, L, k, codes=codes, codebook=cb, dist_mode=O.DIST_ADC_U8,
+                                        flavor=O.FLAVOR_WARP, W=8, rerank_=True)
+        out["throughput_u8_W8_rerank"] = {
+            "gpu_batch_seconds": round(tT, 3),
+            "top_k_ids_and_distances_bit_equal": f"{int(np.sum(np.all(oi == rT.ids[:nq_oracle], axis=1) & np.all(od == rT.dists[:nq_oracle], axis=1)))}/{nq_oracle}",
+            "hops_visited_equal": f"{int(np.sum((oh == rT.hops[:nq_oracle]) & (ov == rT.visited[:nq_oracle])))}/{nq_oracle}"}
+        gt = O.ground_truth(X, Q[:500], k)
+        rec = lambda ids: float(np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / k for i in range(500)]))
+        out["recall_at_10"] = {"variant_D": rec(rD.ids), "variant_A_no_rerank": rec(rA.ids), "throughput": rec(rT.ids)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
