@@ -226,9 +226,11 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
                 if (found > W) found = W;
                 __syncwarp();
                 bool ghost_taken = false;
-                if (strict && s_ng > 0) {  // W == 1
+                const int ng_now = s_ng;   // every lane reads it before lane 0 may rewrite it
+                __syncwarp();
+                if (strict && ng_now > 0) {  // W == 1
                     if (lane == 0) {
-                        int ng = s_ng;
+                        int ng = ng_now;
                         if (key_dbits(s_ghost[0]) > key_dbits(lst[n - 1])) ng = 0;  // worst improved: ghosts are dead
                         if (ng > 0) {
                             int gb = 0;
@@ -391,6 +393,8 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
                     __syncthreads();
                     n = s_n;
                 }
+            } else {
+                __syncthreads();   // nothing survived: still separate this step's reads of the step counters from the next selection
             }
         }
 

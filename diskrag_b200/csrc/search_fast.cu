@@ -382,6 +382,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 const int pos = (int)s_sel[W + s];
                 DR_PT(6);   // (timing build) selection read
                 const uint32_t node = key_id(lst[pos]);
+                __syncwarp();
+                if (lane == 0) lst[pos] |= 1ull;          // mark it expanded: only this warp touches lst[pos] before the barrier
                 const uint32_t *row = a.adj + (size_t)node * R;
                 for (int j0 = 0; j0 < R; j0 += 32) {
                     const int j = j0 + lane;
@@ -414,7 +416,6 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             __syncthreads();
             DR_PT(2);   // select + adjacency + visited
             const bool use_ovf = use_ovf_now;
-            if (tid < ns) lst[s_sel[W + tid]] |= 1ull;        // mark the expanded entries (merge reads them after the next barrier)
             ubase += ns;
             if (tid == 0) s_nn2[(step + 1) & 1] = 0;          // next step's newcomer counter
             ++step;
