@@ -198,6 +198,8 @@ def run_ours(a):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if a.lut == "u8tc" and ((a.dim // a.M) % 8 != 0 or a.M % 4 != 0):
+        a.lut = "u8"                                   # the tcgen05 table needs a sub-dimension that is a multiple of 8
     X, adj, deg, codes, cb, med, info = build_index(a, dev)
     idx = engine.GpuIndex.from_device_ptrs(X.data_ptr(), adj.data_ptr(), codes.data_ptr(), cb.data_ptr(), a.n, a.dim, a.R, a.M,
                                            med, local, keepalive=(X, adj, codes, cb))

@@ -768,7 +768,20 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     int shape = (h->R == 32 && p->W == 8) ? (h->D == 1536 ? 2 : 1) : 0;
     if (shape == 2 && p->L == 100 && p->hash_cap == 0) shape = 3;   // confirmed below once the table size is known
     fast_kernel_t kern = nullptr;
-    int off = ((h->M * 256 + 15) / 16) * 16;
+    // Region 0 holds the ADC table during the traversal and the rerank's row staging slots afterwards.  A small table
+    // (M = 64: 16 KB) would leave room for only two 6 KB rows, i.e. two warps reranking: grow the region towards one slot per
+    // warp as long as three CTAs still fit on the SM.
+    const int slot_bytes = (h->D * 4 + 15) & ~15;
+    int region0 = ((h->M * 256 + 15) / 16) * 16;
+    if (p->rerank && (h->D & 3) == 0) {
+        const int rest = 6 * 1024 + 4096 * 4 + 2048;          // lists, newcomers, a 4096-slot visited table, static + reserve
+        for (int slots = DR_FAST_NT / 32; slots >= 1; --slots) {
+            const int want = slots * slot_bytes;
+            if (want <= region0) break;
+            if (want + rest <= h->smem_optin / 3) { region0 = want; break; }
+        }
+    }
+    int off = region0;
     const int LC = (p->L + 2) & ~1;
     a.o_list0 = off; off += LC * 8;
     a.o_list1 = off; off += LC * 8;
@@ -789,8 +802,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     uint32_t hc = 0;
     int min_hash = 1024;
     while (min_hash * 4 < p->L * 8) min_hash <<= 1;
-    const int slot_bytes = (h->D * 4 + 15) & ~15;
-    a.rr_slots = (h->M * 256) / slot_bytes;
+    a.rr_slots = region0 / slot_bytes;
     int q_extra = 0;
     if (l2_visited) {
         // rerank keys reuse the newcomer keys' bytes, the query vector takes the last staging slot of the table region
