@@ -3,7 +3,7 @@ oracle/oracle.c:orc_vamana_build — the restatement of build_vamana_index_cytho
 tests/test_golden_oracle.py pins row for row against the real reference build.  Sequential by nature (~30 min on one
 core); the adjacency (N x R u32, 0-padded like DiskANNPersist.save_index) is cached under .cache/ and the vectors are
 regenerated from the seed wherever it is used (scripts/parity_config2.py).
-usage: python scripts/build_config2_graph.py [N]"""
+usage: python scripts/build_config2_graph.py [N [D R L tag]]     (tag names the cache file: config2 | config4)"""
 import sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -14,6 +14,10 @@ from diskrag_b200.synth import synth_numpy
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 D, R, L, ALPHA, SEED = 1536, 32, 64, 1.2, 20241
+TAG = "config2"
+if len(sys.argv) > 5:
+    D, R, L, TAG = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
+    SEED = 20243
 O.build()
 X = synth_numpy(N, D, seed=SEED)
 rng = np.random.default_rng(SEED)
@@ -24,7 +28,7 @@ rows = O.vamana_build(X, R, L, ALPHA, med, s0, s1)
 adj = np.zeros((N, R), np.uint32)
 for i, row in enumerate(rows):
     adj[i, :len(row)] = row[:R]
-out = ROOT / ".cache" / f"config2_adj_{N}.npz"
+out = ROOT / ".cache" / f"{TAG}_adj_{N}.npz"
 np.savez_compressed(out, adj=adj, medoid=np.int64(med), N=N, D=D, R=R, L=L, alpha=ALPHA, seed=SEED,
                     deg=np.array([len(r) for r in rows], np.int32), build_s=time.time() - t)
 print(out, "built in", round(time.time() - t, 1), "s; mean degree", float(np.mean([len(r) for r in rows])))
