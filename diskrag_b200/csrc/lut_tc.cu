@@ -86,13 +86,13 @@ __device__ __forceinline__ void stage_B(const float *__restrict__ codebook, int 
 // PHASE 1: lo[b][m] = min_c t and range_bits[b] = max(range_bits[b], max_c t - lo)        (then lut_u8_finalize_kernel)
 // PHASE 2: out32[b][w][c] = the four subspaces' quantised entries, packed
 // Dynamic shared memory: A blocks 4 * (nks+1) * 4 KB, then B blocks 4 * (nks+1) * TC_NQ * 32 B.
-template <int PHASE>
+template <int PHASE, int DS>   // DS: compile-time sub-dimension (8 / 16 / 24), 0 = runtime
 __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTcArgs a) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int ds = a.ds, nks = ds >> 3, nks1 = nks + 1, words = a.M >> 2, D = a.D, M = a.M;
+    const int ds = DS ? DS : a.ds, nks = ds >> 3, nks1 = nks + 1, words = a.M >> 2, D = a.D, M = a.M;
     unsigned char *sA = tc_smem;
     unsigned char *sB = tc_smem + 4 * nks1 * (TC_ROWS * 32);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
@@ -227,8 +227,16 @@ int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B,
     const int ds = D / M, nks1 = ds / 8 + 1, words = M / 4;
     const int smem = 4 * nks1 * (TC_ROWS * 32) + 4 * nks1 * (TC_NQ * 32);
     DR_CHECK(smem <= 200 * 1024, "dr_lut_build(u8, tensor cores): sub-dimension %d too large", ds);   // fewer CTAs per SM when large
-    DR_CUDA(cudaFuncSetAttribute(lut_u8_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    DR_CUDA(cudaFuncSetAttribute(lut_u8_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    void (*k1)(const LutTcArgs) = lut_u8_tc_kernel<1, 0>;
+    void (*k2)(const LutTcArgs) = lut_u8_tc_kernel<2, 0>;
+    switch (ds) {
+        case 8: k1 = lut_u8_tc_kernel<1, 8>; k2 = lut_u8_tc_kernel<2, 8>; break;
+        case 16: k1 = lut_u8_tc_kernel<1, 16>; k2 = lut_u8_tc_kernel<2, 16>; break;
+        case 24: k1 = lut_u8_tc_kernel<1, 24>; k2 = lut_u8_tc_kernel<2, 24>; break;
+        default: break;
+    }
+    DR_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DR_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LutTcArgs a;
     a.codebook = d_codebook; a.Q = d_Q; a.B = B; a.D = D; a.M = M; a.ds = ds;
     a.out32 = reinterpret_cast<uint32_t *>(d_out8); a.scale = d_scale; a.offset = d_offset; a.lo = d_mn; a.range_bits = d_range;
@@ -242,9 +250,9 @@ int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B,
     DR_CHECK(tiles <= 2147483647LL, "dr_lut_build(u8, tensor cores): batch too large");
     dim3 grid((unsigned)tiles, (unsigned)groups);
     DR_CUDA(cudaMemsetAsync(d_range, 0, (size_t)B * 4, s));
-    lut_u8_tc_kernel<1><<<grid, TC_ROWS, smem, s>>>(a);
+    k1<<<grid, TC_ROWS, smem, s>>>(a);
     DR_LAUNCHED();
-    lut_u8_tc_kernel<2><<<grid, TC_ROWS, smem, s>>>(a);
+    k2<<<grid, TC_ROWS, smem, s>>>(a);
     DR_LAUNCHED();
     return 0;
 }
