@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
     const int ds = DS ? DS : a.ds, nks = ds >> 3, nks1 = nks + 1, words = a.M >> 2, D = a.D, M = a.M;
     unsigned char *sA = tc_smem;
     unsigned char *sB = tc_smem + 4 * nks1 * (TC_ROWS * 32);
+    uint32_t *sT = reinterpret_cast<uint32_t *>(sB + 4 * nks1 * (TC_NQ * 32));   // 4 warps x 32 rows x 20 words: store transposition
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
 
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
@@ -125,7 +126,14 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
         if (blockIdx.y == 0 && live) {
             float acc = 0.0f, qn = 0.0f;
             for (int m = 0; m < M; ++m) acc = __fadd_rn(acc, a.lo[(size_t)b * M + m]);
-            for (int j = 0; j < D; ++j) { const float v = qrow[j]; qn = __fmaf_rn(v, v, qn); }
+            if ((D & 3) == 0) {       // same element order as the scalar loop, 16-byte loads
+                for (int j = 0; j < D; j += 4) {
+                    const float4 v = ldg_f4(qrow + j);
+                    qn = __fmaf_rn(v.x, v.x, qn); qn = __fmaf_rn(v.y, v.y, qn); qn = __fmaf_rn(v.z, v.z, qn); qn = __fmaf_rn(v.w, v.w, qn);
+                }
+            } else {
+                for (int j = 0; j < D; ++j) { const float v = qrow[j]; qn = __fmaf_rn(v, v, qn); }
+            }
             a.scale[b] = scale;
             a.offset[b] = __fadd_rn(acc, qn);
         }
@@ -170,7 +178,6 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
                     }
                 }
             } else {
-                uint32_t *orow = a.out32 + ((size_t)(live ? b : b0) * words + w) * 256 + c0;
 #pragma unroll
                 for (int ch = 0; ch < TC_NQ / 16; ++ch) {
                     float v0[16], v1[16], v2[16], v3[16];
@@ -189,10 +196,22 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
                         asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q3) : "f"(v3[i]));
                         pk[i] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
                     }
-                    if (live) {
+                    // A lane holds 64 contiguous bytes of ITS row; written directly, one warp store would touch 32 rows x 16 B.
+                    // Transposed through a per-warp tile (row stride 80 B: conflict-free 16-byte stores), four lanes share a row
+                    // and one warp store covers 8 rows x 64 contiguous bytes (full 32-byte sectors).
+                    uint32_t *tile = sT + wid * (32 * 20);
+                    __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<uint4 *>(orow + ch * 16 + i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<uint4 *>(tile + lane * 20 + i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = i * 8 + (lane >> 2), c4 = (lane & 3) * 4;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(tile + r * 20 + c4);
+                        const long long br = b0 + wid * 32 + r;
+                        if (br < a.B)
+                            *reinterpret_cast<uint4 *>(a.out32 + ((size_t)br * words + w) * 256 + c0 + ch * 16 + c4) = v;
                     }
                 }
             }
@@ -225,7 +244,7 @@ int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B,
              "dr_lut_build(u8, tensor cores): needs M %% 4 == 0 and a sub-dimension that is a multiple of 8 (D=%d M=%d)", D, M);
     if (B == 0) return 0;
     const int ds = D / M, nks1 = ds / 8 + 1, words = M / 4;
-    const int smem = 4 * nks1 * (TC_ROWS * 32) + 4 * nks1 * (TC_NQ * 32);
+    const int smem = 4 * nks1 * (TC_ROWS * 32) + 4 * nks1 * (TC_NQ * 32) + 4 * 32 * 20 * 4;
     DR_CHECK(smem <= 200 * 1024, "dr_lut_build(u8, tensor cores): sub-dimension %d too large", ds);   // fewer CTAs per SM when large
     void (*k1)(const LutTcArgs) = lut_u8_tc_kernel<1, 0>;
     void (*k2)(const LutTcArgs) = lut_u8_tc_kernel<2, 0>;
