@@ -314,7 +314,7 @@ def run_ours(a):
                "config": {"workload": f"{a.n}x{a.dim} synthetic unit-norm, Vamana R={a.R} (GPU-built, Lbuild={a.Lbuild}, alpha=1.2), "
                                       f"PQ M={a.M}, L={a.L}, W={a.W}, adc={a.adc}, table={a.lut}, rerank, top-{a.k}",
                           "queries_per_gpu_per_step": B, "index": "replicated", "queries": "sharded", "recall_at_10": round(rec, 4),
-                          "recall_queries": ngt, "l2_flush": "inputs larger than L2 (index 6.3 GB, per-step LUT 19.7 GB)",
+                          "recall_queries": ngt, "l2_flush": f"inputs larger than L2 (index {(a.n * (a.dim * 4 + a.R * 4 + a.M)) / 1e9:.1f} GB, per-step ADC tables {B * a.M * (256 if a.lut != 'f32' else 1024) / 1e9:.1f} GB, queries {B * a.dim * 4 / 1e9:.2f} GB)",
                           "mean_hops": round(float(h_np.mean()), 1), "mean_visited": round(float(v_np.mean()), 1), "setup": info},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
         print(json.dumps(out))

@@ -862,7 +862,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     a.counter = h->d_counter;
 
     const size_t per_q = (size_t)h->M * 256;
-    int64_t cap = (int64_t)((size_t)4 << 30) / (int64_t)per_q;
+    int64_t cap = (int64_t)((size_t)8 << 30) / (int64_t)per_q;   // table scratch <= 8 GB per launch (160k queries at M = 192)
     if (p->chunk > 0) cap = p->chunk;
     if (cap < 1) cap = 1;
     const int64_t nchunks = (B + cap - 1) / cap;
