@@ -142,6 +142,22 @@ def test_beam_W_vs_oracle(case, orc, W, adc):
         assert np.array_equal(oi, r.ids[qi, :len(oi)]) and np.array_equal(od, r.dists[qi, :len(od)])
 
 
+@pytest.mark.parametrize("W,L", [(12, 48), (4, 300), (16, 20)])
+def test_u8_table_mode_wide_and_long_lists(case, orc, W, L):
+    """more expansions per step than warps (W = 12, 16), lists longer than 255 entries and shorter than W * R:
+    the rank bookkeeping of the merge (u16 ranks, selection of the next step) against the restatement"""
+    c = case
+    r = c["idx"].search(c["Q"][:12], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5)
+    for qi in range(12):
+        t8, sc, off = orc.lut_u8(c["codebook"], c["Q"][qi])
+        l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False)
+        n = r.list_len[qi]
+        assert np.array_equal(l["ids"], r.list_ids[qi, :n]), (qi, W, L)
+        assert (r.hops[qi], r.visited[qi]) == (l["hops"], l["visited"])
+        oi, od = orc.rerank(c["X"], c["Q"][qi], l["ids"], 10, flavor=orc.FLAVOR_WARP)
+        assert np.array_equal(oi, r.ids[qi, :len(oi)]) and np.array_equal(od, r.dists[qi, :len(od)])
+
+
 @pytest.mark.parametrize("W", [1, 4])
 def test_u8_table_mode_vs_oracle(case, orc, W):
     """Throughput mode with the 8-bit ADC table (3 CTAs per SM): bit-for-bit against its restatement."""
