@@ -304,6 +304,22 @@ def run_ours(a):
     e2e = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(B * a.dim * 4),
            "d2h_bytes_per_step": int(B * k * 8 + 3 * B * 4)}
 
+    # ---- the recall / throughput trade-off around the named configuration (context for "QPS at recall >= 0.95"; 1 GPU only)
+    points = None
+    if world == 1:
+        points = []
+        for Lp in (50, 64, 80):
+            pp = engine.make_params(k=k, L=Lp, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut,
+                                    hash_cap=a.hash_cap, prefetch=int(a.prefetch))
+            run = lambda: idx.search_dev(Q.data_ptr(), B, pp, ids.data_ptr(), dd.data_ptr(), hops.data_ptr(), vis.data_ptr(),
+                                         d_list_len=llen.data_ptr(), d_status=stat.data_ptr(), stream=stream)
+            run(); torch.cuda.synchronize(dev)
+            f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+            f0.record(); run(); run(); f1.record(); torch.cuda.synchronize(dev)
+            points.append({"L": Lp, "recall_at_10": round(recall(ids[:ngt].cpu().numpy(), gt, k), 4),
+                           "qps": round(2 * B / (f0.elapsed_time(f1) / 1e3), 1)})
+        step(); torch.cuda.synchronize(dev)            # leave the named configuration's results in the buffers
+
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu_base = cpu_baseline_port(a, X, adj, codes, cb, med, Q, idn)
@@ -315,7 +331,8 @@ def run_ours(a):
                                       f"PQ M={a.M}, L={a.L}, W={a.W}, adc={a.adc}, table={a.lut}, rerank, top-{a.k}",
                           "queries_per_gpu_per_step": B, "index": "replicated", "queries": "sharded", "recall_at_10": round(rec, 4),
                           "recall_queries": ngt, "l2_flush": f"inputs larger than L2 (index {(a.n * (a.dim * 4 + a.R * 4 + a.M)) / 1e9:.1f} GB, per-step ADC tables {B * a.M * (256 if a.lut != 'f32' else 1024) / 1e9:.1f} GB, queries {B * a.dim * 4 / 1e9:.2f} GB)",
-                          "mean_hops": round(float(h_np.mean()), 1), "mean_visited": round(float(v_np.mean()), 1), "setup": info},
+                          "mean_hops": round(float(h_np.mean()), 1), "mean_visited": round(float(v_np.mean()), 1), "setup": info,
+                          "other_operating_points": points},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
         print(json.dumps(out))
     if world > 1:
