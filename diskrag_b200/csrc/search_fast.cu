@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             const int mv = s_mvalid;
             // (4) merge (keys are unique, so ranks are exact):
             //     few survivors   : rank = count of smaller newcomers (no sort, no extra barrier)
-            //     up to 32 per warp: every warp bitonic-sorts one 32-key chunk in registers, then every item sums its
+            //     up to 64 per warp: every warp bitonic-sorts one 64-key chunk in registers, then every item sums its
             //                        binary-search ranks in the other sorted sequences
             //     more            : rank counting over all newcomers
             //     Every placed element also gets its unexpanded rank (unexpanded old entries before it, from ur_old, plus
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 }
             };
             if (mv > 0) {
-                if (mv <= DR_MERGE_LINEAR || mv > 32 * nw) {
+                if (mv <= DR_MERGE_LINEAR || mv > 64 * nw) {
                     for (int x = tid; x < total; x += nt) {
                         u64 key;
                         int pos, from;
@@ -545,23 +545,31 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                         place(key, pos, from, x >= n);
                     }
                 } else {
-                    const int nch = (mv + 31) >> 5;
+                    // every warp bitonic-sorts one 64-key chunk in registers (two keys per lane: element e = lane + 32 r),
+                    // then every item sums its binary-search ranks in the other sorted sequences
+                    const int nch = (mv + 63) >> 6;
                     if (wid < nch) {
-                        const int idx = (wid << 5) + lane;
-                        u64 key = idx < mv ? s_newk[idx] : DR_KEY_MAX;
+                        const int i0 = (wid << 6) + lane, i1 = i0 + 32;
+                        u64 k0 = i0 < mv ? s_newk[i0] : DR_KEY_MAX, k1 = i1 < mv ? s_newk[i1] : DR_KEY_MAX;
 #pragma unroll
-                        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+                        for (int k2 = 2; k2 <= 64; k2 <<= 1) {
 #pragma unroll
                             for (int j = k2 >> 1; j > 0; j >>= 1) {
-                                const u64 other = __shfl_xor_sync(DR_FULL, key, j);
-                                const bool up = ((lane & k2) == 0);            // ascending block
-                                const bool lower = ((lane & j) == 0);          // this lane keeps the smaller of the pair
-                                const bool take_min = (up == lower);
-                                const u64 mn = key < other ? key : other, mx = key < other ? other : key;
-                                key = take_min ? mn : mx;
+                                if (j == 32) {                                   // partners sit in the same lane; k2 == 64: ascending
+                                    const u64 mn = k0 < k1 ? k0 : k1, mx = k0 < k1 ? k1 : k0;
+                                    k0 = mn; k1 = mx;
+                                } else {
+                                    const u64 o0 = __shfl_xor_sync(DR_FULL, k0, j), o1 = __shfl_xor_sync(DR_FULL, k1, j);
+                                    const bool lower = ((lane & j) == 0);          // this element is the smaller index of its pair
+                                    const bool up0 = k2 == 64 ? true : ((lane & k2) == 0);                       // e = lane
+                                    const bool up1 = k2 == 64 ? true : (k2 == 32 ? false : ((lane & k2) == 0));    // e = lane + 32
+                                    k0 = (up0 == lower) ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
+                                    k1 = (up1 == lower) ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
+                                }
                             }
                         }
-                        if (idx < mv) s_newk[idx] = key;
+                        if (i0 < mv) s_newk[i0] = k0;
+                        if (i1 < mv) s_newk[i1] = k1;
                     }
                     __syncthreads();
                     for (int x = tid; x < total; x += nt) {
@@ -571,14 +579,14 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                         else {
                             const int j = x - n;
                             key = s_newk[j];
-                            own = j >> 5;
+                            own = j >> 6;
                             from = lower_bound_u64(lst, n, key);
-                            pos = (j & 31) + from;
+                            pos = (j & 63) + from;
                         }
                         for (int c = 0; c < nch; ++c) {
                             if (c == own) continue;
-                            const int sz = (mv - (c << 5)) < 32 ? (mv - (c << 5)) : 32;
-                            pos += lower_bound_u64(s_newk + (c << 5), sz, key);
+                            const int sz = (mv - (c << 6)) < 64 ? (mv - (c << 6)) : 64;
+                            pos += lower_bound_u64(s_newk + (c << 6), sz, key);
                         }
                         place(key, pos, from, x >= n);
                     }
