@@ -186,11 +186,15 @@ global_table:
     }
 }
 
+#ifndef DR_RR_UNROLL
+#define DR_RR_UNROLL 2
+#endif
 // One piece [e0, e1) of the canonical warp L2^2 (common.cuh:warp_l2sq: lane l owns elements base = 4 l + 128 j, fmaf in
 // increasing j), the row read from shared memory where a bulk copy staged it.  e0 is a multiple of 128.
 __device__ __forceinline__ float l2sq_piece_smem(const float *__restrict__ row, const float *__restrict__ q, int e0, int e1,
                                                  int lane, float acc) {
-#pragma unroll 2
+    constexpr int kUnroll = DR_RR_UNROLL;
+#pragma unroll kUnroll
     for (int base = e0 + lane * 4; base < e1; base += 128) {
         const float4 x = *reinterpret_cast<const float4 *>(row + base);
         const float4 y = *reinterpret_cast<const float4 *>(q + base);
@@ -428,10 +432,20 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 // item i of this warp = newcomer wid + nw * i; lane l owns item l of the current block of 32 items, rows go
                 // through the table four (or two) at a time, and the warp appends its survivors once per block
                 constexpr int KW = (WORDS > 0 ? WORDS : 0);
+#ifdef DR_P2_CONTIG
+                for (int base = 0; base < nn; base += 32 * nw) {     // warp w takes a contiguous run of the block's items
+                    const int cnt_blk = (nn - base) < 32 * nw ? (nn - base) : 32 * nw;
+                    const int per = (cnt_blk + nw - 1) / nw;
+                    int cntw = cnt_blk - wid * per;
+                    cntw = cntw < per ? cntw : per;
+                    if (cntw <= 0) continue;
+                    const uint32_t myid = lane < cntw ? s_newid[base + wid * per + lane] : 0u;
+#else
                 for (int first = wid; first < nn; first += 32 * nw) {
                     int cntw = (nn - first + nw - 1) / nw;
                     cntw = cntw < 32 ? cntw : 32;
                     const uint32_t myid = lane < cntw ? s_newid[first + lane * nw] : 0u;
+#endif
                     uint32_t mysum = 0u;
                     const int rounds = (cntw + 3) >> 2;
                     RowWords<4> wa, wb;   // two groups of code words: one being summed, one in flight
