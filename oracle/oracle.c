@@ -5,9 +5,9 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * Nothing under diskrag_b200/ links, imports or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py runs every function below against the
- * real reference compiled into oracle/_ref (oracle/build_ref.py) and against the committed golden
- * vectors in tests/golden/ that were produced by that real reference (tests/golden/make_golden.py).
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py runs the functions below against the
+ * real reference compiled into oracle/_ref (oracle/build_ref.py), live; tests/test_golden_oracle.py runs them against the
+ * committed golden vectors in tests/golden/ that were produced by that real reference (tests/golden/make_golden.py).
  *
  * Every function cites the reference file:line (relative to /root/reference) that it restates.
  * Where the reference's arithmetic order is knowable (heapq, sequential fp32 ADC sum, numpy

@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY — the checker, never the product.  Only tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline / --impl reference legs may import this module; nothing under
 diskrag_b200/ does.  Parity status: pinned against the real reference (oracle/_ref) and the golden
-vectors under tests/golden/ by tests/test_oracle_vs_reference.py and tests/test_golden.py.
+vectors under tests/golden/ by tests/test_oracle_vs_reference.py (live) and tests/test_golden_oracle.py (committed vectors).
 """
 import ctypes as C
 import subprocess

@@ -1,0 +1,84 @@
+"""The oracle against the REAL reference, live (oracle/_ref = pydiskann compiled from /root/reference by oracle/build_ref.py).
+Complements tests/test_golden_oracle.py (committed vectors from the same reference): fresh seeds, other shapes.  CPU only;
+skipped where oracle/_ref has not been built."""
+import random
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+import ref_loader  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+@pytest.fixture(scope="module")
+def world(orc, ref):
+    """600 x 24 points, a reference-built graph (seeded), a random-sample codebook wrapped the way pq_model.pkl holds it"""
+    from diskrag_b200.pq.fast_pq import _wrap_kmeans
+    rng = np.random.default_rng(17)
+    N, D, M, R, L = 600, 24, 6, 8, 16
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    X[N - 20:] = X[:20]                                            # exact ties
+    Q = rng.standard_normal((12, D)).astype(np.float32)
+    cu, vg, fp = ref["cython_utils"], ref["vamana_graph"], ref["fast_pq"]
+    random.seed(11)
+    st = random.getstate()
+    adj_ref = cu.build_vamana_index_cython(X, R, L, 1.2, 3, False)
+    random.setstate(st)
+    s0 = list(range(N)); random.shuffle(s0)
+    s1 = list(range(N)); random.shuffle(s1)
+    cb = np.stack([X[rng.choice(N, 256, replace=False), m * 4:(m + 1) * 4] for m in range(M)]).astype(np.float32)
+    pq = fp.DiskANNPQ(M, 256)
+    pq.sub_dim = D // M; pq.is_fitted = True
+    pq.kmeans_list = [_wrap_kmeans(cb[m], 42 + m) for m in range(M)]
+    codes = pq.encode(X)
+    return dict(X=X, Q=Q, N=N, D=D, M=M, R=R, L=L, adj_ref=adj_ref, s0=np.array(s0, np.int32), s1=np.array(s1, np.int32),
+                cb=cb, pq=pq, codes=codes)
+
+
+def test_sequential_build_rows_equal(world, orc):
+    """build_vamana_index_cython (cython_utils.pyx:269-492) vs orc_vamana_build with the same two permutations"""
+    w = world
+    rows = orc.vamana_build(w["X"], w["R"], w["L"], 1.2, 3, w["s0"], w["s1"])
+    same = sum(list(a) == list(b) for a, b in zip(rows, w["adj_ref"]))
+    assert same >= 0.99 * w["N"], same                               # -ffast-math may move a near-tie
+
+
+def test_lut_encode_and_distances(world, orc, ref):
+    w = world
+    for q in w["Q"][:4]:
+        assert np.array_equal(w["pq"].compute_distance_table(q), orc.lut(w["cb"], q))          # fast_pq.py:294-318
+    assert np.mean(orc.pq_encode(w["cb"], w["X"]) == w["codes"]) >= 0.9995                     # fast_pq.py:245-267
+    cu = ref["cython_utils"]
+    for i in range(8):
+        np.testing.assert_allclose(cu.l2_distance_fast_cython(w["X"][i], w["X"][i + 1]), orc.l2sq(w["X"][i], w["X"][i + 1]), rtol=1e-5)
+        np.testing.assert_allclose(cu.cosine_similarity_cython(w["X"][i], w["X"][i + 1]), orc.cosine_dist(w["X"][i], w["X"][i + 1]),
+                                   rtol=1e-5, atol=1e-6)
+
+
+def test_variant_A_pq_search_equal(world, orc, ref):
+    """greedy_search_cython + compute_query_distance with PQ enabled (cython_utils.pyx:72-122, vamana_graph.py:301-329)"""
+    w = world
+    vg, cu = ref["vamana_graph"], ref["cython_utils"]
+    adj = np.zeros((w["N"], w["R"]), np.uint32)
+    g = vg.VamanaGraphWithPQ(w["R"], w["pq"])
+    for i, row in enumerate(w["adj_ref"]):
+        adj[i, :len(row)] = row[:w["R"]]
+        node = vg.Node(i, w["X"][i], w["codes"][i])
+        node.neighbors = [int(x) for x in adj[i]]                   # what index.dat holds: 0-padded rows, stored order
+        g.nodes[i] = node
+    g.medoid_idx = 3
+    g.use_pq_for_search = True
+    for q in w["Q"]:
+        g._distance_table_cache.clear()
+        rid = cu.greedy_search_cython(g, 3, q, 20, vg.compute_query_distance)
+        h = orc.search_heap(adj, 3, 20, codes=w["codes"], lut_=orc.lut(w["cb"], q), dist_mode=orc.DIST_ADC_SEQ)
+        assert list(rid) == [int(x) for x in h["ids"]]                 # same ids in the reference's own output order
