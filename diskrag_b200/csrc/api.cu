@@ -245,6 +245,7 @@ int dr_index_info(const dr_index *h, int64_t *N, int32_t *D, int32_t *R, int32_t
 
 int dr_index_export_records(const dr_index *h, void *records) {
     DR_CHECK(h && records, "dr_index_export_records: null argument");
+    DR_LOCK(const_cast<dr_index *>(h));
     DR_CUDA(cudaSetDevice(h->device));
     const size_t bytes = (size_t)h->N * 4 * (h->D + h->R);
     DevBuf rec;
@@ -256,6 +257,7 @@ int dr_index_export_records(const dr_index *h, void *records) {
 
 int dr_search_kernel_timing(dr_index *h, int enable, double *out_ms, int64_t *out_launches) {
     DR_CHECK(h, "dr_search_kernel_timing: null handle");
+    DR_LOCK(h);
     if (out_ms) *out_ms = h->timed_ms;
     if (out_launches) *out_launches = h->timed_launches;
     h->timing = enable != 0;
@@ -269,6 +271,7 @@ int dr_search_batch_dev(dr_index *h, const float *d_Q, int64_t B, const dr_searc
                         int32_t *d_out_list_ids, float *d_out_list_dist, int32_t *d_out_list_len, int32_t *d_trace,
                         int32_t trace_cap, int32_t *d_out_status, void *stream) {
     DR_CHECK(h && p && d_out_ids && (d_Q || B == 0), "dr_search_batch_dev: null argument");
+    DR_LOCK(h);
     DR_CUDA(cudaSetDevice(h->device));
     return launch_search(h, d_Q, B, p, d_lut, d_out_ids, d_out_dist, d_out_hops, d_out_visited, d_out_list_ids,
                          d_out_list_dist, d_out_list_len, d_trace, trace_cap, d_out_status, (cudaStream_t)stream);
@@ -279,6 +282,7 @@ int dr_search_batch(dr_index *h, const float *Q, int64_t B, const dr_search_para
                     int32_t *out_list_len, int32_t *trace, int32_t trace_cap, int32_t *out_status) {
     DR_CHECK(h && p && out_ids && (Q || B == 0), "dr_search_batch: null argument");
     DR_CHECK(p->k >= 1 && p->L >= 1 && p->L <= 512, "dr_search_batch: bad k/L");
+    DR_LOCK(h);
     DR_CUDA(cudaSetDevice(h->device));
     if (B == 0) return 0;
     // carve one staging allocation: Q | lut? | ids | dist | hops | visited | status | list_ids | list_dist | list_len | trace
@@ -361,12 +365,14 @@ int dr_search_batch(dr_index *h, const float *Q, int64_t B, const dr_search_para
 
 int dr_lut_build_dev(dr_index *h, const float *d_Q, int64_t B, float *d_out, void *stream) {
     DR_CHECK(h && h->d_codebook && h->M > 0, "dr_lut_build: index has no codebook");
+    DR_LOCK(h);
     DR_CUDA(cudaSetDevice(h->device));
     return launch_lut_build(h->d_codebook, d_Q, B, h->D, h->M, d_out, (cudaStream_t)stream);
 }
 
 int dr_lut_build(dr_index *h, const float *Q, int64_t B, float *out) {
     DR_CHECK(h && h->d_codebook && h->M > 0, "dr_lut_build: index has no codebook");
+    DR_LOCK(h);
     DR_CUDA(cudaSetDevice(h->device));
     DevBuf q, o;
     if (q.alloc((size_t)B * h->D * 4) || o.alloc((size_t)B * h->M * 1024)) return 1;
@@ -575,6 +581,7 @@ int dr_robust_prune(const float *p, const float *cand, int32_t n, int32_t D, flo
 
 int dr_index_set_deleted(dr_index *h, const uint8_t *mask) {
     DR_CHECK(h, "dr_index_set_deleted: null handle");
+    DR_LOCK(h);
     DR_CUDA(cudaSetDevice(h->device));
     if (!mask) { if (h->d_deleted) cudaFree(h->d_deleted); h->d_deleted = nullptr; return 0; }
     if (!h->d_deleted) DR_CUDA(cudaMalloc(&h->d_deleted, (size_t)h->N));
@@ -584,6 +591,7 @@ int dr_index_set_deleted(dr_index *h, const uint8_t *mask) {
 
 int dr_index_set_start(dr_index *h, int64_t start) {
     DR_CHECK(h && start >= 0 && start < h->N, "dr_index_set_start: out of range");
+    DR_LOCK(h);
     h->medoid = start;
     return 0;
 }

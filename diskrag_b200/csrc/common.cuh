@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/diskrag_b200.h"
@@ -67,7 +68,11 @@ struct dr_index {
     // host-pointer API pipeline (copy-in / compute / copy-out streams)
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[DR_PIPE_EVENTS] = {}, ev_done[DR_PIPE_EVENTS] = {};
+    // The scratch buffers above belong to the handle, so entry points that touch them hold this lock for the duration of the
+    // call: concurrent callers (FastAPI worker threads, ctypes releases the GIL) are serialised per handle instead of racing.
+    std::mutex mu;
 };
+#define DR_LOCK(h) std::lock_guard<std::mutex> dr_lock_guard_((h)->mu)
 
 int dr_scratch(void **ptr, size_t *cur, size_t need);  // grow-only device scratch
 

@@ -189,6 +189,15 @@ global_table:
 #ifndef DR_RR_UNROLL
 #define DR_RR_UNROLL 2
 #endif
+// Rerank rows beyond the staging slots: 0 = fetched only when a slot frees up (48 KB in flight per CTA); 1 = all of them are
+// started on their trip to L2 (cp.async.bulk.prefetch.L2, one instruction per 6 KB row) as soon as the traversal ends, so only
+// the first round of staged copies waits for DRAM; N >= 2 = a rolling window of N rounds ahead of the staged copies
+#ifndef DR_RR_PF
+#define DR_RR_PF 0
+#endif
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // One piece [e0, e1) of the canonical warp L2^2 (common.cuh:warp_l2sq: lane l owns elements base = 4 l + 128 j, fmaf in
 // increasing j), the row read from shared memory where a bulk copy staged it.  e0 is a multiple of 128.
 __device__ __forceinline__ float l2sq_piece_smem(const float *__restrict__ row, const float *__restrict__ q, int e0, int e1,
@@ -230,6 +239,9 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #ifndef DR_MERGE_LINEAR
 #define DR_MERGE_LINEAR 32
 #endif  // up to this many survivors: rank by counting, no sort
+#ifndef DR_L2V
+#define DR_L2V 0   // experiment (scripts/build_variants.py): 1 = the serving-shape specialisations keep the visited set in the
+#endif             // CTA's L2-resident table (no shared-memory hash) so that four CTAs fit on an SM; pair with DR_FAST_NT=192
 
 // WORDS > 0: compile-time M / 4;  WORDS == 0: runtime M (M % 4 == 0, M <= 256);  WORDS < 0: byte path (any M)
 // MINB = CTAs per SM the register budget is cut for (3: 80 registers; 4: 64 registers, used when the visited set moves out
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);
     uint32_t *s_hash = reinterpret_cast<uint32_t *>(dr_smem + a.o_hash);
     u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_rrk);    // rerank keys alias a region that is dead after the traversal
-    const bool no_smem_hash = RW8 >= 3 ? false : (a.hash_cap == 0);
+    const bool no_smem_hash = RW8 >= 3 ? (DR_L2V != 0) : (a.hash_cap == 0);
 
     __shared__ long long s_b;
     __shared__ u64 s_pfkey;   // prefetch == 2: a survivor below this key is among the next step's likely expansions
@@ -266,7 +278,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tab32 = smem_u32(s_lut);
     const int D = RW8 >= 2 ? 1536 : a.D, M = a.M, L = RW8 >= 3 ? 100 : a.L;
-    const uint32_t hcap = RW8 >= 3 ? 4096u : a.hash_cap;
+    const uint32_t hcap = RW8 >= 3 ? (DR_L2V ? 0u : 4096u) : a.hash_cap;
     const int pf = RW8 == 4 ? 5 : a.prefetch;
     const uint8_t *deleted = RW8 == 4 ? nullptr : a.deleted;
     const bool do_rerank = RW8 == 4 ? true : (a.rerank != 0);
@@ -663,6 +675,12 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 if (by0) { mbar_expect_tx(bar0, by0); bulk_g2s_hint(buf, row, by0, bar0, pol_stream); }
                 mbar_expect_tx(bar1, by1); bulk_g2s_hint(buf + e0, row + e0, by1, bar1, pol_stream);
             }
+#if DR_RR_PF
+            if (staged) {
+                const int pf_end = DR_RR_PF == 1 ? n : (n < (1 + DR_RR_PF) * nsl ? n : (1 + DR_RR_PF) * nsl);
+                for (int i = nsl + tid; i < pf_end; i += nt) bulk_prefetch_l2(a.vec + (size_t)key_id(lst[i]) * D, (uint32_t)D * 4u);
+            }
+#endif
             {   // the query vector goes where the (dead) visited table was
                 const float *qg = a.Q + (size_t)b * D;
                 for (int i = tid; i < D; i += nt) s_q[i] = __ldg(qg + i);
@@ -680,6 +698,10 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     for (int i = wid; i < n; i += nsl) {
                         const int inext = i + nsl;
                         const float *rown = inext < n ? a.vec + (size_t)key_id(lst[inext]) * D : nullptr;
+#if DR_RR_PF >= 2
+                        if (lane == 0 && i + (1 + DR_RR_PF) * nsl < n)
+                            bulk_prefetch_l2(a.vec + (size_t)key_id(lst[i + (1 + DR_RR_PF) * nsl]) * D, (uint32_t)D * 4u);
+#endif
                         float acc = 0.0f;
                         if (by0) {
                             mbar_wait(bar0, rr_ph0); rr_ph0 ^= 1u;
@@ -764,8 +786,13 @@ static fast_kernel_t pick_fast_kernel_b(int M) {
     }
 }
 static fast_kernel_t pick_fast_kernel(int M, int minb, int rw8) {
+#if DR_L2V
+    if (rw8 == 4 && minb >= 4) return pick_fast_kernel_b<4, 4>(M);
+    if (rw8 >= 3 && minb >= 4) return pick_fast_kernel_b<4, 3>(M);
+#else
     if (rw8 == 4 && minb < 4) return pick_fast_kernel_b<3, 4>(M);
     if (rw8 >= 3 && minb < 4) return pick_fast_kernel_b<3, 3>(M);
+#endif
     if (rw8 >= 2) return minb >= 4 ? pick_fast_kernel_b<4, 2>(M) : pick_fast_kernel_b<3, 2>(M);
     if (rw8) return minb >= 4 ? pick_fast_kernel_b<4, 1>(M) : pick_fast_kernel_b<3, 1>(M);
     return minb >= 4 ? pick_fast_kernel_b<4, 0>(M) : pick_fast_kernel_b<3, 0>(M);
@@ -786,7 +813,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
              "dr_search: DR_LUT_U8_TC needs M %% 4 == 0, M <= 256 and (D / M) %% 8 == 0 (D=%d M=%d)", h->D, h->M);
     // hash_cap < 0: the visited set lives entirely in the CTA's global table (L2-resident, 32 KB per CTA): no shared-memory
     // hash, so a fourth CTA fits on the SM next to three 48 KB tables (the kernel is bound by resident queries)
-    const bool l2_visited = p->hash_cap < 0;
+    const bool l2_visited = p->hash_cap < 0 || (DR_L2V && p->hash_cap == 0);
     int shape = (h->R == 32 && p->W == 8) ? (h->D == 1536 ? 2 : 1) : 0;
     if (shape == 2 && p->L == 100 && p->hash_cap == 0) shape = 3;   // confirmed below once the table size is known
     fast_kernel_t kern = nullptr;
@@ -855,7 +882,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
         DR_CHECK(fixed + q_extra + 512 <= h->smem_optin, "dr_search(u8): %d B of shared memory needed", fixed + q_extra);
     }
     a.hash_cap = hc;
-    if (shape == 3 && hc != 4096) shape = 2;
+    if (shape == 3 && hc != (DR_L2V ? 0u : 4096u)) shape = 2;
     if (shape == 3 && p->prefetch == 5 && !h->d_deleted && p->rerank) shape = 4;
     kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3, shape);
     const int smem = fixed + (int)hc * 4 + q_extra;

@@ -8,7 +8,7 @@ rep = root / "gpurun_out" / f"{tag}_search.ncu-rep"
 out = root / "profiles"
 det = subprocess.run(["ncu", "-i", str(rep), "--page", "details"], capture_output=True, text=True).stdout
 (out / f"{tag}_search_kernel_ncu.txt").write_text(det)
-lines = subprocess.run([sys.executable, str(root / "scripts" / "ncu_lines.py"), str(rep), kname, cufile, "40"], capture_output=True, text=True, cwd=root).stdout
+lines = subprocess.run([sys.executable, str(root / "scripts" / "ncu_lines.py"), str(rep), "40", str(nq)], capture_output=True, text=True, cwd=root).stdout
 (out / f"{tag}_search_kernel_lines.txt").write_text(lines)
 shutil.copy(root / "gpurun_out" / f"{tag}_launches.csv", out / f"{tag}_step_launches.csv")
 raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
