@@ -334,7 +334,7 @@ def run_ours(a):
                           "mean_hops": round(float(h_np.mean()), 1), "mean_visited": round(float(v_np.mean()), 1), "setup": info,
                           "other_operating_points": points},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -453,11 +453,20 @@ def run_reference(a):
                       "note": "index built by the GPU builder outside the timed region (the reference's builder needs hours at 1M)"},
            "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else a library prints there (NCCL's version banner at
+    communicator creation, for one) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 if __name__ == "__main__":
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
