@@ -165,6 +165,12 @@ class _MicroBatcher:
     def stop(self):
         self.alive = False
         self.t.join(timeout=1.0)
+        while True:      # nobody will answer what is still queued: fail those waiters instead of leaving them blocked
+            try:
+                _, f = self.q.get_nowait()
+            except queue.Empty:
+                break
+            f.set_exception(RuntimeError("search engine closed"))
 
 
 SearchEngine = GpuSearchEngine

@@ -291,3 +291,33 @@ def test_cosine_traversal_vs_oracle_and_reference(case, orc):
         dgpu = np.sort(r.list_dists[qi, :r.list_len[qi]].astype(np.float64))
         np.testing.assert_allclose(np.sort(dref), dgpu, atol=1e-5)
     assert same >= 5 and np.mean(overlap) >= 0.95, (same, overlap)
+
+
+def test_concurrent_callers_on_one_handle(golden, gidx):
+    """ctypes releases the GIL, so FastAPI worker threads can enter dr_search_batch on the same handle at the same time; the
+    handle's scratch (tables, staging, counters) is shared, so the library serialises them (per-handle mutex): every thread
+    must get exactly the single-threaded answer, in every mode."""
+    import threading
+    Q = golden["Q"]
+    modes = [dict(W=1, dist="pq", adc_order="seq", rerank=False), dict(W=4, dist="pq", rerank=True, lut_fmt="u8"),
+             dict(W=1, dist="exact", rerank=False), dict(W=2, dist="pq", adc_order="tree", rerank=True)]
+    want = [gidx.search(Q, k=10, L=40, **m) for m in modes]
+    errs = []
+
+    def worker(t):
+        try:
+            for it in range(6):
+                j = (t + it) % len(modes)
+                r = gidx.search(Q, k=10, L=40, **modes[j])
+                if not (np.array_equal(r.ids, want[j].ids) and np.array_equal(r.dists, want[j].dists)
+                        and np.array_equal(r.hops, want[j].hops)):
+                    errs.append((t, it, j))
+        except Exception as e:          # noqa: BLE001
+            errs.append((t, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs[:4]
