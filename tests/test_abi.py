@@ -63,3 +63,15 @@ def test_product_never_imports_oracle():
         txt = p.read_text()
         assert "liboracle" not in txt and "dlopen" not in txt, p
         assert not [l for l in txt.splitlines() if l.strip().startswith("#include") and "oracle" in l], p
+
+
+def test_only_the_checkers_touch_the_oracle():
+    """oracle/ is test infrastructure: only tests/ (tests/tools/ included), __graft_entry__.py and bench.py's CPU-baseline /
+    reference legs may import it; the tooling under scripts/ may compile it (building is not using) but never imports it."""
+    for p in (ROOT / "scripts").glob("*.py"):
+        txt = p.read_text()
+        assert "import oracle" not in txt and "ref_loader" not in txt and '"oracle"' not in txt, p
+    bench = (ROOT / "bench.py").read_text()
+    uses = [i for i, l in enumerate(bench.splitlines()) if "import oracle" in l or "import ref_loader" in l]
+    legs = [i for i, l in enumerate(bench.splitlines()) if l.startswith("def cpu_baseline_port") or l.startswith("def run_reference")]
+    assert uses and legs and min(uses) > min(legs), "bench.py imports the oracle outside its cpu_baseline / reference legs"

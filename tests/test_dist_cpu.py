@@ -1,6 +1,6 @@
 """Host-side logic of the multi-GPU partitionings with world_size 2 over gloo on the CPU: slicing, the
 all-to-all layout of the partial top-k lists, id offsets and the gather.  The per-shard searches are stood
-in by the oracle's exact brute force (the real ones run on GPUs; scripts/test_multi_gpu.py covers NCCL)."""
+in by the oracle's exact brute force (the real ones run on GPUs; tests/tools/multi_gpu_check.py covers NCCL)."""
 import os
 import sys
 from pathlib import Path

@@ -2,11 +2,11 @@
 oracle/oracle.c:orc_vamana_build — the restatement of build_vamana_index_cython (cython_utils.pyx:269-492) that
 tests/test_golden_oracle.py pins row for row against the real reference build.  Sequential by nature (~30 min on one
 core); the adjacency (N x R u32, 0-padded like DiskANNPersist.save_index) is cached under .cache/ and the vectors are
-regenerated from the seed wherever it is used (scripts/parity_config2.py).
-usage: python scripts/build_config2_graph.py [N [D R L tag]]     (tag names the cache file: config2 | config4)"""
+regenerated from the seed wherever it is used (tests/tools/parity_config2.py).
+usage: python tests/tools/build_config2_graph.py [N [D R L tag]]     (tag names the cache file: config2 | config4)"""
 import sys, time
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
 import numpy as np
 import oracle as O

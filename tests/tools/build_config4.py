@@ -4,7 +4,7 @@ vectors; graph quality judged by recall@10 against a reference-built graph, as n
 The reference's builder is strictly sequential (cython_utils.pyx:269-369: ~hours at 1M), so the comparison graph is a
 reference-EQUIVALENT one (oracle/oracle.c:orc_vamana_build, pinned row for row to the real builder in
 tests/test_golden_oracle.py) over a 50k subsample, built once on the CPU by
-    python scripts/build_config2_graph.py 50000 768 64 100 config4
+    python tests/tools/build_config2_graph.py 50000 768 64 100 config4
 and cached under .cache/.  On the GPU box this script
   (i)  builds the SAME 50k subset with dr_vamana_build (same R, L, alpha), searches both graphs with the same exact search
        (L = 100, k = 10, same queries) and reports both recalls;
@@ -17,7 +17,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
 
 

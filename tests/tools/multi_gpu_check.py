@@ -1,4 +1,4 @@
-"""NCCL check of both partitionings on real GPUs:  torchrun --nproc-per-node G scripts/test_multi_gpu.py
+"""NCCL check of both partitionings on real GPUs:  torchrun --nproc-per-node G tests/tools/multi_gpu_check.py
 index-sharded: every rank builds its own Vamana shard on its GPU, searches all queries, all-to-all + k-way merge kernel."""
 import os, sys, time
 sys.path.insert(0, "."); sys.path.insert(0, "oracle")

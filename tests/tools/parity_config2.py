@@ -1,4 +1,4 @@
-"""BASELINE configs[1]: reference-equivalent graph (sequential 2-pass Vamana, scripts/build_config2_graph.py) over
+"""BASELINE configs[1]: reference-equivalent graph (sequential 2-pass Vamana, tests/tools/build_config2_graph.py) over
 N x 1536 synthetic vectors, written in the pydiskann/io layout, loaded from the index directory, searched as ONE
 10k-query batch on the GPU and compared with the CPU oracle (the literal two-heap form of the reference's searches).
 Run on the GPU box; prints one JSON summary (kept in profiles/).
@@ -18,7 +18,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
 
 
