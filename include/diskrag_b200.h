@@ -16,6 +16,10 @@
  *     numpy-owned buffers, nothing retained after return).  "_dev" functions take device pointers
  *     on the index's device and a cudaStream_t (as void*), and only enqueue work.
  *   - arrays are C-contiguous, row-major.  ids are int32 (N < 2^31).
+ *   - threading: the entry points that use a handle's scratch (search, table build, delete mask, export) hold a
+ *     per-handle mutex for the duration of the call, so concurrent callers on one handle are serialised rather than
+ *     racing; different handles are independent.  Work enqueued by the "_dev" entries of one handle must stay on one
+ *     stream at a time (the next call reuses the handle's table scratch).
  */
 #ifndef DISKRAG_B200_H
 #define DISKRAG_B200_H
