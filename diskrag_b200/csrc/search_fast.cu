@@ -216,14 +216,28 @@ __device__ __forceinline__ float l2sq_piece_smem(const float *__restrict__ row, 
     return acc;
 }
 
-// number of keys of the sorted sequence a[0..n) that are smaller than key
+// number of keys of the sorted sequence a[0..n) that are smaller than key (n < 2 * TOP)
+#ifndef DR_BSEARCH_BF
+#define DR_BSEARCH_BF 1   // 1: fixed-trip power-of-two descent (no data-dependent loop, no divergence between lanes): +1.5 % QPS; 0: classic loop
+#endif
+template <int TOP>
 __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
+#if DR_BSEARCH_BF
+    int pos = 0;
+#pragma unroll
+    for (int step = TOP; step >= 1; step >>= 1) {
+        const int p = pos + step;
+        if (p <= n && a[p - 1] < key) pos = p;
+    }
+    return pos;
+#else
     int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (a[mid] < key) lo = mid + 1; else hi = mid;
     }
     return lo;
+#endif
 }
 
 // optional per-phase cycle accounting (build with -DDR_PHASE_TIMING; thread 0 of every CTA, summed into counter[1..8])
@@ -565,7 +579,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                         u64 key;
                         int pos, from;
                         if (x < n) { key = lst[x]; from = x; }
-                        else { key = s_newk[x - n]; from = lower_bound_u64(lst, n, key); }
+                        else { key = s_newk[x - n]; from = lower_bound_u64<(RW8 >= 3 ? 64 : 512)>(lst, n, key); }
                         pos = from;
                         for (int j = 0; j < mv; ++j) pos += (s_newk[j] < key) ? 1 : 0;
                         place(key, pos, from, x >= n);
@@ -606,13 +620,13 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                             const int j = x - n;
                             key = s_newk[j];
                             own = j >> 6;
-                            from = lower_bound_u64(lst, n, key);
+                            from = lower_bound_u64<(RW8 >= 3 ? 64 : 512)>(lst, n, key);
                             pos = (j & 63) + from;
                         }
                         for (int c = 0; c < nch; ++c) {
                             if (c == own) continue;
                             const int sz = (mv - (c << 6)) < 64 ? (mv - (c << 6)) : 64;
-                            pos += lower_bound_u64(s_newk + (c << 6), sz, key);
+                            pos += lower_bound_u64<64>(s_newk + (c << 6), sz, key);
                         }
                         place(key, pos, from, x >= n);
                     }
