@@ -253,21 +253,6 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #ifndef DR_MERGE_LINEAR
 #define DR_MERGE_LINEAR 32
 #endif  // up to this many survivors: rank by counting, no sort
-// Experiment, default off (measured: G = 4 is 15 % SLOWER, the per-warp imbalance costs more than the barrier): DR_P1_OWN = G (1..8): the warp that expands a node keeps the first G of the
-// neighbours it claimed and runs them through the table itself, BEFORE the block barrier: their code-row loads are issued the moment
-// the claim is known (no L2-prefetch-then-reload), the waits of the eight warps are no longer aligned, and a step whose expansions
-// all had <= G newcomers needs one barrier less (the queue of leftovers is empty).  Same survivors, order-independent merge: results
-// are unchanged by construction.
-#ifndef DR_P1_OWN
-#define DR_P1_OWN 0
-#endif
-#if DR_P1_OWN
-#define DR_NN_ALL nn_all      // every newcomer of the step (nn = the leftovers queued for the shared pass)
-#define DR_MVALID (*p_mv)     // survivor counter of the step (double-buffered: survivors are appended before the barrier too)
-#else
-#define DR_NN_ALL nn
-#define DR_MVALID s_mvalid
-#endif
 #ifndef DR_L2V
 #define DR_L2V 0   // experiment (scripts/build_variants.py): 1 = the serving-shape specialisations keep the visited set in the
 #endif             // CTA's L2-resident table (no shared-memory hash) so that four CTAs fit on an SM; pair with DR_FAST_NT=192
@@ -299,11 +284,6 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     __shared__ __align__(8) uint64_t s_lutbar;
     __shared__ __align__(8) uint64_t s_rrbar[16];   // rerank staging: two half-row barriers per warp
     __shared__ int s_nn2[2], s_ns, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
-#if DR_P1_OWN
-    __shared__ int s_nq2[2], s_mv2[2];                 // leftovers queued for the shared pass / survivors, per step parity
-    __shared__ uint32_t s_own[DR_FAST_NT / 32][8];      // the expanding warp's own newcomers
-    constexpr int KWO = (WORDS > 0 ? WORDS : 0);
-#endif
 
     const int tid = threadIdx.x;
     constexpr int nt = DR_FAST_NT, nw = DR_FAST_NT / 32;   // the launcher always uses DR_FAST_NT threads
@@ -344,11 +324,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
         if (b >= a.B) break;
 
         // ---- stage the query's table (permuting load: global [w][c][4] -> bank-per-lane layout), the query, the hash
-        if (tid == 0) { s_hcount = 1; s_ovfcount = no_smem_hash ? 1 : 0; s_ovfused = no_smem_hash ? 1 : 0; s_status = 0; s_nn2[0] = 0;
-#if DR_P1_OWN
-            s_nq2[0] = 0; s_mv2[0] = 0;
-#endif
-        }
+        if (tid == 0) { s_hcount = 1; s_ovfcount = no_smem_hash ? 1 : 0; s_ovfused = no_smem_hash ? 1 : 0; s_status = 0; s_nn2[0] = 0; }
         if (WP) {
             const int nfull = words >> 5, rem = words & 31;
             const uint4 *src = reinterpret_cast<const uint4 *>(a.lut8 + (size_t)b * M * 256);
@@ -432,12 +408,6 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 if (use_ovf_now) s_ovfused = 1;
             }
             const bool spec = (pf & 2) != 0;
-#if DR_P1_OWN
-            int *p_nq = &s_nq2[step & 1], *p_mv = &s_mv2[step & 1];
-            const bool full0 = (n >= L);
-            const u64 worst0 = lst[n - 1] & ~1ull;     // bit 0 (expanded) may be set concurrently by the entry's owner: masked
-            const u64 pfkey0 = s_pfkey;
-#endif
             for (int s = wid; s < ns; s += nw) {
                 const int pos = (int)s_sel[W + s];
                 DR_PT(6);   // (timing build) selection read
@@ -459,64 +429,6 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     const unsigned m = __ballot_sync(DR_FULL, isnew);
                     const int cnt = __popc(m);
                     int basepos = 0;
-#if DR_P1_OWN
-                    const int own = WP ? (cnt < DR_P1_OWN ? cnt : DR_P1_OWN) : 0;   // warp-uniform
-                    const int myrank = __popc(m & lt_mask);
-                    if (cnt) {
-                        if (lane == 0) {
-                            atomicAdd(p_nn, cnt);                                   // all newcomers (visited / hash accounting)
-                            if (cnt > own) basepos = atomicAdd(p_nq, cnt - own);    // leftovers go to the shared queue
-                        }
-                        basepos = __shfl_sync(DR_FULL, basepos, 0);
-                    }
-                    if (isnew && myrank >= own) {
-                        s_newid[basepos + myrank - own] = nb;
-                        if (pf & 4) {
-                            const uint8_t *cr = a.codes + (size_t)nb * M;
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(cr));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(cr + (M > 128 ? 128 : M - 1)));
-                        }
-                    }
-                    if (own) {
-                        if (isnew && myrank < own) s_own[wid][myrank] = nb;
-                        __syncwarp();
-                        uint32_t gid[8];
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) gid[g] = s_own[wid][g < own ? g : 0];   // short groups repeat a valid row
-                        __syncwarp();
-                        RowWords<4> wa, wb;
-                        {
-                            const uint32_t g4[4] = {gid[0], gid[1], gid[2], gid[3]};
-                            rows_load<KWO, 4>(a.codes, M, g4, lane, wa);
-                        }
-                        if (own > 4) {
-                            const uint32_t g4[4] = {gid[4], gid[5], gid[6], gid[7]};
-                            rows_load<KWO, 4>(a.codes, M, g4, lane, wb);
-                        }
-                        uint32_t gs[4], gs2[4] = {0u, 0u, 0u, 0u};
-                        rows_sum<KWO, 4>(M, tab32, wa, own > 2 ? 2 : 1, lane, gs);
-                        if (own > 4) rows_sum<KWO, 4>(M, tab32, wb, own > 6 ? 2 : 1, lane, gs2);
-                        uint32_t mysum = 0u, myid = 0u;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (lane == g) { mysum = gs[g]; myid = gid[g]; }
-                            if (lane == 4 + g) { mysum = gs2[g]; myid = gid[4 + g]; }
-                        }
-                        const u64 key = make_ikey(mysum, myid);
-                        const bool ok = lane < own && (!full0 || key < worst0);
-                        const unsigned okm = __ballot_sync(DR_FULL, ok);
-                        if (okm) {
-                            int basep = 0;
-                            if (lane == 0) basep = atomicAdd(p_mv, __popc(okm));
-                            basep = __shfl_sync(DR_FULL, basep, 0);
-                            if (ok) {
-                                s_newk[basep + __popc(okm & lt_mask)] = key;
-                                if ((pf & 1) || ((pf & 2) && key < pfkey0))
-                                    for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)myid * R + o));
-                            }
-                        }
-                    }
-#else
                     if (cnt) {
                         if (lane == 0) basepos = atomicAdd(p_nn, cnt);
                         basepos = __shfl_sync(DR_FULL, basepos, 0);
@@ -529,7 +441,6 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(cr + (M > 128 ? 128 : M - 1)));
                         }
                     }
-#endif
                 }
             }
             __syncthreads();
@@ -537,16 +448,9 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             const bool use_ovf = use_ovf_now;
             ubase += ns;
             if (tid == 0) s_nn2[(step + 1) & 1] = 0;          // next step's newcomer counter
-#if DR_P1_OWN
-            if (tid == 0) { s_nq2[(step + 1) & 1] = 0; s_mv2[(step + 1) & 1] = 0; }
-            const int nn_all = *p_nn;                           // every newcomer of the step
-            ++step;
-            const int nn = *p_nq;                               // what is left for the shared pass
-#else
             ++step;
             // (3) quantised ADC of the newcomers; the survivors are appended compactly
             const int nn = *p_nn;
-#endif
             const bool full = (n >= L);
             const u64 worstk = lst[n - 1] & ~1ull;
             const u64 pfkey = s_pfkey;
@@ -612,7 +516,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     const unsigned okm = __ballot_sync(DR_FULL, ok);
                     if (okm) {
                         int basep = 0;
-                        if (lane == 0) basep = atomicAdd(&DR_MVALID, __popc(okm));
+                        if (lane == 0) basep = atomicAdd(&s_mvalid, __popc(okm));
                         basep = __shfl_sync(DR_FULL, basep, 0);
                         if (ok) {
                             s_newk[basep + __popc(okm & lt_mask)] = key;
@@ -627,22 +531,18 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     const uint32_t sum = adc_u8_warp(a.codes + (size_t)id * M, s_lut, M, lane);
                     if (lane == 0) {
                         const u64 key = make_ikey(sum, id);
-                        if (!full || key < worstk) s_newk[atomicAdd(&DR_MVALID, 1)] = key;
+                        if (!full || key < worstk) s_newk[atomicAdd(&s_mvalid, 1)] = key;
                     }
                 }
             }
             if (tid == 0) {
-                if (use_ovf) s_ovfcount += DR_NN_ALL; else s_hcount += DR_NN_ALL;
+                if (use_ovf) s_ovfcount += nn; else s_hcount += nn;
             }
-#if DR_P1_OWN
-            if (nn) __syncthreads();    // nothing was queued: every survivor was appended before the previous barrier
-#else
             __syncthreads();
-#endif
             DR_PT(3);   // ADC
-            nvis += DR_NN_ALL;
+            nvis += nn;
             hops += ns;
-            const int mv = DR_MVALID;
+            const int mv = s_mvalid;
             // (4) merge (keys are unique, so ranks are exact):
             //     few survivors   : rank = count of smaller newcomers (no sort, no extra barrier)
             //     up to 64 per warp: every warp bitonic-sorts one 64-key chunk in registers, then every item sums its
