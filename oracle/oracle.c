@@ -6,7 +6,7 @@
  * Nothing under diskrag_b200/ links, imports or calls it.
  *
  * Parity status: PINNED.  tests/test_oracle_vs_reference.py runs the functions below against the
- * real reference compiled into oracle/_ref (oracle/build_ref.py), live; tests/test_golden_oracle.py runs them against the
+ * real reference compiled into oracle/_ref (oracle/build_ref.py), live; tests/test_golden_oracle.py and tests/test_golden_config0.py run them against the
  * committed golden vectors in tests/golden/ that were produced by that real reference (tests/golden/make_golden.py).
  *
  * Every function cites the reference file:line (relative to /root/reference) that it restates.

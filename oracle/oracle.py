@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY — the checker, never the product.  Only tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline / --impl reference legs may import this module; nothing under
 diskrag_b200/ does.  Parity status: pinned against the real reference (oracle/_ref) and the golden
-vectors under tests/golden/ by tests/test_oracle_vs_reference.py (live) and tests/test_golden_oracle.py (committed vectors).
+vectors under tests/golden/ by tests/test_oracle_vs_reference.py (live) and tests/test_golden_oracle.py and tests/test_golden_config0.py (committed vectors; the latter at BASELINE configs[0] scale).
 """
 import ctypes as C
 import subprocess
