@@ -304,21 +304,20 @@ int launch_prune_one(const float *d_X, int n, int D, float alpha, int R, uint32_
     DR_CHECK(n >= 0 && n <= PR_CMAX, "dr_robust_prune: at most %d candidates (got %d)", PR_CMAX, n);
     DR_CHECK(R >= 1 && R <= 128, "dr_robust_prune: R must be in 1..128");
     // a 1-node "graph": node id n, whose current row lists the candidates 0..n-1
-    static int32_t *d_zero = nullptr;
     PruneArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.X = d_X; pa.D = D; pa.adj = d_row - (size_t)n * (n > R ? n : R); pa.deg = d_deg - n;  // row/deg of node n land on d_row/d_deg
     pa.R = R; pa.stride = (n > R ? n : R); pa.alpha = alpha; pa.mode = 0;
-    if (!d_zero) { DR_CUDA(cudaMalloc(&d_zero, 8)); DR_CUDA(cudaMemset(d_zero, 0, 8)); }
-    int32_t *d_node = nullptr;
-    DR_CUDA(cudaMalloc(&d_node, 4));
-    DR_CUDA(cudaMemcpyAsync(d_node, &n, 4, cudaMemcpyHostToDevice, s));
-    pa.nodes = d_node; pa.list_ids = d_zero; pa.list_dist = (const float *)d_zero; pa.list_len = d_zero; pa.L = 1; pa.n_items = 1;
+    // scratch of this call, on the current device: [0..1] = an empty search list (ids / length 0), [2] = the node id n
+    struct Scratch { int32_t *p = nullptr; ~Scratch() { if (p) cudaFree(p); } } sc;
+    DR_CUDA(cudaMalloc(&sc.p, 16));
+    const int32_t init[4] = {0, 0, n, 0};
+    DR_CUDA(cudaMemcpyAsync(sc.p, init, 16, cudaMemcpyHostToDevice, s));
+    pa.nodes = sc.p + 2; pa.list_ids = sc.p; pa.list_dist = (const float *)sc.p; pa.list_len = sc.p; pa.L = 1; pa.n_items = 1;
     const size_t smem = (size_t)2 * D * 4;
     DR_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prune_kernel<<<1, PR_THREADS, smem, s>>>(pa);
     DR_LAUNCHED();
     DR_CUDA(cudaStreamSynchronize(s));
-    cudaFree(d_node);
     return 0;
 }
