@@ -17,7 +17,6 @@ import mmap
 import os
 import pickle
 from collections import OrderedDict
-from pathlib import Path
 
 import numpy as np
 

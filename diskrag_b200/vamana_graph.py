@@ -22,11 +22,8 @@ by popping the *best* entries (:592-593), which yields recall 0.036 on its own b
 §3.3).  That is a defect, not a contract; here beam_search[_with_pq] returns the k best of a correct search
 with list size max(k, beam_width), as (sqrt(d), id) tuples like the reference.
 """
-from typing import List, Optional, Tuple
-
 import numpy as np
 
-from . import cython_utils as _cu
 from . import ops
 from ._lib import as_f32, check, lib, ptr
 from .cython_utils import (build_vamana_index_cython, compute_approximate_medoid_cython, cosine_similarity_cython,  # noqa: F401
