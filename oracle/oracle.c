@@ -652,6 +652,28 @@ static int pfi_cmp(const void *a, const void *b) {
     if (x.d > y.d) return 1;
     return (x.id > y.id) - (x.id < y.id);
 }
+/* The distance loops INSIDE the C++ builder (cython_utils.pyx:384-386, 411-413, 452-454, 477-479).  The source is the same
+ * sequential `dist += (a-b)*(a-b)`, but the reference is compiled -O3 -ffast-math (pydiskann/setup.py:10) and its own arithmetic is
+ * what the compiler made of that: g++ 13 on x86-64 (SSE2 baseline) vectorises the strided memoryview loop two elements at a time
+ * (objdump of oracle/_ref: movss/unpcklps pairs, subps, mulps, addps into ONE two-lane accumulator, then lane0 + lane1, then a
+ * scalar tail; n <= 4 stays scalar).  I.e. even-indexed and odd-indexed terms are summed separately and added at the end.  The
+ * sequential build is chaotic — ONE near-tie decided differently (measured: d(p*,p') vs d(p,p') 4 ulps apart at insertion 469 of a
+ * 1500-point build) changes almost every row afterwards — so the builder restatement has to use the compiled order to stay
+ * row-identical beyond a few hundred points.  Compiler-specific by nature: tests/test_oracle_vs_reference.py checks it live. */
+static float l2sq_refbuild(const float *x, const float *y, int n) {
+    if (n <= 4) return orc_l2sq_seq(x, y, n);
+    float s0 = 0.0f, s1 = 0.0f;
+    const int h = n >> 1;
+    for (int i = 0; i < h; ++i) {
+        float d0 = x[2 * i] - y[2 * i], d1 = x[2 * i + 1] - y[2 * i + 1];
+        s0 += d0 * d0;
+        s1 += d1 * d1;
+    }
+    float s = s0 + s1;
+    if (n & 1) { float d = x[n - 1] - y[n - 1]; s += d * d; }
+    return s;
+}
+
 typedef struct { int *v; int n, cap; } ivec_t;
 static void iv_push(ivec_t *a, int x) {
     if (a->n == a->cap) { a->cap = a->cap ? a->cap * 2 : 8; a->v = (int *)realloc(a->v, sizeof(int) * (size_t)a->cap); }
@@ -668,7 +690,7 @@ static int build_search(const float *P, int D, const ivec_t *adj, long N, int st
     const float *q = P + (size_t)qi * D;
     pfi_t *cand = NULL; int nc = 0, ccap = 0;
     pfi_t *res = (pfi_t *)malloc(sizeof(pfi_t) * (size_t)(L + 2)); int nr = 0;
-    float dist = orc_l2sq_seq(P + (size_t)start * D, q, D);
+    float dist = l2sq_refbuild(P + (size_t)start * D, q, D);
 #define CPUSH(e) do { if (nc == ccap) { ccap = ccap ? ccap * 2 : 256; cand = (pfi_t *)realloc(cand, sizeof(pfi_t) * (size_t)ccap); } cand[nc++] = (e); } while (0)
     CPUSH(((pfi_t){dist, start}));
     res[nr++] = (pfi_t){-dist, start};
@@ -681,7 +703,7 @@ static int build_search(const float *P, int D, const ivec_t *adj, long N, int st
             int nb = adj[cur].v[i];
             if (vis_stamp[nb] == stamp) continue;
             vis_stamp[nb] = stamp;
-            float nd = orc_l2sq_seq(P + (size_t)nb * D, q, D);
+            float nd = l2sq_refbuild(P + (size_t)nb * D, q, D);
             if (nr < L || nd < -res[0].d) {
                 /* compact the consumed prefix lazily so that push_back semantics hold */
                 CPUSH(((pfi_t){nd, nb}));
@@ -707,7 +729,7 @@ static void build_prune(const float *P, int D, ivec_t *adj, int p, const int *cs
     for (int t = 0; t < ncset; ++t) {
         int cid = cset[t];
         if (cid == p) continue;
-        cw[n++] = (pfi_t){orc_l2sq_seq(P + (size_t)p * D, P + (size_t)cid * D, D), cid};
+        cw[n++] = (pfi_t){l2sq_refbuild(P + (size_t)p * D, P + (size_t)cid * D, D), cid};
     }
     qsort(cw, (size_t)n, sizeof(pfi_t), pfi_cmp);
     int bound = n; /* cached loop bound */
@@ -724,7 +746,7 @@ static void build_prune(const float *P, int D, ivec_t *adj, int p, const int *cs
             int insel = 0;
             for (int s = 0; s < ns; ++s) if (sel[s] == pp) { insel = 1; break; }
             if (insel) { ++j; continue; }
-            float dsp = orc_l2sq_seq(P + (size_t)pstar * D, P + (size_t)pp * D, D);
+            float dsp = l2sq_refbuild(P + (size_t)pstar * D, P + (size_t)pp * D, D);
             if (alpha * dsp <= cw[j].d) {
                 memmove(cw + j, cw + j + 1, sizeof(pfi_t) * (size_t)(n - j - 1)); /* erase(begin+j); tail byte image stays */
                 --n;

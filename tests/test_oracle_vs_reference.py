@@ -82,3 +82,22 @@ def test_variant_A_pq_search_equal(world, orc, ref):
         rid = cu.greedy_search_cython(g, 3, q, 20, vg.compute_query_distance)
         h = orc.search_heap(adj, 3, 20, codes=w["codes"], lut_=orc.lut(w["cb"], q), dist_mode=orc.DIST_ADC_SEQ)
         assert list(rid) == [int(x) for x in h["ids"]]                 # same ids in the reference's own output order
+
+
+def test_sequential_build_follows_the_compiled_arithmetic(orc, ref):
+    """The builder's distance loops are compiled -O3 -ffast-math (pydiskann/setup.py:10): g++ sums even- and odd-indexed terms in two
+    lanes and adds them at the end (oracle.c:l2sq_refbuild, from the disassembly of oracle/_ref).  With plain sequential sums this
+    very case diverged at insertion 469 (two distances 4 ulps apart decided the other way) and 1498 of 1500 rows ended up different;
+    with the compiled order every row is identical.  tests/tools/check_build_config0.py does the same at BASELINE configs[0] scale
+    (10k x 1536, R = 32, L = 64: 10000 / 10000 rows, profiles/r01l_build_config0_check.json)."""
+    from diskrag_b200.synth import synth_numpy
+    N, D, R, L, med = 1500, 64, 16, 32, 3
+    X = np.ascontiguousarray(synth_numpy(10000, 1536, seed=20240)[:N, :D])
+    random.seed(5)
+    st = random.getstate()
+    adj_ref = ref["cython_utils"].build_vamana_index_cython(X, R, L, 1.2, med, False)
+    random.setstate(st)
+    s0 = list(range(N)); random.shuffle(s0)
+    s1 = list(range(N)); random.shuffle(s1)
+    rows = orc.vamana_build(X, R, L, 1.2, med, np.array(s0, np.int32), np.array(s1, np.int32))
+    assert sum(list(a) == list(b) for a, b in zip(rows, adj_ref)) == N
