@@ -1,7 +1,9 @@
 """BASELINE configs[1] input: a REFERENCE-EQUIVALENT Vamana graph over 100k x 1536 synthetic vectors, built on the CPU by
 oracle/oracle.c:orc_vamana_build — the restatement of build_vamana_index_cython (cython_utils.pyx:269-492) that
-tests/test_golden_oracle.py pins row for row against the real reference build.  Sequential by nature (~30 min on one
-core); the adjacency (N x R u32, 0-padded like DiskANNPersist.save_index) is cached under .cache/ and the vectors are
+tests/test_golden_oracle.py pins row for row against the real reference build at 600 points and
+tests/tools/check_build_config0.py at 10k x 1536 (10000 / 10000 rows, with the compiled summation order of oracle.c:l2sq_refbuild;
+graphs cached before that fix used plain sequential sums: same algorithm, statistically the same graph, not edge-identical to what the
+reference binary would output).  Sequential by nature (~25 min on one core); the adjacency (N x R u32, 0-padded like DiskANNPersist.save_index) is cached under .cache/ and the vectors are
 regenerated from the seed wherever it is used (tests/tools/parity_config2.py).
 usage: python tests/tools/build_config2_graph.py [N [D R L tag]]     (tag names the cache file: config2 | config4)"""
 import sys, time
