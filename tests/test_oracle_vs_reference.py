@@ -49,7 +49,7 @@ def test_sequential_build_rows_equal(world, orc):
     w = world
     rows = orc.vamana_build(w["X"], w["R"], w["L"], 1.2, 3, w["s0"], w["s1"])
     same = sum(list(a) == list(b) for a, b in zip(rows, w["adj_ref"]))
-    assert same >= 0.99 * w["N"], same                               # -ffast-math may move a near-tie
+    assert same == w["N"], same                                      # compiled summation order restated: every row
 
 
 def test_lut_encode_and_distances(world, orc, ref):
