@@ -168,7 +168,10 @@ static float l2sq_flavor(const float *v, const float *q, int n, int flavor) {
     }
     }
 }
-float orc_l2sq(const float *v, const float *q, int n, int flavor) { return l2sq_flavor(v, q, n, flavor); }
+static float l2sq_refbuild(const float *x, const float *y, int n);
+/* flavor 4 = the order g++ -O3 -ffast-math gives the reference's own `dist += (a-b)*(a-b)` loops (l2_distance_fast_cython and the
+ * builder, see l2sq_refbuild below): bit-identical to the compiled reference in oracle/_ref. */
+float orc_l2sq(const float *v, const float *q, int n, int flavor) { return flavor == 4 ? l2sq_refbuild(v, q, n) : l2sq_flavor(v, q, n, flavor); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* Product quantiser                                                                          */

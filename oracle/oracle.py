@@ -15,7 +15,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB = None
 
 DIST_ADC_SEQ, DIST_L2_SQRT, DIST_L2_SQ, DIST_ADC_TREE, DIST_ADC_U8, DIST_COSINE = 0, 1, 2, 3, 4, 5
-FLAVOR_DOUBLE, FLAVOR_NUMPY, FLAVOR_WARP, FLAVOR_SEQ = 0, 1, 2, 3
+FLAVOR_DOUBLE, FLAVOR_NUMPY, FLAVOR_WARP, FLAVOR_SEQ, FLAVOR_REFCC = 0, 1, 2, 3, 4
 
 
 def build(force: bool = False) -> Path:

@@ -101,3 +101,14 @@ def test_sequential_build_follows_the_compiled_arithmetic(orc, ref):
     s1 = list(range(N)); random.shuffle(s1)
     rows = orc.vamana_build(X, R, L, 1.2, med, np.array(s0, np.int32), np.array(s1, np.int32))
     assert sum(list(a) == list(b) for a, b in zip(rows, adj_ref)) == N
+
+
+def test_l2_helper_bit_equal_in_the_compiled_order(orc, ref):
+    """l2_distance_fast_cython (cython_utils.pyx:18-24) is the same `dist += d*d` loop under -O3 -ffast-math: two lanes (even / odd
+    terms), lane0 + lane1, scalar tail, scalar for n <= 4.  With that order (FLAVOR_REFCC) the restatement is bit-equal, not 1e-5."""
+    cu = ref["cython_utils"]
+    rng = np.random.default_rng(3)
+    for n in (1, 3, 4, 5, 7, 8, 24, 127, 128, 1536, 3071):
+        for _ in range(6):
+            x = rng.standard_normal(n).astype(np.float32); y = rng.standard_normal(n).astype(np.float32)
+            assert np.float32(cu.l2_distance_fast_cython(x, y)) == np.float32(orc.l2sq(x, y, orc.FLAVOR_REFCC)), n
