@@ -415,7 +415,7 @@ static inline float node_dist(const sctx_t *c, long id) {
     case 5: /* distance_metric == 'cosine' (vamana_graph.py:325-326): flavor 2 = GPU warp order, else the reference's loop */
         return c->flavor == 2 ? orc_cosine_warp(c->vec + (size_t)id * c->D, c->q, c->D)
                               : (float)orc_cosine_dist(c->vec + (size_t)id * c->D, c->q, c->D);
-    default: return l2sq_flavor(c->vec + (size_t)id * c->D, c->q, c->D, c->flavor);
+    default: return orc_l2sq(c->vec + (size_t)id * c->D, c->q, c->D, c->flavor);   /* flavor 4: l2_distance_fast_cython's compiled order */
     }
 }
 
@@ -605,6 +605,80 @@ int orc_rerank(const float *vec, int D, const float *q, int flavor,
     for (int i = 0; i < m; ++i) { out_ids[i] = t[i].id; out_d[i] = t[i].d; }
     free(t);
     return m;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Variant C: vamana_graph.py:535-605 beam_search_with_pq (and :690-717 beam_search, the same   */
+/* loop without the delete checks), restated literally INCLUDING its inverted truncation:       */
+/*   beam  = heapq min-heap of (dist, id); top_k = heapq min-heap of (-dist, id), capped at k;  */
+/*   pop the best of beam; stop when it is worse than the worst of a full top_k (:580-581);     */
+/*   every unvisited, undeleted neighbour gets a distance and enters BOTH heaps when top_k is    */
+/*   not full or it beats top_k's worst (:589-593, evicting (max dist, min id));                */
+/*   then `while len(beam) > beam_width: heappop(beam)` (:595-596) throws away the BEST entries */
+/*   of the frontier and keeps the beam_width WORST ones.                                       */
+/* Output (:599-601): the top_k heap ARRAY mapped to (sqrt(d), id) and sorted stably by         */
+/* distance, so exact ties keep heap-array order; out_d holds sqrtf(d) when sqrt_out, else d.   */
+/* deleted (may be NULL): is_deleted flags; the caller resolves a deleted start (:560-567).     */
+/* Rows are scanned in stored order (the reference iterates a Python set; callers that want to  */
+/* compare hand it lists in this order).  Returns the number of results (<= k).                 */
+/* ------------------------------------------------------------------------------------------ */
+int orc_beam_c(const uint32_t *adj, int R, long N,
+               const uint8_t *codes, int M, const float *lut,
+               const float *vec, int D, const float *q, int flavor,
+               int dist_mode, const uint8_t *deleted, int sqrt_out,
+               int start, int beam_width, int k,
+               int32_t *out_ids, float *out_d, int32_t *out_hops, int32_t *out_nvisited,
+               int32_t *trace, int trace_cap) {
+    sctx_t c = {adj, R, N, codes, M, lut, vec, D, q, flavor, dist_mode};
+    uint8_t *visited = (uint8_t *)calloc((size_t)N, 1);
+    heap_t beam, top;
+    heap_init(&beam, beam_width + R + 8);
+    heap_init(&top, k + 2);
+    int hops = 0, nvis = 0;
+
+    float d0 = node_dist(&c, start);
+    visited[start] = 1;
+    if (trace && nvis < trace_cap) trace[nvis] = start;
+    ++nvis;
+    heap_push(&beam, (ent_t){d0, start});
+    heap_push(&top, (ent_t){-d0, start});
+
+    while (beam.n > 0) {
+        ent_t cur = heap_pop(&beam);
+        if (deleted && deleted[cur.id]) continue;                       /* :577-578 */
+        if (cur.d > -top.a[0].d && top.n == k) break;                   /* :580-581 */
+        ++hops;
+        const uint32_t *row = adj + (size_t)cur.id * R;
+        for (int j = 0; j < R; ++j) {
+            uint32_t nb = row[j];
+            if ((long)nb >= N) continue;
+            if (visited[nb] || (deleted && deleted[nb])) continue;     /* :584 */
+            visited[nb] = 1;
+            float nd = node_dist(&c, nb);
+            if (trace && nvis < trace_cap) trace[nvis] = (int32_t)nb;
+            ++nvis;
+            if (top.n < k || nd < -top.a[0].d) {                        /* :589 */
+                heap_push(&beam, (ent_t){nd, (int32_t)nb});
+                heap_push(&top, (ent_t){-nd, (int32_t)nb});
+                if (top.n > k) heap_pop(&top);
+            }
+        }
+        while (beam.n > beam_width) heap_pop(&beam);                    /* :595-596: drops the best */
+    }
+    int n = 0;
+    ent_t *tmp = (ent_t *)malloc(sizeof(ent_t) * (size_t)(top.n > 0 ? top.n : 1));
+    for (int i = 0; i < top.n; ++i) {
+        if (deleted && deleted[top.a[i].id]) continue;                  /* :599 */
+        float d = -top.a[i].d;
+        tmp[n++] = (ent_t){sqrt_out ? sqrtf(d) : d, top.a[i].id};
+    }
+    stable_sort_by_dist(tmp, n);                                        /* :601 key = distance only */
+    for (int i = 0; i < n; ++i) { out_ids[i] = tmp[i].id; out_d[i] = tmp[i].d; }
+    free(tmp);
+    if (out_hops) *out_hops = hops;
+    if (out_nvisited) *out_nvisited = nvis;
+    heap_free(&beam); heap_free(&top); free(visited);
+    return n;
 }
 
 /* Batched drivers for the CPU baseline (one query per OpenMP task).  form: 0 heap, 1 list. */

@@ -148,6 +148,34 @@ def search_list(adj, start, L, *, codes=None, lut_=None, vec=None, q=None, dist_
                    (C.c_int(W), C.c_int(int(strict_ties))), start, L, trace)
 
 
+def beam_c(adj, start, beam_width, k, *, codes=None, lut_=None, vec=None, q=None, dist_mode=DIST_ADC_SEQ,
+           flavor=FLAVOR_REFCC, deleted=None, sqrt_out=True, trace=0):
+    """Variant C, literally: beam_search_with_pq / beam_search (vamana_graph.py:535-605, 690-717) with the reference's
+    inverted frontier truncation; rows scanned in stored order."""
+    adj = np.ascontiguousarray(adj, np.uint32)
+    N, R = adj.shape
+    M = D = 0
+    if codes is not None:
+        codes = np.ascontiguousarray(codes, np.uint8); M = codes.shape[1]; lut_ = _f32(lut_)
+    if vec is not None:
+        vec = _f32(vec); D = vec.shape[1]
+    if q is not None:
+        q = _f32(q)
+    if deleted is not None:
+        deleted = np.ascontiguousarray(deleted, np.uint8)
+    ids = np.full(k + 1, -1, np.int32); d = np.full(k + 1, np.inf, np.float32)
+    hops = C.c_int32(0); nvis = C.c_int32(0)
+    tr = np.full(trace, -1, np.int32) if trace else None
+    n = lib().orc_beam_c(_p(adj), C.c_int(R), C.c_long(N), _p(codes), C.c_int(M), _p(lut_), _p(vec), C.c_int(D), _p(q),
+                         C.c_int(flavor), C.c_int(dist_mode), _p(deleted), C.c_int(int(sqrt_out)), C.c_int(int(start)),
+                         C.c_int(int(beam_width)), C.c_int(int(k)), _p(ids), _p(d), C.byref(hops), C.byref(nvis),
+                         _p(tr), C.c_int(trace))
+    res = {"ids": ids[:n].copy(), "dists": d[:n].copy(), "hops": hops.value, "visited": nvis.value}
+    if trace:
+        res["trace"] = tr[:min(trace, nvis.value)].copy()
+    return res
+
+
 def rerank(vec, q, ids, k, flavor=FLAVOR_WARP):
     vec, q = _f32(vec), _f32(q)
     ids = np.ascontiguousarray(ids, np.int32)

@@ -112,3 +112,44 @@ def test_l2_helper_bit_equal_in_the_compiled_order(orc, ref):
         for _ in range(6):
             x = rng.standard_normal(n).astype(np.float32); y = rng.standard_normal(n).astype(np.float32)
             assert np.float32(cu.l2_distance_fast_cython(x, y)) == np.float32(orc.l2sq(x, y, orc.FLAVOR_REFCC)), n
+
+
+def _ref_graph(w, vg):
+    """the reference's object graph over the world's arrays; neighbours as lists in index.dat order (0-padded rows)"""
+    adj = np.zeros((w["N"], w["R"]), np.uint32)
+    g = vg.VamanaGraphWithPQ(w["R"], w["pq"])
+    for i, row in enumerate(w["adj_ref"]):
+        adj[i, :len(row)] = row[:w["R"]]
+        node = vg.Node(i, w["X"][i], w["codes"][i])
+        node.neighbors = [int(x) for x in adj[i]]
+        g.nodes[i] = node
+    g.medoid_idx = 3
+    return g, adj
+
+
+@pytest.mark.parametrize("bw,k", [(5, 3), (8, 5), (2, 10), (16, 10), (1, 1)])
+def test_variant_C_beam_search_equal(world, orc, ref, bw, k):
+    """beam_search_with_pq / beam_search (vamana_graph.py:535-605, 690-717) vs orc_beam_c: the reference's k-capped beam with its
+    inverted frontier truncation, PQ distances (ADC bits), exact distances (l2_distance_fast_cython's compiled order, bit-equal)
+    and lazily deleted nodes.  Results in the reference's own output order (heap-array order inside exact ties)."""
+    w = world
+    vg = ref["vamana_graph"]
+    g, adj = _ref_graph(w, vg)
+    dead = np.zeros(w["N"], np.uint8)
+    for use_deleted in (False, True):
+        if use_deleted:
+            for i in (5, 17, 40, 41, 42, 300, 301, 599):
+                g.nodes[i].is_deleted = True; dead[i] = 1
+        for q in w["Q"]:
+            r = vg.beam_search_with_pq(g, q, 3, bw, k, use_pq=True)
+            o = orc.beam_c(adj, 3, bw, k, codes=w["codes"], lut_=orc.lut(w["cb"], q), dist_mode=orc.DIST_ADC_SEQ, deleted=dead)
+            assert [int(i) for _, i in r] == [int(i) for i in o["ids"]]
+            assert np.array_equal(np.array([d for d, _ in r], np.float32), o["dists"])           # np.sqrt of the f32 ADC sum
+            r = vg.beam_search_with_pq(g, q, 3, bw, k, use_pq=False)
+            o = orc.beam_c(adj, 3, bw, k, vec=w["X"], q=q, dist_mode=orc.DIST_L2_SQ, flavor=orc.FLAVOR_REFCC, deleted=dead,
+                           sqrt_out=False)
+            assert [int(i) for _, i in r] == [int(i) for i in o["ids"]]
+            assert np.array_equal(np.array([d for d, _ in r]), np.sqrt(o["dists"].astype(np.float64)))  # np.sqrt of a Python float
+            if not use_deleted:
+                r2 = vg.beam_search(g, q, 3, bw, k)                                              # dispatches to the same loop
+                assert [int(i) for _, i in r2] == [int(i) for i in o["ids"]]
