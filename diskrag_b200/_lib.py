@@ -43,6 +43,7 @@ SIGNATURES = {
     "dr_index_export_records": (C.c_int, [_vp, _vp]),
     "dr_search_batch": (C.c_int, [_vp, _vp, _i64, _PP(SearchParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "dr_search_batch_dev": (C.c_int, [_vp, _vp, _i64, _PP(SearchParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "dr_beam_search_c": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dr_launch_count": (_i64, []),
     "dr_search_kernel_timing": (C.c_int, [_vp, C.c_int, _PP(_dbl), _PP(_i64)]),
     "dr_lut_build": (C.c_int, [_vp, _vp, _i64, _vp]),

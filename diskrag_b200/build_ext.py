@@ -7,7 +7,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libdiskrag_b200.so"
-SOURCES = ["api.cu", "search.cu", "search_fast.cu", "lut_tc.cu", "kmeans_tc.cu", "pq.cu", "distance.cu", "build.cu"]
+SOURCES = ["api.cu", "search.cu", "search_fast.cu", "lut_tc.cu", "kmeans_tc.cu", "pq.cu", "distance.cu", "build.cu", "beam_c.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # FMAs only where written explicitly: the summation orders are part of the contract

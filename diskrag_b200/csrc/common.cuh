@@ -85,6 +85,9 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
 int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, int32_t *ids, float *dist,
                        int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist, int32_t *list_len,
                        int32_t *status, cudaStream_t s);   // search_fast.cu: u8-table throughput kernel
+void beam_c_plan(const dr_index *h, int64_t B, long long *grid_out, size_t *bitmap_bytes_out);   // beam_c.cu
+int launch_beam_c(dr_index *h, const float *d_Q, int64_t B, int k, int bw, int dist, int sqrt_out, const float *d_lut,
+                  uint32_t *d_bitmaps, int32_t *ids, float *dists, int32_t *hops, int32_t *visited, cudaStream_t s);
 int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
                         float *d_offset, float *d_mn, unsigned *d_range, int word_layout, cudaStream_t s);  // pq.cu
 int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,

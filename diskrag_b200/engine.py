@@ -150,6 +150,25 @@ class GpuIndex:
         return SearchResult(ids=ids, dists=dd, hops=hops, visited=vis, status=st, list_ids=lids, list_dists=ldist,
                             list_len=llen, trace=tr)
 
+    def beam_search_c(self, Q, k=3, beam_width=5, dist="pq", sqrt_out=True) -> SearchResult:
+        """Variant C with the reference's own semantics (vamana_graph.py:535-605; csrc/beam_c.cu): the k-capped beam whose
+        truncation keeps the beam_width WORST frontier entries.  Results sorted by (dist, id); ids -1 padded."""
+        Q = as_f32(np.atleast_2d(Q))
+        B, D = Q.shape
+        if D != self.D:
+            raise ValueError(f"query dimension {D} != index dimension {self.D}")
+        if dist not in ("pq", "exact"):
+            raise ValueError("beam_search_c: dist must be 'pq' or 'exact'")
+        if dist == "pq" and self.M == 0:
+            raise ValueError("index has no PQ codes; use dist='exact'")
+        ids = np.empty((B, k), np.int32); dd = np.empty((B, k), np.float32)
+        hops = np.empty(B, np.int32); vis = np.empty(B, np.int32)
+        check(lib().dr_beam_search_c(self._h, ptr(Q), B, int(k), int(beam_width),
+                                     _lib.DR_DIST_PQ if dist == "pq" else _lib.DR_DIST_EXACT, int(bool(sqrt_out)),
+                                     ptr(ids), ptr(dd), ptr(hops), ptr(vis)), "dr_beam_search_c")
+        return SearchResult(ids=ids, dists=dd, hops=hops, visited=vis, status=np.zeros(B, np.int32), list_ids=None,
+                            list_dists=None, list_len=None, trace=None)
+
     def search_host(self, Q, params: SearchParams, ids, dists=None, hops=None, visited=None, status=None):
         """Same call as `search` but into caller-owned host arrays (e.g. pinned buffers): Q f32[B,D] ->
         ids i32[B,k], dists f32[B,k], hops/visited/status i32[B].  H2D and D2H copies happen inside."""

@@ -495,7 +495,10 @@ greedy_search_optimized = greedy_search
 greedy_search_with_pq = greedy_search
 
 
-def beam_search_with_pq(graph, query_vector, start_idx=None, beam_width=5, k=3, use_pq=True):
+def beam_search_with_pq(graph, query_vector, start_idx=None, beam_width=5, k=3, use_pq=True, *, reference_semantics=False):
+    """Variant C (:535-605).  By default the correct search (list size max(k, beam_width)): the reference's own loop throws
+    the BEST frontier entries away when it truncates (:595-596), which costs it recall.  reference_semantics=True runs that
+    loop as written (csrc/beam_c.cu, dr_beam_search_c) for callers that depend on the reference's exact answers; l2 only."""
     g = _as_graph(graph)
     if start_idx is None:
         start_idx = g.medoid_idx if g.medoid_idx is not None else 0
@@ -505,14 +508,20 @@ def beam_search_with_pq(graph, query_vector, start_idx=None, beam_width=5, k=3, 
     pq = bool(use_pq and g.pq_model and g.pq_model.is_fitted and g._codes is not None)
     idx = g.gpu_index()
     check(lib().dr_index_set_start(idx._h, start))
+    if reference_semantics:
+        if not pq and getattr(g, "distance_metric", "l2") != "l2":
+            raise ValueError("reference_semantics=True supports distance_metric='l2' only")
+        r = idx.beam_search_c(as_f32(query_vector).reshape(1, -1), k=int(k), beam_width=int(beam_width),
+                              dist="pq" if pq else "exact", sqrt_out=True)
+        return [(r.dists[0, i], int(r.ids[0, i])) for i in range(int(k)) if r.ids[0, i] >= 0]
     L = max(int(k), int(beam_width))
     r = idx.search(as_f32(query_vector).reshape(1, -1), k=int(k), L=L, W=1, dist="pq" if pq else "exact", rerank=False,
                    sqrt_out=True)
     return [(r.dists[0, i], int(r.ids[0, i])) for i in range(int(k)) if r.ids[0, i] >= 0]
 
 
-def beam_search(graph, query_vector, start_idx, beam_width=5, k=3):
-    return beam_search_with_pq(graph, query_vector, start_idx, beam_width, k, False)
+def beam_search(graph, query_vector, start_idx, beam_width=5, k=3, *, reference_semantics=False):
+    return beam_search_with_pq(graph, query_vector, start_idx, beam_width, k, False, reference_semantics=reference_semantics)
 
 
 _READER_CACHE = {}

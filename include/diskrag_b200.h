@@ -127,6 +127,15 @@ int dr_search_batch_dev(dr_index *h, const float *d_Q, int64_t B, const dr_searc
                         int32_t *d_out_ids, float *d_out_dist, int32_t *d_out_hops, int32_t *d_out_visited,
                         int32_t *d_out_list_ids, float *d_out_list_dist, int32_t *d_out_list_len,
                         int32_t *d_trace, int32_t trace_cap, int32_t *d_out_status, void *stream);
+/* Variant C with the reference's OWN semantics: beam_search_with_pq (vamana_graph.py:535-605) / beam_search (:690-717), the
+ * k-capped beam whose frontier truncation keeps the beam_width WORST entries (:595-596).  dr_search_batch is the search the
+ * shims run by default; this entry point returns what the reference's function returns on the same graph, for callers that
+ * depend on it (restated in oracle/oracle.c:orc_beam_c and checked against the real reference).  Q f32[B,D] on the host;
+ * dist = DR_DIST_PQ (ADC, sequential fp32 sum) or DR_DIST_EXACT (squared L2); the start node is the index's (dr_index_set_start);
+ * lazily deleted nodes are skipped like :577-584.  out_ids i32[B,k] (-1 padded) and out_dist f32[B,k] sorted by (dist, id);
+ * sqrt_out = 1 reports sqrt(d) like :601.  out_dist / out_hops / out_visited may be NULL. */
+int dr_beam_search_c(dr_index *h, const float *Q, int64_t B, int32_t k, int32_t beam_width, int32_t dist, int32_t sqrt_out,
+                     int32_t *out_ids, float *out_dist, int32_t *out_hops, int32_t *out_visited);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t dr_launch_count(void);
 /* device time (ms) and launches of the search kernel alone, accumulated since the last reset,
