@@ -681,6 +681,93 @@ int orc_beam_c(const uint32_t *adj, int R, long N,
     return n;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Variant E: SearchEngineCorrect._pq_accelerated_graph_search (search_engine.py:398-506), the  */
+/* served search, restated literally.  It is stochastic — a neighbour whose (non-squared!) ADC  */
+/* distance lies in [0.8, 1.2) x the worst kept (squared) exact distance gets its exact distance */
+/* with probability 0.2 (np.random.random() < 0.2, :394-395) — so the restatement carries       */
+/* numpy's legacy generator: MT19937 seeded like np.random.seed(int) (init_genrand) and         */
+/* random_sample() = genrand_res53.  With the same seed it reproduces the reference draw for    */
+/* draw.  mt: 625 words of generator state (624 + position), owned by the caller.               */
+/* ------------------------------------------------------------------------------------------ */
+void orc_mt_seed(uint32_t *mt, uint32_t seed) {
+    mt[0] = seed;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    mt[624] = 624;
+}
+static uint32_t mt_next(uint32_t *mt) {
+    if (mt[624] >= 624) {
+        for (int i = 0; i < 624; ++i) {
+            uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+            mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        mt[624] = 0;
+    }
+    uint32_t y = mt[mt[624]++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+double orc_mt_random(uint32_t *mt) {
+    uint32_t a = mt_next(mt) >> 5, b = mt_next(mt) >> 6;
+    return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+}
+
+/* stats: [0] nodes_visited, [1] exact_distance_computations, [2] pq_distance_computations, [3] search_steps.
+ * beam_width <= 0 = None (no frontier truncation, the /search default passes 8).  out_d = exact squared L2 in
+ * numpy's summation order (np.sum(diff * diff), :374-379).  Returns min(k, len(results)). */
+int orc_search_e(const uint32_t *adj, int R, long N,
+                 const uint8_t *codes, int M, const float *lut,
+                 const float *vec, int D, const float *q,
+                 int start, int L, int k, int beam_width, uint32_t *mt,
+                 int32_t *out_ids, float *out_d, int32_t *stats) {
+    uint8_t *visited = (uint8_t *)calloc((size_t)N, 1);
+    heap_t cand, res;
+    heap_init(&cand, 4 * L + 64);
+    heap_init(&res, L + 2);
+    int nvis = 1, nexact = 0, npq = 0, steps = 0;
+    const long max_steps = (long)L * 10 < N ? (long)L * 10 : N;                       /* :430 */
+    visited[start] = 1;
+    float d0 = orc_l2sq_numpy(vec + (size_t)start * D, q, D); ++nexact;
+    heap_push(&cand, (ent_t){d0, start});
+    heap_push(&res, (ent_t){-d0, start});
+    while (cand.n > 0 && steps < max_steps) {
+        ++steps;
+        ent_t cur = heap_pop(&cand);
+        if (res.n >= L && cur.d > -res.a[0].d) break;                                 /* :439-440 */
+        const uint32_t *row = adj + (size_t)cur.id * R;
+        for (int j = 0; j < R; ++j) {
+            uint32_t nb = row[j];
+            if ((long)nb >= N || visited[nb]) continue;
+            visited[nb] = 1; ++nvis;
+            float pq = sqrtf(adc_seq(codes + (size_t)nb * M, lut, M)); ++npq;       /* asymmetric_distance: sqrt (:368-369) */
+            float worst = res.n ? -res.a[0].d : INFINITY;
+            int take;                                                                 /* _should_compute_exact_distance (:381-397) */
+            if (res.n < L) take = 1;
+            else if (pq < worst * 0.8f) take = 1;                                     /* np.float32 * python float stays float32 */
+            else if (pq < worst * 1.2f) take = orc_mt_random(mt) < 0.2;
+            else take = 0;
+            if (!take) continue;
+            float ed = orc_l2sq_numpy(vec + (size_t)nb * D, q, D); ++nexact;
+            if (res.n < L || ed < -res.a[0].d) {
+                heap_push(&cand, (ent_t){ed, (int32_t)nb});
+                heap_push(&res, (ent_t){-ed, (int32_t)nb});
+                if (res.n > L) heap_pop(&res);
+            }
+        }
+        if (beam_width > 0 && cand.n > beam_width) heap_truncate_nsmallest(&cand, beam_width);   /* :477-479 */
+    }
+    int n = res.n;
+    ent_t *tmp = (ent_t *)malloc(sizeof(ent_t) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i) tmp[i] = (ent_t){-res.a[i].d, res.a[i].id};
+    stable_sort_by_dist(tmp, n);                                                      /* :487 key = distance */
+    int m = n < k ? n : k;
+    for (int i = 0; i < m; ++i) { out_ids[i] = tmp[i].id; out_d[i] = tmp[i].d; }
+    free(tmp);
+    if (stats) { stats[0] = nvis; stats[1] = nexact; stats[2] = npq; stats[3] = steps; }
+    heap_free(&cand); heap_free(&res); free(visited);
+    return m;
+}
+
 /* Batched drivers for the CPU baseline (one query per OpenMP task).  form: 0 heap, 1 list. */
 void orc_search_batch(const uint32_t *adj, int R, long N,
                       const uint8_t *codes, int M, const float *codebook,

@@ -176,6 +176,33 @@ def beam_c(adj, start, beam_width, k, *, codes=None, lut_=None, vec=None, q=None
     return res
 
 
+class NumpyLegacyRandom:
+    """np.random.seed(int) + np.random.random(), restated (MT19937 init_genrand / genrand_res53) for variant E."""
+
+    def __init__(self, seed):
+        self.state = np.zeros(625, np.uint32)
+        lib().orc_mt_seed(_p(self.state), C.c_uint32(int(seed) & 0xFFFFFFFF))
+
+    def random(self):
+        lib().orc_mt_random.restype = C.c_double
+        return float(lib().orc_mt_random(_p(self.state)))
+
+
+def search_e(adj, vec, codes, lut_, q, start, L, k, beam_width=None, rng=None):
+    """Variant E, literally: SearchEngineCorrect._pq_accelerated_graph_search (search_engine.py:398-506), stochastic gate
+    included; rng = NumpyLegacyRandom(seed) plays np.random.seed(seed).  -> ids, exact squared distances, stats dict."""
+    adj = np.ascontiguousarray(adj, np.uint32); vec = _f32(vec); q = _f32(q); lut_ = _f32(lut_)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    N, R = adj.shape
+    rng = rng or NumpyLegacyRandom(0)
+    ids = np.full(k, -1, np.int32); d = np.full(k, np.inf, np.float32); st = np.zeros(4, np.int32)
+    n = lib().orc_search_e(_p(adj), C.c_int(R), C.c_long(N), _p(codes), C.c_int(codes.shape[1]), _p(lut_), _p(vec),
+                           C.c_int(vec.shape[1]), _p(q), C.c_int(int(start)), C.c_int(int(L)), C.c_int(int(k)),
+                           C.c_int(int(beam_width or 0)), _p(rng.state), _p(ids), _p(d), _p(st))
+    return ids[:n].copy(), d[:n].copy(), {"nodes_visited": int(st[0]), "exact_distance_computations": int(st[1]),
+                                          "pq_distance_computations": int(st[2]), "search_steps": int(st[3])}
+
+
 def rerank(vec, q, ids, k, flavor=FLAVOR_WARP):
     vec, q = _f32(vec), _f32(q)
     ids = np.ascontiguousarray(ids, np.int32)

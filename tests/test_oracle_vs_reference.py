@@ -153,3 +153,86 @@ def test_variant_C_beam_search_equal(world, orc, ref, bw, k):
             if not use_deleted:
                 r2 = vg.beam_search(g, q, 3, bw, k)                                              # dispatches to the same loop
                 assert [int(i) for _, i in r2] == [int(i) for i in o["ids"]]
+
+
+def _load_reference_search_engine():
+    """search_engine.py of the reference, imported from /root/reference with its text-pipeline imports (preprocessing.*: polars,
+    OpenAI config) stubbed for the duration of the import; pydiskann resolves to oracle/_ref.  None where the tree is absent."""
+    import importlib.util
+    import types
+    src = Path("/root/reference/search_engine.py")
+    if not src.exists():
+        return None
+    stubs = {"preprocessing": types.ModuleType("preprocessing"), "preprocessing.collection": types.ModuleType("preprocessing.collection"),
+             "preprocessing.config": types.ModuleType("preprocessing.config")}
+    stubs["preprocessing.collection"].CollectionManager = object
+    stubs["preprocessing.config"].CollectionInfo = object
+    stubs["preprocessing.config"].validate_vector_dimension = lambda *a, **k: True
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_search_engine", str(src))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def test_variant_E_served_search_equal_under_a_fixed_seed(world, orc, ref, tmp_path):
+    """SearchEngineCorrect._pq_accelerated_graph_search (search_engine.py:398-506) is stochastic (np.random.random() < 0.2, :394-395);
+    with np.random.seed(s) it is reproducible, and orc_search_e — carrying numpy's legacy MT19937 — reproduces it draw for draw:
+    same ids in the same order, exact squared distances bit-equal (np.sum(diff * diff)), same visited / exact / PQ / step counts."""
+    import threading
+    se = _load_reference_search_engine()
+    if se is None:
+        pytest.skip("/root/reference/search_engine.py not present")
+    from diskrag_b200.pq.fast_pq import _wrap_kmeans
+    vg, dp, cu, fp = ref["vamana_graph"], ref["diskann_persist"], ref["cython_utils"], ref["fast_pq"]
+    # unit-norm points (like the embeddings DiskRAG serves): squared distances below 1 sit under their own square roots, so all
+    # three branches of the gate (:381-397) are taken; the module's Gaussian world never leaves the first two
+    rng0 = np.random.default_rng(23)
+    w = dict(world)
+    X = rng0.standard_normal((w["N"], w["D"])).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True) * np.float32(1.6)
+    X[w["N"] - 20:] = X[:20]
+    Q = rng0.standard_normal((12, w["D"])).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True) * np.float32(1.6)
+    random.seed(29)
+    w["adj_ref"] = cu.build_vamana_index_cython(X, w["R"], w["L"], 1.2, 3, False)
+    ds = w["D"] // w["M"]
+    w["cb"] = np.stack([X[rng0.choice(w["N"], 256, replace=False), m * ds:(m + 1) * ds] for m in range(w["M"])]).astype(np.float32)
+    pq = fp.DiskANNPQ(w["M"], 256)
+    pq.sub_dim = ds; pq.is_fitted = True
+    pq.kmeans_list = [_wrap_kmeans(w["cb"][m], 42 + m) for m in range(w["M"])]
+    w.update(X=X, Q=Q, pq=pq, codes=pq.encode(X))
+    g, adj = _ref_graph(w, vg)
+    for node in g.nodes.values():
+        node.neighbors = [int(x) for x in w["adj_ref"][node.idx]]       # save_index pads the rows itself
+    dp.DiskANNPersist(dim=w["D"], R=w["R"]).save_index(str(tmp_path / "index.dat"), g)
+    eng = object.__new__(se.SearchEngineCorrect)                         # SURVEY §8c: the seam without the collection store
+    eng.reader = dp.MMapNodeReader(str(tmp_path / "index.dat"), dim=w["D"], R=w["R"])
+    eng.pq_model = w["pq"]; eng.pq_codes = w["codes"]; eng.n_subvectors = w["M"]; eng.sub_dim = w["D"] // w["M"]
+    eng.num_centroids = 256; eng.meta = {"N": w["N"]}; eng.medoid_idx = 3; eng.use_pq = True
+    eng.search_stats = {"total_searches": 0, "total_exact_computations": 0, "total_pq_computations": 0, "total_search_time": 0.0}
+    eng.use_thread_safe_stats = True; eng._stats_lock = threading.Lock()
+    gated = draws = 0
+    for seed, (L, k, bw) in enumerate([(20, 10, None), (20, 10, 8), (8, 5, 4), (40, 10, 8), (5, 5, None)]):
+        np.random.seed(seed)
+        rng = orc.NumpyLegacyRandom(seed)
+        for q in w["Q"]:
+            res, st = eng._pq_accelerated_graph_search(q, k=k, L=L, beam_width=bw)
+            ids, d2, ost = orc.search_e(adj, w["X"], w["codes"], orc.lut(w["cb"], q), q, 3, L, k, bw, rng)
+            assert [int(i) for _, i in res] == [int(i) for i in ids], (seed, L, k, bw)
+            assert np.array_equal(np.array([d for d, _ in res], np.float32), d2)
+            for key in ("nodes_visited", "exact_distance_computations", "pq_distance_computations", "search_steps"):
+                assert st[key] == ost[key], (key, seed)
+            gated += ost["pq_distance_computations"] - (ost["exact_distance_computations"] - 1)
+        draws += int(rng.state[624] != 624)
+        assert np.random.random() == rng.random()                       # both generators consumed the same number of draws
+    assert gated > 0 and draws > 0                                                    # the PQ gate did skip exact distances somewhere
+    eng.reader.close()
