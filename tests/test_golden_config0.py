@@ -114,3 +114,21 @@ def test_gpu_rerank_and_exact_search_equal_the_reference(g0, vectors):
         np.testing.assert_allclose(d.dists[qi], g["exp_D_dist"][qi], rtol=1e-4)
         assert set(d.ids[qi].tolist()) == set(g["exp_D_ids"][qi].tolist()), qi
     assert rec(t.ids) >= float(g["recall_rerank"]) - 0.02
+
+
+def test_deterministic_seam_against_the_stochastic_served_search(g0, orc, vectors):
+    """§8 a8: the GPU seam replaces the reference's stochastic variant E (search_engine.py:398-506) by PQ traversal + exact rerank.
+    On the reference-built configs[0] index, with variant E restated literally (orc_search_e, pinned live against the real method):
+    at the served settings (L = 100, beam_width = 8, search_engine.py:530) E reaches recall@10 0.942 with ~1066 exact distance
+    computations per query; the deterministic composition (the fixture's recall_rerank, produced by the real reference's own
+    functions and reproduced bit-for-bit by the GPU path) reaches 0.947 with 100."""
+    g, X = g0, vectors
+    rec = lambda ids: float(np.mean([len(set(ids[i]) & set(g["gt"][i].tolist())) / 10 for i in range(len(ids))]))
+    rng = orc.NumpyLegacyRandom(0)
+    out, exact = [], []
+    for qi in range(g["Q"].shape[0]):
+        q = g["Q"][qi]
+        ids, _, st = orc.search_e(g["adj"], X, g["codes"], orc.lut(g["codebook"], q), q, g["medoid"], 100, 10, 8, rng)
+        out.append(ids.tolist()); exact.append(st["exact_distance_computations"])
+    assert float(g["recall_rerank"]) >= rec(out) - 0.005
+    assert np.mean(exact) > 5 * 100                               # what the stochastic gate spends on exact distances per query
