@@ -372,22 +372,26 @@ int dr_beam_search_c(dr_index *h, const float *Q, int64_t B, int32_t k, int32_t 
     if (B == 0) return 0;
     const bool pq = dist == DR_DIST_PQ;
     DR_CHECK(!pq || (h->d_codebook && h->d_codes && h->M > 0), "dr_beam_search_c: index has no PQ codes / codebook");
+    const int64_t CH = B < 4096 ? B : 4096;   // queries per launch: bounds the table buffer (M KB per query)
     long long grid; size_t per_cta;
-    beam_c_plan(h, B, &grid, &per_cta);
+    beam_c_plan(h, CH, &grid, &per_cta);
     DevBuf q, lut, bm, ids, dd, hh, vv;
-    if (q.alloc((size_t)B * h->D * 4) || bm.alloc(per_cta * (size_t)grid) || ids.alloc((size_t)B * k * 4) ||
-        dd.alloc((size_t)B * k * 4) || hh.alloc((size_t)B * 4) || vv.alloc((size_t)B * 4)) return 1;
-    if (pq && lut.alloc((size_t)B * h->M * 1024)) return 1;
+    if (q.alloc((size_t)CH * h->D * 4) || bm.alloc(per_cta * (size_t)grid) || ids.alloc((size_t)CH * k * 4) ||
+        dd.alloc((size_t)CH * k * 4) || hh.alloc((size_t)CH * 4) || vv.alloc((size_t)CH * 4)) return 1;
+    if (pq && lut.alloc((size_t)CH * h->M * 1024)) return 1;
     cudaStream_t s = 0;   // one-query-per-call compatibility path: the default stream, no pipeline
-    DR_CUDA(cudaMemcpyAsync(q.p, Q, (size_t)B * h->D * 4, cudaMemcpyHostToDevice, s));
-    if (pq && launch_lut_build(h->d_codebook, q.as<float>(), B, h->D, h->M, lut.as<float>(), s)) return 1;
-    if (launch_beam_c(h, q.as<float>(), B, k, beam_width, dist, sqrt_out, pq ? lut.as<float>() : nullptr, bm.as<uint32_t>(),
-                      ids.as<int32_t>(), dd.as<float>(), hh.as<int32_t>(), vv.as<int32_t>(), s)) return 1;
-    DR_CUDA(cudaMemcpyAsync(out_ids, ids.p, (size_t)B * k * 4, cudaMemcpyDeviceToHost, s));
-    if (out_dist) DR_CUDA(cudaMemcpyAsync(out_dist, dd.p, (size_t)B * k * 4, cudaMemcpyDeviceToHost, s));
-    if (out_hops) DR_CUDA(cudaMemcpyAsync(out_hops, hh.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (out_visited) DR_CUDA(cudaMemcpyAsync(out_visited, vv.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    DR_CUDA(cudaStreamSynchronize(s));
+    for (int64_t c0 = 0; c0 < B; c0 += CH) {
+        const int64_t nb = (B - c0) < CH ? (B - c0) : CH;
+        DR_CUDA(cudaMemcpyAsync(q.p, Q + (size_t)c0 * h->D, (size_t)nb * h->D * 4, cudaMemcpyHostToDevice, s));
+        if (pq && launch_lut_build(h->d_codebook, q.as<float>(), nb, h->D, h->M, lut.as<float>(), s)) return 1;
+        if (launch_beam_c(h, q.as<float>(), nb, k, beam_width, dist, sqrt_out, pq ? lut.as<float>() : nullptr, bm.as<uint32_t>(),
+                          ids.as<int32_t>(), dd.as<float>(), hh.as<int32_t>(), vv.as<int32_t>(), s)) return 1;
+        DR_CUDA(cudaMemcpyAsync(out_ids + (size_t)c0 * k, ids.p, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, s));
+        if (out_dist) DR_CUDA(cudaMemcpyAsync(out_dist + (size_t)c0 * k, dd.p, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, s));
+        if (out_hops) DR_CUDA(cudaMemcpyAsync(out_hops + c0, hh.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+        if (out_visited) DR_CUDA(cudaMemcpyAsync(out_visited + c0, vv.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+        DR_CUDA(cudaStreamSynchronize(s));
+    }
     return 0;
 }
 
