@@ -236,3 +236,20 @@ def test_variant_E_served_search_equal_under_a_fixed_seed(world, orc, ref, tmp_p
         assert np.random.random() == rng.random()                       # both generators consumed the same number of draws
     assert gated > 0 and draws > 0                                                    # the PQ gate did skip exact distances somewhere
     eng.reader.close()
+
+
+def test_reference_python_prune_keeps_the_R_nearest(world, ref):
+    """Evidence for a deliberate difference: robust_prune_cython (cython_utils.pyx:124-167, the prune insert_node
+    uses) iterates the list object it started with while its removals rebind the name (:151 vs :165), so no candidate is ever
+    pruned: the result is the R nearest live candidates whatever alpha is.  The shim runs a real RobustPrune instead
+    (dr_robust_prune), as SURVEY §8(f3) asks; this test keeps the statement about the reference honest."""
+    w = world
+    vg, cu = ref["vamana_graph"], ref["cython_utils"]
+    g, _ = _ref_graph(w, vg)
+    rng = np.random.default_rng(5)
+    for alpha in (1.0, 1.2, 2.0):
+        for p in (0, 7, 123, 599):
+            cands = set(int(c) for c in rng.choice(w["N"], 40, replace=False) if int(c) != p)
+            cu.robust_prune_cython(g, p, cands, alpha, w["R"], vg.compute_distance)
+            d = sorted((cu.l2_distance_fast_cython(w["X"][p], w["X"][c]), c) for c in cands)
+            assert g.nodes[p].neighbors == set(c for _, c in d[:w["R"]]), (alpha, p)
