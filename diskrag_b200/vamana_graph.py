@@ -539,7 +539,7 @@ def _reader_index(reader) -> GpuIndex:
     n = rec.size // (4 * (reader.D + reader.R))
     idx = GpuIndex.from_records(rec, n, reader.D, reader.R, medoid=0)
     if len(_READER_CACHE) > 8:
-        _, old = _READER_CACHE.popitem()
+        old = _READER_CACHE.pop(next(iter(_READER_CACHE)))      # the oldest entry (dicts keep insertion order)
         old[1].close()
     _READER_CACHE[key] = (reader, idx)
     return idx
