@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import canon
+from conftest import ROOT, canon
 
 
 def test_lut_bit_exact(golden, orc):
@@ -109,3 +109,42 @@ def test_sequential_build_bit_equal(golden, orc):
         same += list(exp) == list(row)
     # the builder restatement follows the summation order the reference's compiler produced (oracle.c:l2sq_refbuild): every row
     assert same == NB
+
+
+def test_variants_C_and_E_golden(golden, orc):
+    """tests/golden/ref_variants_ce.npz (tests/golden/make_golden_variants.py): what the REAL reference returned on the ref_small
+    index for variant C (beam_search_with_pq, vamana_graph.py:535-605, live and with lazily deleted nodes, PQ and exact) and for the
+    stochastic variant E (SearchEngineCorrect._pq_accelerated_graph_search, search_engine.py:398-506, under np.random.seed).  The
+    oracle's literal restatements reproduce every list: ids in the reference's output order, distances bit-equal, E's visited /
+    exact / PQ / step counts, and the generator position after each run."""
+    g = golden
+    z = np.load(ROOT / "tests" / "golden" / "ref_variants_ce.npz")
+    nq = int(z["nq"])
+    Q = g["Q"][:nq]
+    luts = [orc.lut(g["codebook"], q) for q in Q]
+    for tag, dead in (("live", np.zeros(g["N"], np.uint8)), ("del", z["deleted"])):
+        for bw, k in z["shapes_c"]:
+            for qi, q in enumerate(Q):
+                e_ids = z[f"exp_C_{tag}_pq_bw{bw}_k{k}_ids"][qi]; e_d = z[f"exp_C_{tag}_pq_bw{bw}_k{k}_d"][qi]
+                n = int((e_ids >= 0).sum())
+                o = orc.beam_c(g["adj"], g["medoid"], int(bw), int(k), codes=g["codes"], lut_=luts[qi], dist_mode=orc.DIST_ADC_SEQ,
+                               deleted=dead)
+                assert list(o["ids"]) == list(e_ids[:n]) and np.array_equal(o["dists"], e_d[:n].astype(np.float32))
+                e_ids = z[f"exp_C_{tag}_l2_bw{bw}_k{k}_ids"][qi]; e_d = z[f"exp_C_{tag}_l2_bw{bw}_k{k}_d"][qi]
+                n = int((e_ids >= 0).sum())
+                o = orc.beam_c(g["adj"], g["medoid"], int(bw), int(k), vec=g["vec"], q=q, dist_mode=orc.DIST_L2_SQ,
+                               flavor=orc.FLAVOR_REFCC, deleted=dead, sqrt_out=False)
+                assert list(o["ids"]) == list(e_ids[:n]) and np.array_equal(np.sqrt(o["dists"].astype(np.float64)), e_d[:n])
+    gated = 0
+    for seed, (L, k, bw) in enumerate(z["shapes_e"]):
+        rng = orc.NumpyLegacyRandom(seed)
+        for qi, q in enumerate(Q):
+            ids, d2, st = orc.search_e(g["adj"], g["vec"], g["codes"], luts[qi], q, g["medoid"], int(L), int(k), int(bw), rng)
+            e_ids = z[f"exp_E_seed{seed}_ids"][qi]
+            n = int((e_ids >= 0).sum())
+            assert list(ids) == list(e_ids[:n]) and np.array_equal(d2, z[f"exp_E_seed{seed}_d2"][qi][:n])
+            assert [st["nodes_visited"], st["exact_distance_computations"], st["pq_distance_computations"], st["search_steps"]] \
+                == list(z[f"exp_E_seed{seed}_stats"][qi])
+            gated += st["pq_distance_computations"] - (st["exact_distance_computations"] - 1)
+        assert rng.random() == float(z[f"exp_E_seed{seed}_next_draw"])
+    assert gated > 0

@@ -50,6 +50,36 @@ def check_case(c, shapes, deleted_ids=()):
     return n_checked
 
 
+def check_golden():
+    """the device against what the REAL reference returned (tests/golden/ref_variants_ce.npz, ref_small index): PQ lists bit-equal
+    (ids and sqrt'ed ADC distances), exact lists: same ids, distances within 1e-4 relative (BASELINE's tolerance)"""
+    z = np.load(ROOT / "tests" / "golden" / "ref_small.npz"); v = np.load(ROOT / "tests" / "golden" / "ref_variants_ce.npz")
+    N, D, R, med = int(z["N"]), int(z["D"]), int(z["R"]), int(z["medoid"])
+    Q = z["Q"][:int(v["nq"])]
+    n = 0
+    from diskrag_b200._lib import check, lib, ptr
+    with GpuIndex.from_records(z["records"], N, D, R, z["codes"], z["codebook"], med) as idx:
+        for tag in ("live", "del"):
+            check(lib().dr_index_set_deleted(idx._h, ptr(np.ascontiguousarray(v["deleted"])) if tag == "del" else None))
+            for bw, k in v["shapes_c"]:
+                r = idx.beam_search_c(Q, k=int(k), beam_width=int(bw), dist="pq", sqrt_out=True)
+                x = idx.beam_search_c(Q, k=int(k), beam_width=int(bw), dist="exact", sqrt_out=True)
+                for qi in range(len(Q)):
+                    a = canon(v[f"exp_C_{tag}_pq_bw{bw}_k{k}_ids"][qi], v[f"exp_C_{tag}_pq_bw{bw}_k{k}_d"][qi].astype(np.float32))
+                    b = canon(r.ids[qi], r.dists[qi])
+                    e_ids = v[f"exp_C_{tag}_l2_bw{bw}_k{k}_ids"][qi]; e_d = v[f"exp_C_{tag}_l2_bw{bw}_k{k}_d"][qi]
+                    m = int((e_ids >= 0).sum())
+                    ok = (np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+                          and set(x.ids[qi][x.ids[qi] >= 0].tolist()) == set(e_ids[:m].tolist())
+                          and np.allclose(np.sort(x.dists[qi][:m]), np.sort(e_d[:m]), rtol=1e-4))
+                    if not ok:
+                        print(json.dumps({"ok": False, "golden": True, "tag": tag, "bw": int(bw), "k": int(k), "query": qi,
+                                          "gpu_pq": [r.ids[qi].tolist(), r.dists[qi].tolist()], "gpu_l2": [x.ids[qi].tolist(), x.dists[qi].tolist()]}))
+                        sys.exit(1)
+                    n += 1
+    return n
+
+
 def main():
     orc.build()
     shapes = [(5, 3), (8, 5), (2, 10), (16, 10), (1, 1), (64, 10), (0, 4)]
@@ -58,7 +88,8 @@ def main():
     n += check_case(make_case(orc, 3000, 96, 24, 40, 48, seed=6, nq=16), shapes)                          # R > 32: two passes per row
     n += check_case(make_case(orc, 1500, 50, 10, 12, 24, seed=7, nq=16), shapes[:3],                      # D % 4 != 0, lazy deletes
                     deleted_ids=(1, 2, 3, 50, 51, 700, 1499))
-    print(json.dumps({"ok": True, "queries_checked": n}))
+    ng = check_golden()
+    print(json.dumps({"ok": True, "queries_checked": n, "golden_lists_checked": ng}))
 
 
 if __name__ == "__main__":
