@@ -12,3 +12,6 @@ timeout 300 python tests/tools/beam_c_check.py > gpurun_out/pending_beam_c.log 2
 timeout 600 python -m pytest tests/test_golden_config0.py tests/test_beam_c_gpu.py -q -m gpu --runxfail 2>&1 | tee gpurun_out/pending_golden_config0.log | tail -5
 # 3. build.cu single-point prune after the per-call scratch change (commit 0534d7e) — part of the regular suite
 timeout 900 python -m pytest tests/test_build_gpu.py -q -m gpu -x 2>&1 | tail -3
+# 4. BASELINE configs[1] parity on the 100k graph rebuilt with the compiled summation order (.cache/config2_adj_100000.npz; if absent:
+#    python tests/tools/build_config2_graph.py first, ~12 min of one CPU core, in the build container)
+ls .cache/config2_adj_100000.npz && timeout 1500 python tests/tools/parity_config2.py 10000 2000 > gpurun_out/pending_config2_parity.json 2> gpurun_out/pending_config2_parity.log; tail -c 1500 gpurun_out/pending_config2_parity.json
