@@ -12,6 +12,14 @@ sys.path.insert(0, str(ROOT / "oracle"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "pending_device: device check that has not had its first GPU run yet; collected last, so that "
+                                       "whatever it does to the CUDA context cannot reach the rest of the suite")
+
+
+def pytest_collection_modifyitems(config, items):
+    pending = [it for it in items if it.get_closest_marker("pending_device")]
+    if pending:
+        items[:] = [it for it in items if not it.get_closest_marker("pending_device")] + pending
 
 
 @pytest.fixture(scope="session")

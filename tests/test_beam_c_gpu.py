@@ -13,6 +13,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 @pytest.mark.gpu
+@pytest.mark.pending_device
 @pytest.mark.xfail(strict=False, reason="first device run pending (kernel written after the round's GPU budget was spent)")
 def test_beam_c_equals_the_oracle_restatement():
     p = subprocess.run([sys.executable, str(ROOT / "tests" / "tools" / "beam_c_check.py")], capture_output=True, text=True,

@@ -74,6 +74,7 @@ def test_oracle_rerank_and_variant_D(g0, orc, vectors):
 
 
 @pytest.mark.gpu
+@pytest.mark.pending_device
 @first_device_run_pending
 def test_gpu_pq_traversal_equals_the_reference(g0):
     """Variant A on the reference-built graph and the reference's own PQ codes, no vectors needed: the device list (reference-order
@@ -95,6 +96,7 @@ def test_gpu_pq_traversal_equals_the_reference(g0):
 
 
 @pytest.mark.gpu
+@pytest.mark.pending_device
 @first_device_run_pending
 def test_gpu_rerank_and_exact_search_equal_the_reference(g0, vectors):
     """With the vectors: PQ traversal + fused exact rerank returns the reference's rerank composition (identical top-10 ids,
