@@ -419,13 +419,15 @@ static inline float node_dist(const sctx_t *c, long id) {
     }
 }
 
-int orc_search_heap(const uint32_t *adj, int R, long N,
+/* deleted (may be NULL): is_deleted flags — lazily deleted nodes are never visited (cython_utils.pyx:100-109) and are filtered
+ * from the output (:120); the caller resolves a deleted start (:84-90). */
+static int search_heap_impl(const uint32_t *adj, int R, long N,
                     const uint8_t *codes, int M, const float *lut,
                     const float *vec, int D, const float *q, int flavor,
                     int dist_mode, int truncate_frontier,
                     int start, int L,
                     int32_t *out_ids, float *out_d, int32_t *out_hops, int32_t *out_nvisited,
-                    int32_t *trace, int trace_cap) {
+                    int32_t *trace, int trace_cap, const uint8_t *deleted) {
     sctx_t c = {adj, R, N, codes, M, lut, vec, D, q, flavor, dist_mode};
     uint8_t *visited = (uint8_t *)calloc((size_t)N, 1);
     heap_t cand, res;
@@ -442,6 +444,7 @@ int orc_search_heap(const uint32_t *adj, int R, long N,
 
     while (cand.n > 0) {
         ent_t cur = heap_pop(&cand);
+        if (deleted && deleted[cur.id]) continue;                   /* cython_utils.pyx:100-101 */
         float worst = -res.a[0].d;
         if (truncate_frontier) { /* D: `dist > worst and len(top_k) >= beam_width` (vamana_graph.py:734) */
             if (cur.d > worst && res.n >= L) break;
@@ -453,7 +456,7 @@ int orc_search_heap(const uint32_t *adj, int R, long N,
         for (int j = 0; j < R; ++j) {
             uint32_t nb = row[j];
             if ((long)nb >= N) continue; /* never true for a valid file; guards the byte map */
-            if (visited[nb]) continue;
+            if (visited[nb] || (deleted && deleted[nb])) continue;   /* :109 */
             visited[nb] = 1;
             float nd = node_dist(&c, nb);
             if (trace && nvis < trace_cap) trace[nvis] = (int32_t)nb;
@@ -467,9 +470,10 @@ int orc_search_heap(const uint32_t *adj, int R, long N,
         if (truncate_frontier) heap_truncate_nsmallest(&cand, L);
     }
     /* output order */
-    int n = res.n;
-    ent_t *tmp = (ent_t *)malloc(sizeof(ent_t) * (size_t)(n > 0 ? n : 1));
-    for (int i = 0; i < n; ++i) tmp[i] = (ent_t){-res.a[i].d, res.a[i].id};
+    int n = 0;
+    ent_t *tmp = (ent_t *)malloc(sizeof(ent_t) * (size_t)(res.n > 0 ? res.n : 1));
+    for (int i = 0; i < res.n; ++i)
+        if (!(deleted && deleted[res.a[i].id])) tmp[n++] = (ent_t){-res.a[i].d, res.a[i].id};   /* :120 */
     if (truncate_frontier) qsort(tmp, (size_t)n, sizeof(ent_t), ent_cmp); /* D: sorted([(dist, id)]) full tuple order (vamana_graph.py:758) */
     else stable_sort_by_dist(tmp, n);                                      /* A/B: stable by dist */
     for (int i = 0; i < n; ++i) { out_ids[i] = tmp[i].id; out_d[i] = tmp[i].d; }
@@ -478,6 +482,21 @@ int orc_search_heap(const uint32_t *adj, int R, long N,
     if (out_nvisited) *out_nvisited = nvis;
     heap_free(&cand); heap_free(&res); free(visited);
     return n;
+}
+
+int orc_search_heap(const uint32_t *adj, int R, long N, const uint8_t *codes, int M, const float *lut,
+                    const float *vec, int D, const float *q, int flavor, int dist_mode, int truncate_frontier,
+                    int start, int L, int32_t *out_ids, float *out_d, int32_t *out_hops, int32_t *out_nvisited,
+                    int32_t *trace, int trace_cap) {
+    return search_heap_impl(adj, R, N, codes, M, lut, vec, D, q, flavor, dist_mode, truncate_frontier, start, L, out_ids, out_d,
+                            out_hops, out_nvisited, trace, trace_cap, NULL);
+}
+int orc_search_heap_del(const uint32_t *adj, int R, long N, const uint8_t *codes, int M, const float *lut,
+                        const float *vec, int D, const float *q, int flavor, int dist_mode, int truncate_frontier,
+                        int start, int L, int32_t *out_ids, float *out_d, int32_t *out_hops, int32_t *out_nvisited,
+                        int32_t *trace, int trace_cap, const uint8_t *deleted) {
+    return search_heap_impl(adj, R, N, codes, M, lut, vec, D, q, flavor, dist_mode, truncate_frontier, start, L, out_ids, out_d,
+                            out_hops, out_nvisited, trace, trace_cap, deleted);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -494,13 +513,13 @@ typedef struct { float d; int32_t id; int expanded; } lent_t;
 
 static inline int key_lt(float da, int32_t ia, float db, int32_t ib) { return da < db || (da == db && ia < ib); }
 
-int orc_search_list(const uint32_t *adj, int R, long N,
+static int search_list_impl(const uint32_t *adj, int R, long N,
                     const uint8_t *codes, int M, const float *lut,
                     const float *vec, int D, const float *q, int flavor,
                     int dist_mode, int W, int strict_ties,
                     int start, int L,
                     int32_t *out_ids, float *out_d, int32_t *out_hops, int32_t *out_nvisited,
-                    int32_t *trace, int trace_cap) {
+                    int32_t *trace, int trace_cap, const uint8_t *deleted) {
     sctx_t c = {adj, R, N, codes, M, lut, vec, D, q, flavor, dist_mode};
     uint8_t *visited = (uint8_t *)calloc((size_t)N, 1);
     lent_t *lst = (lent_t *)malloc(sizeof(lent_t) * (size_t)(L + 1));
@@ -546,7 +565,7 @@ int orc_search_list(const uint32_t *adj, int R, long N,
             const uint32_t *row = adj + (size_t)cur_ids[s] * R;
             for (int j = 0; j < R; ++j) {
                 uint32_t nb = row[j];
-                if ((long)nb >= N || visited[nb]) continue;
+                if ((long)nb >= N || visited[nb] || (deleted && deleted[nb])) continue;
                 visited[nb] = 1;
                 float nd = node_dist(&c, nb);
                 if (trace && nvis < trace_cap) trace[nvis] = (int32_t)nb;
@@ -591,6 +610,21 @@ int orc_search_list(const uint32_t *adj, int R, long N,
     if (out_nvisited) *out_nvisited = nvis;
     free(visited); free(lst); free(ghost); free(nw);
     return n;
+}
+
+int orc_search_list(const uint32_t *adj, int R, long N, const uint8_t *codes, int M, const float *lut,
+                    const float *vec, int D, const float *q, int flavor, int dist_mode, int W, int strict_ties,
+                    int start, int L, int32_t *out_ids, float *out_d, int32_t *out_hops, int32_t *out_nvisited,
+                    int32_t *trace, int trace_cap) {
+    return search_list_impl(adj, R, N, codes, M, lut, vec, D, q, flavor, dist_mode, W, strict_ties, start, L, out_ids, out_d,
+                            out_hops, out_nvisited, trace, trace_cap, NULL);
+}
+int orc_search_list_del(const uint32_t *adj, int R, long N, const uint8_t *codes, int M, const float *lut,
+                        const float *vec, int D, const float *q, int flavor, int dist_mode, int W, int strict_ties,
+                        int start, int L, int32_t *out_ids, float *out_d, int32_t *out_hops, int32_t *out_nvisited,
+                        int32_t *trace, int trace_cap, const uint8_t *deleted) {
+    return search_list_impl(adj, R, N, codes, M, lut, vec, D, q, flavor, dist_mode, W, strict_ties, start, L, out_ids, out_d,
+                            out_hops, out_nvisited, trace, trace_cap, deleted);
 }
 
 /* Rerank of a candidate list by exact squared L2: the composition the reference never writes as one

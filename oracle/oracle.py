@@ -108,7 +108,7 @@ def pq_sdc(codebook, c1, c2):
     return float(lib().orc_pq_sdc(_p(codebook), _p(c1), _p(c2), C.c_int(M), C.c_int(ds)))
 
 
-def _search(fn_name, adj, codes, lut_, vec, q, flavor, dist_mode, extra, start, L, trace):
+def _search(fn_name, adj, codes, lut_, vec, q, flavor, dist_mode, extra, start, L, trace, deleted=None):
     adj = np.ascontiguousarray(adj, np.uint32)
     N, R = adj.shape
     M = 0
@@ -123,11 +123,15 @@ def _search(fn_name, adj, codes, lut_, vec, q, flavor, dist_mode, extra, start, 
     ids = np.full(L + 1, -1, np.int32); d = np.full(L + 1, np.inf, np.float32)
     hops = C.c_int32(0); nvis = C.c_int32(0)
     tr = np.full(trace, -1, np.int32) if trace else None
+    tail = ()
+    if deleted is not None:                     # is_deleted flags (cython_utils.pyx:100-109, 120); the caller resolves a deleted start
+        deleted = np.ascontiguousarray(deleted, np.uint8)
+        fn_name += "_del"; tail = (_p(deleted),)
     n = getattr(lib(), fn_name)(
         _p(adj), C.c_int(R), C.c_long(N), _p(codes), C.c_int(M), _p(lut_),
         _p(vec), C.c_int(D), _p(q), C.c_int(flavor), C.c_int(dist_mode), *extra,
         C.c_int(int(start)), C.c_int(L), _p(ids), _p(d), C.byref(hops), C.byref(nvis),
-        _p(tr), C.c_int(trace))
+        _p(tr), C.c_int(trace), *tail)
     res = {"ids": ids[:n].copy(), "dists": d[:n].copy(), "hops": hops.value, "visited": nvis.value}
     if trace:
         res["trace"] = tr[:min(trace, nvis.value)].copy()
@@ -135,17 +139,17 @@ def _search(fn_name, adj, codes, lut_, vec, q, flavor, dist_mode, extra, start, 
 
 
 def search_heap(adj, start, L, *, codes=None, lut_=None, vec=None, q=None, dist_mode=DIST_ADC_SEQ,
-                flavor=FLAVOR_DOUBLE, truncate_frontier=False, trace=0):
+                flavor=FLAVOR_DOUBLE, truncate_frontier=False, trace=0, deleted=None):
     """Literal two-heap form of variants A/B/D (cython_utils.pyx:72-122, vamana_graph.py:607-640,719-760)."""
     return _search("orc_search_heap", adj, codes, lut_, vec, q, flavor, dist_mode,
-                   (C.c_int(int(truncate_frontier)),), start, L, trace)
+                   (C.c_int(int(truncate_frontier)),), start, L, trace, deleted)
 
 
 def search_list(adj, start, L, *, codes=None, lut_=None, vec=None, q=None, dist_mode=DIST_ADC_SEQ,
-                flavor=FLAVOR_WARP, W=1, strict_ties=True, trace=0):
+                flavor=FLAVOR_WARP, W=1, strict_ties=True, trace=0, deleted=None):
     """Sorted-L-list form with W expansions per step: the exact statement of the GPU kernel."""
     return _search("orc_search_list", adj, codes, lut_, vec, q, flavor, dist_mode,
-                   (C.c_int(W), C.c_int(int(strict_ties))), start, L, trace)
+                   (C.c_int(W), C.c_int(int(strict_ties))), start, L, trace, deleted)
 
 
 def beam_c(adj, start, beam_width, k, *, codes=None, lut_=None, vec=None, q=None, dist_mode=DIST_ADC_SEQ,

@@ -10,6 +10,7 @@ import pytest
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
 import ref_loader  # noqa: E402
+from conftest import canon  # noqa: E402
 
 pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref not built")
 
@@ -253,3 +254,31 @@ def test_reference_python_prune_keeps_the_R_nearest(world, ref):
             cu.robust_prune_cython(g, p, cands, alpha, w["R"], vg.compute_distance)
             d = sorted((cu.l2_distance_fast_cython(w["X"][p], w["X"][c]), c) for c in cands)
             assert g.nodes[p].neighbors == set(c for _, c in d[:w["R"]]), (alpha, p)
+
+
+def test_variant_A_with_lazily_deleted_nodes(world, orc, ref):
+    """greedy_search_cython on a graph with is_deleted nodes (cython_utils.pyx:84-90, 100-101, 109, 120; §8 a14): deleted nodes are
+    never visited and never returned, a deleted start is replaced by the first live node.  Heap form == the reference's list in its
+    own order; list form (what the GPU runs with its delete mask) == heap form, including hop and visited counts."""
+    w = world
+    vg, cu = ref["vamana_graph"], ref["cython_utils"]
+    g, adj = _ref_graph(w, vg)
+    rng = np.random.default_rng(9)
+    dead = np.zeros(w["N"], np.uint8)
+    dead[rng.choice(w["N"], 60, replace=False)] = 1
+    dead[3] = 1                                                          # the start itself
+    for i in np.flatnonzero(dead):
+        g.nodes[int(i)].is_deleted = True
+    start = int(np.flatnonzero(dead == 0)[0])                            # :84-90
+    for use_pq in (True, False):
+        g.use_pq_for_search = use_pq
+        for q in w["Q"]:
+            g._distance_table_cache.clear()
+            rid = cu.greedy_search_cython(g, 3, q, 20, vg.compute_query_distance)
+            kw = (dict(codes=w["codes"], lut_=orc.lut(w["cb"], q), dist_mode=orc.DIST_ADC_SEQ) if use_pq else
+                  dict(vec=w["X"], q=q, dist_mode=orc.DIST_L2_SQ, flavor=orc.FLAVOR_REFCC))
+            h = orc.search_heap(adj, start, 20, deleted=dead, **kw)
+            assert list(rid) == [int(x) for x in h["ids"]] and not dead[h["ids"]].any()
+            l = orc.search_list(adj, start, 20, W=1, strict_ties=True, deleted=dead, **kw)
+            a, b = canon(h["ids"], h["dists"]), (l["ids"], l["dists"])
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and (h["hops"], h["visited"]) == (l["hops"], l["visited"])
