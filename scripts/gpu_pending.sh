@@ -8,8 +8,8 @@ mkdir -p gpurun_out
 # 1. variant C with the reference's own semantics (csrc/beam_c.cu) == oracle.c:orc_beam_c, under compute-sanitizer first
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tests/tools/beam_c_check.py > gpurun_out/pending_beam_c_memcheck.log 2>&1; echo "beam_c memcheck rc=$?"
 timeout 300 python tests/tools/beam_c_check.py > gpurun_out/pending_beam_c.log 2>&1; echo "beam_c rc=$?"; tail -1 gpurun_out/pending_beam_c.log
-# 2. BASELINE configs[0] fixture from the REAL reference: device results against the reference's own outputs
-timeout 600 python -m pytest tests/test_golden_config0.py tests/test_beam_c_gpu.py -q -m gpu --runxfail 2>&1 | tee gpurun_out/pending_golden_config0.log | tail -5
+# 2. every device check still carrying the pending_device marker (configs[0] fixture against the REAL reference outputs, beam_c, delete-mask parity), with xfail off
+timeout 900 python -m pytest tests -q -m "gpu and pending_device" --runxfail 2>&1 | tee gpurun_out/pending_golden_config0.log | tail -5
 # 3. build.cu single-point prune after the per-call scratch change (commit 0534d7e) — part of the regular suite
 timeout 900 python -m pytest tests/test_build_gpu.py -q -m gpu -x 2>&1 | tail -3
 # 4. BASELINE configs[1] parity on the 100k graph rebuilt with the compiled summation order (.cache/config2_adj_100000.npz; if absent:
