@@ -1,0 +1,72 @@
+"""CPU: the TEXT of csrc/beam_c.cu's kernel, executed without a GPU by a lockstep warp emulator (tests/tools/warp_emul.h: one OS thread
+per lane, every warp collective an exchange between two barriers), against the oracle's literal restatement of the reference's
+beam_search_with_pq (oracle.c:orc_beam_c, pinned to the real reference).  The kernel body and the device helpers it uses are cut out
+of the .cu / .cuh files at test time, so what runs here is what nvcc compiles; what this cannot show is anything that depends on
+the GPU's memory system or scheduler — the device run (tests/test_beam_c_gpu.py) stays pending."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, canon, make_case
+
+TOOLS = ROOT / "tests" / "tools"
+BUILD = TOOLS / "build"
+
+
+@pytest.fixture(scope="module")
+def emul():
+    cm = (ROOT / "diskrag_b200" / "csrc" / "common.cuh").read_text()
+    bc = (ROOT / "diskrag_b200" / "csrc" / "beam_c.cu").read_text()
+    helpers = cm[cm.index("#define DR_FULL"):cm.index("// Canonical cosine DISTANCE")]       # f2ord ... warp_l2sq
+    kernel = bc[bc.index("struct BeamCArgs"):bc.index("// number of resident CTAs")]          # args, ADC helper, the kernel
+    BUILD.mkdir(exist_ok=True)
+    (BUILD / "beam_c_kernel.inc").write_text(helpers + "\n" + kernel)
+    so = BUILD / "beam_c_emul.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-I", str(BUILD), "-I", str(TOOLS),
+                           str(TOOLS / "beam_c_emul_main.cpp"), "-o", str(so)])
+    return C.CDLL(str(so))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def run_emulated(emul, c, Q, luts, k, bw, dist, dead, sqrt_out):
+    B = Q.shape[0]
+    ids = np.empty((B, k), np.int32); dd = np.empty((B, k), np.float32); hops = np.empty(B, np.int32); vis = np.empty(B, np.int32)
+    rc = emul.emul_beam_c(_p(c["X"]), _p(c["adj"]), _p(c["codes"]), _p(dead), _p(Q), _p(luts), C.c_longlong(c["N"]), C.c_int(c["D"]),
+                          C.c_int(c["R"]), C.c_int(c["M"]), C.c_longlong(B), C.c_int(k), C.c_int(bw), C.c_int(0 if dist == "pq" else 1),
+                          C.c_int(int(sqrt_out)), C.c_uint32(c["medoid"]), _p(ids), _p(dd), _p(hops), _p(vis))
+    assert rc == 0
+    return ids, dd, hops, vis
+
+
+@pytest.mark.parametrize("shape", [(1500, 32, 4, 8, 16, 1, 40), (1200, 96, 12, 40, 48, 2, 0), (900, 30, 5, 12, 24, 5, 0)],
+                         ids=["ties", "R40_two_passes", "D_not_multiple_of_4"])
+def test_kernel_text_equals_the_oracle(emul, orc, shape):
+    N, D, M, R, Lb, seed, dup = shape
+    c = make_case(orc, N, D, M, R, Lb, seed, nq=6, dup=dup)
+    c["X"] = np.ascontiguousarray(c["X"], np.float32); c["adj"] = np.ascontiguousarray(c["adj"], np.uint32)
+    c["codes"] = np.ascontiguousarray(c["codes"], np.uint8)
+    Q = np.ascontiguousarray(c["Q"], np.float32)
+    luts = np.ascontiguousarray(np.stack([orc.lut(c["codebook"], q) for q in Q]), np.float32)
+    rng = np.random.default_rng(seed)
+    dead = np.zeros(N, np.uint8); dead[rng.choice(N, N // 20, replace=False)] = 1; dead[c["medoid"]] = 0
+    for deleted in (None, dead):
+        for bw, k in [(5, 3), (2, 10), (16, 10), (1, 1), (0, 4)]:
+            for dist in ("pq", "exact"):
+                ids, dd, hops, vis = run_emulated(emul, c, Q, luts, k, bw, dist, deleted, sqrt_out=(dist == "pq"))
+                for qi, q in enumerate(Q):
+                    if dist == "pq":
+                        o = orc.beam_c(c["adj"], c["medoid"], bw, k, codes=c["codes"], lut_=luts[qi], dist_mode=orc.DIST_ADC_SEQ,
+                                       deleted=deleted, sqrt_out=True)
+                    else:
+                        o = orc.beam_c(c["adj"], c["medoid"], bw, k, vec=c["X"], q=q, dist_mode=orc.DIST_L2_SQ, flavor=orc.FLAVOR_WARP,
+                                       deleted=deleted, sqrt_out=False)
+                    a = canon(o["ids"], o["dists"]); b = canon(ids[qi], dd[qi])
+                    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (bw, k, dist, qi)     # ids, distances: bits
+                    assert (int(hops[qi]), int(vis[qi])) == (o["hops"], o["visited"]), (bw, k, dist, qi)
+                    assert (ids[qi, len(o["ids"]):] == -1).all()
