@@ -70,3 +70,28 @@ def test_kernel_text_equals_the_oracle(emul, orc, shape):
                     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (bw, k, dist, qi)     # ids, distances: bits
                     assert (int(hops[qi]), int(vis[qi])) == (o["hops"], o["visited"]), (bw, k, dist, qi)
                     assert (ids[qi, len(o["ids"]):] == -1).all()
+
+
+def test_kernel_text_equals_the_real_reference_outputs(emul, golden, orc):
+    """The same kernel text against what the REAL reference's beam_search_with_pq returned (tests/golden/ref_variants_ce.npz, made by
+    tests/golden/make_golden_variants.py): PQ lists bit-equal (ids, sqrt'ed ADC distances), live and with lazily deleted nodes; exact
+    lists: same ids, distances within 1e-4 relative (the device sums in warp order, the reference in its compiled order)."""
+    g = golden
+    v = np.load(ROOT / "tests" / "golden" / "ref_variants_ce.npz")
+    Q = np.ascontiguousarray(g["Q"][:int(v["nq"])], np.float32)
+    c = dict(X=np.ascontiguousarray(g["vec"], np.float32), adj=np.ascontiguousarray(g["adj"], np.uint32),
+             codes=np.ascontiguousarray(g["codes"], np.uint8), N=g["N"], D=g["D"], R=g["R"], M=g["M"], medoid=g["medoid"])
+    luts = np.ascontiguousarray(np.stack([orc.lut(g["codebook"], q) for q in Q]), np.float32)
+    for tag, dead in (("live", None), ("del", np.ascontiguousarray(v["deleted"]))):
+        for bw, k in v["shapes_c"]:
+            bw, k = int(bw), int(k)
+            ids, dd, _, _ = run_emulated(emul, c, Q, luts, k, bw, "pq", dead, sqrt_out=True)
+            xi, xd, _, _ = run_emulated(emul, c, Q, luts, k, bw, "exact", dead, sqrt_out=True)
+            for qi in range(len(Q)):
+                a = canon(v[f"exp_C_{tag}_pq_bw{bw}_k{k}_ids"][qi], v[f"exp_C_{tag}_pq_bw{bw}_k{k}_d"][qi].astype(np.float32))
+                b = canon(ids[qi], dd[qi])
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (tag, bw, k, qi)
+                e_ids = v[f"exp_C_{tag}_l2_bw{bw}_k{k}_ids"][qi]; e_d = v[f"exp_C_{tag}_l2_bw{bw}_k{k}_d"][qi]
+                m = int((e_ids >= 0).sum())
+                assert set(xi[qi][xi[qi] >= 0].tolist()) == set(e_ids[:m].tolist()), (tag, bw, k, qi)
+                np.testing.assert_allclose(np.sort(xd[qi][:m]), np.sort(e_d[:m]), rtol=1e-4)
