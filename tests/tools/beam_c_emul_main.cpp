@@ -33,5 +33,8 @@ extern "C" int emul_beam_c(const float *vec, const uint32_t *adj, const uint8_t 
     for (int i = 0; i < 32; ++i) pthread_join(th[i], nullptr);
     pthread_barrier_destroy(&emul_bar);
     free(a.bitmap);
+    // the kernel must stay inside the dynamic shared memory launch_beam_c asks for (same expression as in beam_c.cu)
+    for (size_t i = smem; i < sizeof(beamc_smem); ++i)
+        if (beamc_smem[i] != 0xCD) return 3;
     return 0;
 }
