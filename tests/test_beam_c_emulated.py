@@ -95,3 +95,35 @@ def test_kernel_text_equals_the_real_reference_outputs(emul, golden, orc):
                 m = int((e_ids >= 0).sum())
                 assert set(xi[qi][xi[qi] >= 0].tolist()) == set(e_ids[:m].tolist()), (tag, bw, k, qi)
                 np.testing.assert_allclose(np.sort(xd[qi][:m]), np.sort(e_d[:m]), rtol=1e-4)
+
+
+def test_kernel_text_on_adversarial_rows(emul, orc):
+    """Rows full of repeated ids (inside one 32-wide pass and across the two passes of an R = 40 row), self loops, 0-padding, two-byte
+    codes (massive exact ADC ties), duplicated points: first-occurrence claiming (match_any + atomicOr) and the tie rules of the
+    eviction must follow the reference's sequential scan exactly."""
+    rng = np.random.default_rng(77)
+    N, D, M, R = 96, 8, 2, 40
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    X[N // 2:] = X[:N // 2]                                             # every point has an exact duplicate
+    cb = rng.standard_normal((M, 256, D // M)).astype(np.float32)
+    codes = rng.integers(0, 3, (N, M)).astype(np.uint8)                 # 9 distinct codes: ADC ties everywhere
+    adj = rng.integers(0, N, (N, R)).astype(np.uint32)
+    adj[:, 5:9] = adj[:, 4:5]                                           # repeats inside the first pass
+    adj[:, 33:36] = adj[:, 2:3]                                         # repeats across passes
+    adj[np.arange(N), 10] = np.arange(N)                                # self loops
+    adj[::3, 20:] = 0                                                   # 0-padded tails
+    Q = rng.standard_normal((8, D)).astype(np.float32)
+    c = dict(X=X, adj=adj, codes=codes, N=N, D=D, R=R, M=M, medoid=7)
+    luts = np.ascontiguousarray(np.stack([orc.lut(cb, q) for q in Q]), np.float32)
+    dead = np.zeros(N, np.uint8); dead[[1, 2, 30, 31, 90]] = 1
+    for deleted in (None, dead):
+        for bw, k in [(1, 1), (3, 2), (5, 3), (8, 12), (40, 20), (0, 2)]:
+            for dist in ("pq", "exact"):
+                ids, dd, hops, vis = run_emulated(emul, c, Q, luts, k, bw, dist, deleted, sqrt_out=False)
+                for qi, q in enumerate(Q):
+                    kw = (dict(codes=codes, lut_=luts[qi], dist_mode=orc.DIST_ADC_SEQ) if dist == "pq" else
+                          dict(vec=X, q=q, dist_mode=orc.DIST_L2_SQ, flavor=orc.FLAVOR_WARP))
+                    o = orc.beam_c(adj, 7, bw, k, deleted=deleted, sqrt_out=False, **kw)
+                    a = canon(o["ids"], o["dists"]); b = canon(ids[qi], dd[qi])
+                    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (bw, k, dist, qi, a, b)
+                    assert (int(hops[qi]), int(vis[qi])) == (o["hops"], o["visited"]), (bw, k, dist, qi)
