@@ -2,7 +2,7 @@
 per lane, every warp collective an exchange between two barriers), against the oracle's literal restatement of the reference's
 beam_search_with_pq (oracle.c:orc_beam_c, pinned to the real reference).  The kernel body and the device helpers it uses are cut out
 of the .cu / .cuh files at test time, so what runs here is what nvcc compiles; what this cannot show is anything that depends on
-the GPU's memory system or scheduler — the device run (tests/test_beam_c_gpu.py) stays pending."""
+the GPU's memory system or scheduler; the device run is tests/test_beam_c_gpu.py."""
 import ctypes as C
 import subprocess
 from pathlib import Path

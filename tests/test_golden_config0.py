@@ -22,7 +22,6 @@ pytestmark = pytest.mark.skipif(not FIX.exists(), reason="tests/golden/ref_confi
 # The fixture was generated after this round's GPU budget was spent: the two GPU checks below have not run on a device yet.  The
 # CPU half (oracle == reference on this fixture) is green, and the GPU == oracle on the same modes elsewhere in the suite; until the
 # first device run confirms it they must not be able to turn the shared suite red.  Drop the marker once they show up as XPASS.
-first_device_run_pending = pytest.mark.xfail(strict=False, reason="not yet run on a GPU (fixture generated after the round's GPU budget was spent)")
 
 
 @pytest.fixture(scope="module")
@@ -74,8 +73,6 @@ def test_oracle_rerank_and_variant_D(g0, orc, vectors):
 
 
 @pytest.mark.gpu
-@pytest.mark.pending_device
-@first_device_run_pending
 def test_gpu_pq_traversal_equals_the_reference(g0):
     """Variant A on the reference-built graph and the reference's own PQ codes, no vectors needed: the device list (reference-order
     mode: f32 table, sequential ADC, W = 1, strict ties) holds exactly the reference's ids and ADC distances."""
@@ -96,8 +93,6 @@ def test_gpu_pq_traversal_equals_the_reference(g0):
 
 
 @pytest.mark.gpu
-@pytest.mark.pending_device
-@first_device_run_pending
 def test_gpu_rerank_and_exact_search_equal_the_reference(g0, vectors):
     """With the vectors: PQ traversal + fused exact rerank returns the reference's rerank composition (identical top-10 ids,
     distances within 1e-4 relative), variant D (exact traversal, L = 64) the reference's beam_search_from_disk top-10; the

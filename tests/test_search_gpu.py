@@ -324,8 +324,6 @@ def test_concurrent_callers_on_one_handle(golden, gidx):
 
 
 @pytest.mark.gpu
-@pytest.mark.pending_device
-@pytest.mark.xfail(strict=False, reason="comparison written after the round's GPU budget was spent (the delete mask itself is device-tested in test_build_gpu.py)")
 def test_lazy_delete_mask_equals_the_oracle(orc):
     """§8 a14: with a delete mask (dr_index_set_deleted) the device search equals the oracle's restatement of the reference's
     is_deleted handling (cython_utils.pyx:100-109, pinned live in test_oracle_vs_reference.py::test_variant_A_with_lazily_deleted_nodes):

@@ -22,16 +22,17 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
 
 
-def main():
+def run(nq_exact=10_000, nq_oracle=2_000):
     import oracle as O
     from diskrag_b200.engine import GpuIndex
     from diskrag_b200.io.diskann_persist import DiskANNPersist
     from diskrag_b200.pq.fast_pq import DiskANNPQ
     from diskrag_b200.synth import synth_numpy
     O.build()
-    nq_exact = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000
-    nq_oracle = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000          # queries the CPU oracle re-runs per variant
-    cached = sorted((ROOT / ".cache").glob("config2_adj_*.npz"), key=lambda p: int(p.stem.split("_")[-1]))
+    # the committed graph: 100k x 1536 built by the restatement of the reference's builder in its COMPILED summation order
+    # (profiles/r01m_config2_graph.json: adj_sha256 6d78fd48...; the same restatement reproduces the REAL reference's 10k build
+    # row for row, profiles/r01l_build_config0_check.json)
+    cached = sorted((ROOT / "tests" / "golden").glob("config1_adj_*.npz"), key=lambda p: int(p.stem.split("_")[-1]))
     if cached:
         z = np.load(cached[-1])
         adj, med, N, D, R, seed = z["adj"], int(z["medoid"]), int(z["N"]), int(z["D"]), int(z["R"]), int(z["seed"])
@@ -112,11 +113,32 @@ def main():
             "gpu_batch_seconds": round(tT, 3),
             "top_k_ids_and_distances_bit_equal": f"{int(np.sum(np.all(oi == rT.ids[:nq_oracle], axis=1) & np.all(od == rT.dists[:nq_oracle], axis=1)))}/{nq_oracle}",
             "hops_visited_equal": f"{int(np.sum((oh == rT.hops[:nq_oracle]) & (ov == rT.visited[:nq_oracle])))}/{nq_oracle}"}
+        # ---- how far the bench mode (u8 table built on tensor cores, W = 8) is from the reference's own answer ----------
+        # reference answer = variant A (cython_utils.pyx:72-122, f32 table, sequential ADC, W = 1) + the exact rerank of
+        # search_engine.py:374-379.  The GPU's variant A is bit-equal to the oracle's (checked above), so the whole batch is
+        # compared on the device results; the oracle re-runs the composition on the first nq_oracle queries.
+        rAr = idx.search(Q, k=k, L=L, W=1, dist="pq", adc_order="seq", rerank=True)
+        rB = idx.search(Q, k=k, L=L, W=8, dist="pq", adc_order="tree", rerank=True, lut_fmt="u8tc", prefetch=5)
+        set_eq = lambda a, b: np.array([set(a[i].tolist()) == set(b[i].tolist()) for i in range(a.shape[0])])
+        eqB = set_eq(rB.ids, rAr.ids); eqT = set_eq(rT.ids, rAr.ids)
+        okR = 0
+        for qi in range(nq_oracle):
+            h = O.search_heap(adj, med, L, codes=codes, lut_=O.lut(cb, Q[qi]), dist_mode=O.DIST_ADC_SEQ)
+            ri, _ = O.rerank(X, Q[qi], h["ids"], k, flavor=O.FLAVOR_NUMPY)
+            okR += set(ri.tolist()) == set(rAr.ids[qi].tolist())
+        out["bench_mode_vs_reference_answer"] = {
+            "reference_answer": "variant A (f32 table, sequential ADC, W=1, L=100) + exact rerank, top-10 id SET",
+            "gpu_variantA_rerank_sets_equal_to_oracle_composition": f"{okR}/{nq_oracle}",
+            "u8tc_W8_top10_sets_equal": f"{int(eqB.sum())}/{len(eqB)}", "u8tc_W8_fraction": float(eqB.mean()),
+            "u8_exact_W8_top10_sets_equal": f"{int(eqT.sum())}/{len(eqT)}", "u8_exact_W8_fraction": float(eqT.mean()),
+            "mean_top10_overlap_u8tc_W8": float(np.mean([len(set(rB.ids[i].tolist()) & set(rAr.ids[i].tolist())) / k for i in range(len(eqB))]))}
         gt = O.ground_truth(X, Q[:500], k)
         rec = lambda ids: float(np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / k for i in range(500)]))
-        out["recall_at_10"] = {"variant_D": rec(rD.ids), "variant_A_no_rerank": rec(rA.ids), "throughput": rec(rT.ids)}
-    print(json.dumps(out))
+        out["recall_at_10"] = {"variant_D": rec(rD.ids), "variant_A_no_rerank": rec(rA.ids), "variant_A_rerank": rec(rAr.ids),
+                               "throughput_u8": rec(rT.ids), "bench_mode_u8tc": rec(rB.ids)}
+    out["N"] = N
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 10_000, int(sys.argv[2]) if len(sys.argv) > 2 else 2_000)))
