@@ -15,17 +15,28 @@ def pytest_configure(config):
 
 
 def _device_count():
+    from diskrag_b200._lib import device_count
+    return int(device_count())
+
+
+def _box_has_nvidia_gpu():
+    import shutil
+    import subprocess
+    if not shutil.which("nvidia-smi"):
+        return False
     try:
-        from diskrag_b200._lib import lib
-        return int(lib().dr_device_count())
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout.count("GPU ") > 0
     except Exception:
-        return 0
+        return False
 
 
 def pytest_collection_modifyitems(config, items):
     # a box without CUDA skips the device tests instead of erroring in them (the product itself has no CPU fallback:
     # every compute entry point fails loudly there, which tests/test_abi.py checks)
     if any(it.get_closest_marker("gpu") for it in items) and _device_count() == 0:
+        # never skip silently on a GPU box: if the driver sees a GPU and the library does not, that is a failure of the product
+        if _box_has_nvidia_gpu():
+            raise pytest.UsageError("nvidia-smi lists a GPU but libdiskrag_b200.so reports no CUDA device: refusing to skip the device tests")
         skip = pytest.mark.skip(reason="no CUDA device on this box (device tests run with -m gpu on the B200 box)")
         for it in items:
             if it.get_closest_marker("gpu"):
