@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--hash-cap", type=int, default=0, help="force the visited-table size (occupancy experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-points", action="store_true", help="skip the other operating points / parity-mode legs (kernel A/B runs)")
     ap.add_argument("--cuda-profile", action="store_true", help="wrap one extra step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
 
@@ -306,7 +307,7 @@ def run_ours(a):
 
     # ---- the recall / throughput trade-off around the named configuration (context for "QPS at recall >= 0.95"; 1 GPU only)
     points = None
-    if world == 1:
+    if world == 1 and not a.no_points:
         points = []
         for Lp in (50, 64, 80):
             pp = engine.make_params(k=k, L=Lp, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut,

@@ -23,7 +23,7 @@ class SearchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("L", C.c_int32), ("W", C.c_int32), ("dist", C.c_int32),
                 ("adc_order", C.c_int32), ("rerank", C.c_int32), ("sqrt_out", C.c_int32),
                 ("hash_cap", C.c_int32), ("chunk", C.c_int32), ("threads", C.c_int32), ("lut_fmt", C.c_int32),
-                ("prefetch", C.c_int32)]
+                ("prefetch", C.c_int32), ("start_plus1", C.c_int32), ("ignore_deleted", C.c_int32)]
 
 
 _vp, _i32, _i64, _u64, _f32, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
@@ -43,7 +43,7 @@ SIGNATURES = {
     "dr_index_export_records": (C.c_int, [_vp, _vp]),
     "dr_search_batch": (C.c_int, [_vp, _vp, _i64, _PP(SearchParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "dr_search_batch_dev": (C.c_int, [_vp, _vp, _i64, _PP(SearchParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
-    "dr_beam_search_c": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "dr_beam_search_c": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
     "dr_launch_count": (_i64, []),
     "dr_search_kernel_timing": (C.c_int, [_vp, C.c_int, _PP(_dbl), _PP(_i64)]),
     "dr_lut_build": (C.c_int, [_vp, _vp, _i64, _vp]),
@@ -67,6 +67,10 @@ SIGNATURES = {
     "dr_robust_prune": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _i32, _vp, _PP(_i32), C.c_int]),
     "dr_index_set_deleted": (C.c_int, [_vp, _vp]),
     "dr_index_set_start": (C.c_int, [_vp, _i64]),
+    "dr_index_append": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "dr_index_patch_rows": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "dr_index_patch_vectors": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "dr_index_set_deleted_rows": (C.c_int, [_vp, _vp, _i64, _vp]),
     "dr_topk_merge_dev": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, C.c_int, _vp]),
 }
 

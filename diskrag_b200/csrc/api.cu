@@ -97,6 +97,52 @@ int launch_interleave(const float *d_vec, const uint32_t *d_adj, int64_t N, int 
     return 0;
 }
 
+// ---- dynamic updates: O(rows touched) -------------------------------------------------------------------------
+__global__ void scatter_rows_kernel(const long long *__restrict__ rows, long long n, int words, const uint32_t *__restrict__ src,
+                                    uint32_t *__restrict__ dst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * words) return;
+    const long long i = t / words;
+    const int j = (int)(t - i * words);
+    dst[(size_t)rows[i] * words + j] = src[t];
+}
+__global__ void scatter_bytes_kernel(const long long *__restrict__ rows, long long n, int width, const uint8_t *__restrict__ src,
+                                     uint8_t *__restrict__ dst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const long long i = t / width;
+    const int j = (int)(t - i * width);
+    dst[(size_t)rows[i] * width + j] = src[t];
+}
+static int scatter_rows(const int64_t *rows_host, int64_t n, int words, const void *src_host, void *dst_dev, int64_t N, bool bytes) {
+    if (n == 0) return 0;
+    for (int64_t i = 0; i < n; ++i)
+        DR_CHECK(rows_host[i] >= 0 && rows_host[i] < N, "dr_index_patch: row %lld out of range (N=%lld)", (long long)rows_host[i], (long long)N);
+    DevBuf r, s;
+    const size_t payload = (size_t)n * words * (bytes ? 1 : 4);
+    if (r.alloc((size_t)n * 8) || s.alloc(payload)) return 1;
+    DR_CUDA(cudaMemcpy(r.p, rows_host, (size_t)n * 8, cudaMemcpyHostToDevice));
+    DR_CUDA(cudaMemcpy(s.p, src_host, payload, cudaMemcpyHostToDevice));
+    const long long tot = (long long)n * words;
+    if (bytes) scatter_bytes_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(r.as<long long>(), n, words, s.as<uint8_t>(), (uint8_t *)dst_dev);
+    else scatter_rows_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(r.as<long long>(), n, words, s.as<uint32_t>(), (uint32_t *)dst_dev);
+    DR_LAUNCHED();
+    DR_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+template <class T>
+static int grow_array(T **p, size_t old_elems, size_t new_elems, int fill_byte = -1) {
+    if (!*p) return 0;
+    T *q = nullptr;
+    DR_CUDA(cudaMalloc(&q, new_elems * sizeof(T)));
+    DR_CUDA(cudaMemcpy(q, *p, old_elems * sizeof(T), cudaMemcpyDeviceToDevice));
+    if (fill_byte >= 0) DR_CUDA(cudaMemset(q + old_elems, fill_byte, (new_elems - old_elems) * sizeof(T)));
+    cudaFree(*p);
+    *p = q;
+    return 0;
+}
+
 extern "C" {
 
 int dr_abi_version(void) { return DR_ABI_VERSION; }
@@ -131,8 +177,10 @@ static int index_common(dr_index *h, int64_t N, int D, int R, int M, int64_t med
     DR_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sms = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->cap = N;
     DR_CUDA(cudaEventCreate(&h->ev0));
     DR_CUDA(cudaEventCreate(&h->ev1));
+    DR_CUDA(cudaEventCreateWithFlags(&h->ev_scratch, cudaEventDisableTiming));
     return 0;
 }
 
@@ -228,6 +276,7 @@ int dr_index_destroy(dr_index *h) {
     }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_scratch) cudaEventDestroy(h->ev_scratch);
     delete h;
     return 0;
 }
@@ -364,7 +413,7 @@ int dr_search_batch(dr_index *h, const float *Q, int64_t B, const dr_search_para
 }
 
 int dr_beam_search_c(dr_index *h, const float *Q, int64_t B, int32_t k, int32_t beam_width, int32_t dist, int32_t sqrt_out,
-                     int32_t *out_ids, float *out_dist, int32_t *out_hops, int32_t *out_visited) {
+                     int64_t start, int32_t *out_ids, float *out_dist, int32_t *out_hops, int32_t *out_visited) {
     DR_CHECK(h && out_ids && (Q || B == 0), "dr_beam_search_c: null argument");
     DR_CHECK(k >= 1 && k <= 1024, "dr_beam_search_c: k must be in 1..1024");
     DR_LOCK(h);
@@ -385,7 +434,7 @@ int dr_beam_search_c(dr_index *h, const float *Q, int64_t B, int32_t k, int32_t 
         DR_CUDA(cudaMemcpyAsync(q.p, Q + (size_t)c0 * h->D, (size_t)nb * h->D * 4, cudaMemcpyHostToDevice, s));
         if (pq && launch_lut_build(h->d_codebook, q.as<float>(), nb, h->D, h->M, lut.as<float>(), s)) return 1;
         if (launch_beam_c(h, q.as<float>(), nb, k, beam_width, dist, sqrt_out, pq ? lut.as<float>() : nullptr, bm.as<uint32_t>(),
-                          ids.as<int32_t>(), dd.as<float>(), hh.as<int32_t>(), vv.as<int32_t>(), s)) return 1;
+                          ids.as<int32_t>(), dd.as<float>(), hh.as<int32_t>(), vv.as<int32_t>(), s, start)) return 1;
         DR_CUDA(cudaMemcpyAsync(out_ids + (size_t)c0 * k, ids.p, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, s));
         if (out_dist) DR_CUDA(cudaMemcpyAsync(out_dist + (size_t)c0 * k, dd.p, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, s));
         if (out_hops) DR_CUDA(cudaMemcpyAsync(out_hops + c0, hh.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
@@ -616,9 +665,68 @@ int dr_index_set_deleted(dr_index *h, const uint8_t *mask) {
     DR_LOCK(h);
     DR_CUDA(cudaSetDevice(h->device));
     if (!mask) { if (h->d_deleted) cudaFree(h->d_deleted); h->d_deleted = nullptr; return 0; }
-    if (!h->d_deleted) DR_CUDA(cudaMalloc(&h->d_deleted, (size_t)h->N));
+    if (!h->d_deleted) DR_CUDA(cudaMalloc(&h->d_deleted, (size_t)(h->cap > h->N ? h->cap : h->N)));
     DR_CUDA(cudaMemcpy(h->d_deleted, mask, (size_t)h->N, cudaMemcpyHostToDevice));
     return 0;
+}
+
+int dr_index_append(dr_index *h, const float *vec, const uint8_t *codes, int64_t n) {
+    DR_CHECK(h && (vec || n == 0) && n >= 0, "dr_index_append: bad argument");
+    DR_LOCK(h);
+    DR_CUDA(cudaSetDevice(h->device));
+    DR_CHECK(h->owns, "dr_index_append: the index adopted caller-owned device arrays (dr_index_create_dev) and cannot grow");
+    DR_CHECK(!(h->d_codes && !codes && n > 0), "dr_index_append: the index has PQ codes; codes u8[n,M] are required");
+    DR_CHECK(h->N + n < (1ll << 31), "dr_index_append: N must stay < 2^31");
+    if (n == 0) return 0;
+    DR_CUDA(cudaDeviceSynchronize());                    // no search may still be reading the arrays that are about to move
+    if (h->N + n > h->cap) {
+        int64_t ncap = h->cap + h->cap / 2 + 1024;
+        if (ncap < h->N + n) ncap = h->N + n;
+        if (grow_array(&h->d_vec, (size_t)h->N * h->D, (size_t)ncap * h->D)) return 1;
+        if (grow_array(&h->d_adj, (size_t)h->N * h->R, (size_t)ncap * h->R, 0xFF)) return 1;      // new rows: no neighbours
+        if (grow_array(&h->d_codes, (size_t)h->N * h->M, (size_t)ncap * h->M)) return 1;
+        if (grow_array(&h->d_deleted, (size_t)h->N, (size_t)ncap, 0)) return 1;
+        h->cap = ncap;
+    } else {
+        DR_CUDA(cudaMemset(h->d_adj + (size_t)h->N * h->R, 0xFF, (size_t)n * h->R * 4));
+        if (h->d_deleted) DR_CUDA(cudaMemset(h->d_deleted + h->N, 0, (size_t)n));
+    }
+    DR_CUDA(cudaMemcpy(h->d_vec + (size_t)h->N * h->D, vec, (size_t)n * h->D * 4, cudaMemcpyHostToDevice));
+    if (h->d_codes) DR_CUDA(cudaMemcpy(h->d_codes + (size_t)h->N * h->M, codes, (size_t)n * h->M, cudaMemcpyHostToDevice));
+    h->N += n;
+    return 0;
+}
+
+int dr_index_patch_rows(dr_index *h, const int64_t *rows, int64_t n, const uint32_t *adj) {
+    DR_CHECK(h && (n == 0 || (rows && adj)), "dr_index_patch_rows: null argument");
+    DR_LOCK(h);
+    DR_CUDA(cudaSetDevice(h->device));
+    DR_CHECK(h->owns, "dr_index_patch_rows: the index adopted caller-owned device arrays (dr_index_create_dev)");
+    DR_CUDA(cudaDeviceSynchronize());
+    return scatter_rows(rows, n, h->R, adj, h->d_adj, h->N, false);
+}
+
+int dr_index_patch_vectors(dr_index *h, const int64_t *rows, int64_t n, const float *vec, const uint8_t *codes) {
+    DR_CHECK(h && (n == 0 || (rows && vec)), "dr_index_patch_vectors: null argument");
+    DR_LOCK(h);
+    DR_CUDA(cudaSetDevice(h->device));
+    DR_CHECK(h->owns, "dr_index_patch_vectors: the index adopted caller-owned device arrays (dr_index_create_dev)");
+    DR_CUDA(cudaDeviceSynchronize());
+    if (scatter_rows(rows, n, h->D, vec, h->d_vec, h->N, false)) return 1;
+    if (h->d_codes && codes) return scatter_rows(rows, n, h->M, codes, h->d_codes, h->N, true);
+    return 0;
+}
+
+int dr_index_set_deleted_rows(dr_index *h, const int64_t *rows, int64_t n, const uint8_t *flags) {
+    DR_CHECK(h && (n == 0 || (rows && flags)), "dr_index_set_deleted_rows: null argument");
+    DR_LOCK(h);
+    DR_CUDA(cudaSetDevice(h->device));
+    DR_CUDA(cudaDeviceSynchronize());
+    if (!h->d_deleted) {
+        DR_CUDA(cudaMalloc(&h->d_deleted, (size_t)(h->cap > h->N ? h->cap : h->N)));
+        DR_CUDA(cudaMemset(h->d_deleted, 0, (size_t)(h->cap > h->N ? h->cap : h->N)));
+    }
+    return scatter_rows(rows, n, 1, flags, h->d_deleted, h->N, true);
 }
 
 int dr_index_set_start(dr_index *h, int64_t start) {

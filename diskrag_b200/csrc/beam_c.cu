@@ -184,7 +184,9 @@ void beam_c_plan(const dr_index *h, int64_t B, long long *grid_out, size_t *bitm
 }
 
 int launch_beam_c(dr_index *h, const float *d_Q, int64_t B, int k, int bw, int dist, int sqrt_out, const float *d_lut,
-                  uint32_t *d_bitmaps, int32_t *ids, float *dists, int32_t *hops, int32_t *visited, cudaStream_t s) {
+                  uint32_t *d_bitmaps, int32_t *ids, float *dists, int32_t *hops, int32_t *visited, cudaStream_t s, int64_t start) {
+    if (start < 0) start = h->medoid;
+    DR_CHECK(start < h->N, "dr_beam_search_c: start node %lld out of range", (long long)start);
     DR_CHECK(k >= 1 && k <= 1024 && bw >= 0 && bw <= 4096, "dr_beam_search_c: k must be in 1..1024, beam_width in 0..4096");
     DR_CHECK(dist == DR_DIST_PQ || dist == DR_DIST_EXACT, "dr_beam_search_c: dist must be DR_DIST_PQ or DR_DIST_EXACT");
     DR_CHECK(h->N < (1ll << 31), "dr_beam_search_c: ids must fit 31 bits");
@@ -196,7 +198,7 @@ int launch_beam_c(dr_index *h, const float *d_Q, int64_t B, int k, int bw, int d
     a.vec = h->d_vec; a.adj = h->d_adj; a.codes = h->d_codes; a.deg = h->d_deg; a.deleted = h->d_deleted;
     a.Q = d_Q; a.lut = dist == DR_DIST_PQ ? d_lut : nullptr;
     a.N = h->N; a.D = h->D; a.R = h->R; a.M = h->M; a.B = B; a.k = k; a.bw = bw; a.dist = dist; a.sqrt_out = sqrt_out;
-    a.start = (uint32_t)h->medoid;
+    a.start = (uint32_t)start;
     a.out_ids = ids; a.out_dist = dists; a.out_hops = hops; a.out_visited = visited;
     a.words = (h->N + 31) / 32;
     long long grid; size_t per_cta;

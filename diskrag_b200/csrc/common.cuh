@@ -47,6 +47,7 @@ extern std::atomic<long long> g_launches;
 struct dr_index {
     int device = 0;
     int64_t N = 0;
+    int64_t cap = 0;              // rows allocated (>= N) when the arrays are owned: dr_index_append grows them
     int D = 0, R = 0, M = 0;
     int64_t medoid = 0;
     bool owns = true;
@@ -65,6 +66,8 @@ struct dr_index {
     // search-kernel timing (bench roofline)
     bool timing = false; double timed_ms = 0.0; long long timed_launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // last use of the shared scratch: a search enqueued on a different stream waits for it on the device
+    cudaEvent_t ev_scratch = nullptr; cudaStream_t scratch_stream = nullptr; bool scratch_used = false;
     // host-pointer API pipeline (copy-in / compute / copy-out streams)
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[DR_PIPE_EVENTS] = {}, ev_done[DR_PIPE_EVENTS] = {};
@@ -87,7 +90,8 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
                        int32_t *status, cudaStream_t s);   // search_fast.cu: u8-table throughput kernel
 void beam_c_plan(const dr_index *h, int64_t B, long long *grid_out, size_t *bitmap_bytes_out);   // beam_c.cu
 int launch_beam_c(dr_index *h, const float *d_Q, int64_t B, int k, int bw, int dist, int sqrt_out, const float *d_lut,
-                  uint32_t *d_bitmaps, int32_t *ids, float *dists, int32_t *hops, int32_t *visited, cudaStream_t s);
+                  uint32_t *d_bitmaps, int32_t *ids, float *dists, int32_t *hops, int32_t *visited, cudaStream_t s,
+                  int64_t start = -1);
 int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
                         float *d_offset, float *d_mn, unsigned *d_range, int word_layout, cudaStream_t s);  // pq.cu
 int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,

@@ -463,17 +463,41 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
 // ---------------------------------------------------------------------------------------------------
 static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
+static int launch_search_impl(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, const float *d_lut,
+                              int32_t *ids, float *dist, int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist,
+                              int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s,
+                              const int32_t *qmap);
+
+// The handle's scratch (ADC tables, work counter, overflow tables) is shared by every call on the handle.  Calls enqueued on
+// ONE stream are ordered by the stream; a call on a different stream first waits, on the device, for the previous call's
+// kernels (an event recorded after every launch), so two in-flight calls can never share the scratch.
 int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, const float *d_lut,
                   int32_t *ids, float *dist, int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist,
                   int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s,
                   const int32_t *qmap) {
+    if (h->ev_scratch && h->scratch_used && h->scratch_stream != s) DR_CUDA(cudaStreamWaitEvent(s, h->ev_scratch, 0));
+    const int rc = launch_search_impl(h, d_Q, B, p, d_lut, ids, dist, hops, visited, list_ids, list_dist, list_len, trace, trace_cap,
+                                      status, s, qmap);
+    if (h->ev_scratch && B > 0) {
+        DR_CUDA(cudaEventRecord(h->ev_scratch, s));
+        h->scratch_stream = s; h->scratch_used = true;
+    }
+    return rc;
+}
+
+static int launch_search_impl(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, const float *d_lut,
+                              int32_t *ids, float *dist, int32_t *hops, int32_t *visited, int32_t *list_ids, float *list_dist,
+                              int32_t *list_len, int32_t *trace, int32_t trace_cap, int32_t *status, cudaStream_t s,
+                              const int32_t *qmap) {
     DR_CHECK(p->k >= 1 && p->L >= 1 && p->L <= 512 && p->k <= p->L, "dr_search: need 1 <= k <= L <= 512 (k=%d L=%d)", p->k, p->L);
     DR_CHECK(p->W >= 1 && p->W <= 32, "dr_search: W must be in 1..32 (got %d)", p->W);
     const bool pq = p->dist == DR_DIST_PQ;
     DR_CHECK(p->dist == DR_DIST_PQ || p->dist == DR_DIST_EXACT || p->dist == DR_DIST_COSINE, "dr_search: unknown dist %d", p->dist);
     DR_CHECK(p->dist != DR_DIST_COSINE || !p->rerank, "dr_search: the rerank is a squared-L2 rerank; DR_DIST_COSINE returns the traversal's own order");
     if (pq) DR_CHECK(h->d_codes && h->M > 0, "dr_search: index has no PQ codes");
-    DR_CHECK(h->medoid >= 0 && h->medoid < h->N, "dr_search: medoid out of range");
+    const int64_t start = p->start_plus1 > 0 ? (int64_t)p->start_plus1 - 1 : h->medoid;
+    DR_CHECK(p->start_plus1 >= 0 && start >= 0 && start < h->N, "dr_search: start node %lld out of range (N=%lld)", (long long)start,
+             (long long)h->N);
     if (B == 0) return 0;
     if (p->lut_fmt == DR_LUT_U8 || p->lut_fmt == DR_LUT_U8_TC) {
         DR_CHECK(pq && !d_lut && !trace && !qmap && !h->d_deg, "dr_search: the u8-table mode is PQ-only, builds its own tables and has no trace");
@@ -484,13 +508,13 @@ int launch_search(dr_index *h, const float *d_Q, int64_t B, const dr_search_para
     memset(&a, 0, sizeof(a));
     a.vec = h->d_vec; a.adj = h->d_adj; a.codes = h->d_codes;
     a.deg = h->d_deg;
-    a.deleted = h->d_deleted;
+    a.deleted = p->ignore_deleted ? nullptr : h->d_deleted;
     a.N = h->N; a.D = h->D; a.R = h->R; a.M = h->M;
     a.k = p->k; a.L = p->L; a.W = p->W;
     a.dist = p->dist; a.adc_tree = (pq && p->adc_order == DR_ADC_TREE) ? 1 : 0;
     a.rerank = p->rerank; a.sqrt_out = p->sqrt_out;
     a.strict = (p->W == 1) ? 1 : 0;
-    a.start = (uint32_t)h->medoid;
+    a.start = (uint32_t)start;
     a.trace_cap = trace ? trace_cap : 0;
 
     // shared-memory layout

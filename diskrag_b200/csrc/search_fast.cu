@@ -27,7 +27,7 @@ struct FastArgs {
     int32_t *list_ids; float *list_dist; int32_t *list_len; int32_t *status;
     u64 *counter;
     uint32_t *ovf; uint32_t ovf_cap; uint32_t hash_cap;
-    int o_q, o_rrk, o_list0, o_list1, o_ur0, o_ur1, o_newk, o_newid, o_sel, o_hash;
+    int o_q, o_rrk, o_list0, o_list1, o_ur0, o_ur1, o_newk, o_newid, o_sel, o_adjrow, o_hash;
     int rr_slots;   // rerank staging slots available in the table region (the query vector may occupy the last one)
 };
 
@@ -253,6 +253,10 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #ifndef DR_MERGE_LINEAR
 #define DR_MERGE_LINEAR 32
 #endif  // up to this many survivors: rank by counting, no sort
+// prefetch mask the serving-shape specialisation (RW8 = 4) is compiled for (dr_search_params.prefetch must equal it)
+#ifndef DR_PF_SPEC
+#define DR_PF_SPEC 5
+#endif
 #ifndef DR_L2V
 #define DR_L2V 0   // experiment (scripts/build_variants.py): 1 = the serving-shape specialisations keep the visited set in the
 #endif             // CTA's L2-resident table (no shared-memory hash) so that four CTAs fit on an SM; pair with DR_FAST_NT=192
@@ -274,7 +278,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     uint16_t *s_ur1 = reinterpret_cast<uint16_t *>(dr_smem + a.o_ur1);
     u64 *s_newk = reinterpret_cast<u64 *>(dr_smem + a.o_newk);
     uint32_t *s_newid = reinterpret_cast<uint32_t *>(dr_smem + a.o_newid);
-    uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);
+    uint32_t *s_sel = reinterpret_cast<uint32_t *>(dr_smem + a.o_sel);      // [0, W): next-in-line positions; [W, 2W): the selection
+    uint32_t *s_adjrow = reinterpret_cast<uint32_t *>(dr_smem + a.o_adjrow);   // prefetch & 16: the W selected nodes' adjacency rows
     uint32_t *s_hash = reinterpret_cast<uint32_t *>(dr_smem + a.o_hash);
     u64 *s_rrk = reinterpret_cast<u64 *>(dr_smem + a.o_rrk);    // rerank keys alias a region that is dead after the traversal
     const bool no_smem_hash = RW8 >= 3 ? (DR_L2V != 0) : (a.hash_cap == 0);
@@ -283,7 +288,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     __shared__ u64 s_pfkey;   // prefetch == 2: a survivor below this key is among the next step's likely expansions
     __shared__ __align__(8) uint64_t s_lutbar;
     __shared__ __align__(8) uint64_t s_rrbar[16];   // rerank staging: two half-row barriers per warp
-    __shared__ int s_nn2[2], s_ns, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
+    __shared__ __align__(8) uint64_t s_adjbar[16];  // prefetch & 16: one barrier per selected node's adjacency row
+    __shared__ int s_nn2[2], s_ns, s_nspec, s_mvalid, s_hcount, s_ovfcount, s_ovfused, s_status;
 
     const int tid = threadIdx.x;
     constexpr int nt = DR_FAST_NT, nw = DR_FAST_NT / 32;   // the launcher always uses DR_FAST_NT threads
@@ -293,7 +299,10 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     const uint32_t tab32 = smem_u32(s_lut);
     const int D = RW8 >= 2 ? 1536 : a.D, M = a.M, L = RW8 >= 3 ? 100 : a.L;
     const uint32_t hcap = RW8 >= 3 ? (DR_L2V ? 0u : 4096u) : a.hash_cap;
-    const int pf = RW8 == 4 ? 5 : a.prefetch;
+    const int pf = RW8 == 4 ? DR_PF_SPEC : a.prefetch;
+    const bool adj_async = (pf & 16) != 0;   // the launcher clears the bit unless R % 4 == 0 and W <= 16
+    const bool spec_code = (pf & 8) != 0;
+    uint32_t adj_par = 0u;                   // bit s: parity of s_adjbar[s] this warp waits for next
     const uint8_t *deleted = RW8 == 4 ? nullptr : a.deleted;
     const bool do_rerank = RW8 == 4 ? true : (a.rerank != 0);
     const int R = RW8 ? 32 : a.R, W = RW8 ? 8 : a.W;
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
 #endif
     if (tid == 0) {
         mbar_init(&s_lutbar, 1);
-        for (int i = 0; i < 16; ++i) mbar_init(&s_rrbar[i], 1);
+        for (int i = 0; i < 16; ++i) { mbar_init(&s_rrbar[i], 1); mbar_init(&s_adjbar[i], 1); }
         fence_mbar_init();
     }
     uint32_t rr_ph0 = 0, rr_ph1 = 0;
@@ -380,7 +389,12 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 else s_hash[fib_slot(a.start, hshift)] = a.start;
                 s_ur0[0] = 0; s_ur0[1] = 1;      // one unexpanded entry
                 s_sel[W] = 0u; s_ns = 1;         // the first step expands list position 0
+                s_nspec = 0;
                 s_pfkey = DR_KEY_MAX;
+                if (adj_async) {
+                    mbar_expect_tx(&s_adjbar[0], (uint32_t)R * 4u);
+                    bulk_g2s(s_adjrow, a.adj + (size_t)a.start * R, (uint32_t)R * 4u, &s_adjbar[0]);
+                }
             }
         }
         int cur = 0, n = 1, hops = 0, nvis = 1, step = 0;
@@ -401,6 +415,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             const bool use_ovf_now = (s_hcount + W * R > hlimit);   // same value for every thread (read after the last barrier)
             if (use_ovf_now && (s_ovfcount + W * R > ovf_limit)) {
                 if (tid == 0) s_status |= DR_ST_VISITED_OVERFLOW;
+                if (adj_async)      // rows already on their way: consume their barrier phases so the next query starts in step
+                    for (int s = wid; s < ns; s += nw) { mbar_wait(&s_adjbar[s], (adj_par >> s) & 1u); adj_par ^= 1u << s; }
                 break;
             }
             if (tid == 0) {
@@ -408,6 +424,12 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 if (use_ovf_now) s_ovfused = 1;
             }
             const bool spec = (pf & 2) != 0;
+            // prefetch & 8: the nodes next in line (unexpanded ranks W .. 2W-1) are this step's likely successors: read their
+            // adjacency rows now (L2 hits: prefetched when they were accepted) and start the code rows of their unseen
+            // neighbours on the trip to L2, one whole step before the ADC phase that needs them.  Nothing is claimed.
+            const int nspec = (spec_code && !use_ovf_now && !no_smem_hash) ? s_nspec : 0;
+            uint32_t nb2 = DR_EMPTY;
+            if (wid < nspec && lane < R) nb2 = __ldg(a.adj + (size_t)key_id(lst[s_sel[wid]]) * R + lane);
             for (int s = wid; s < ns; s += nw) {
                 const int pos = (int)s_sel[W + s];
                 DR_PT(6);   // (timing build) selection read
@@ -415,9 +437,13 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 __syncwarp();
                 if (lane == 0) lst[pos] |= 1ull;          // mark it expanded: only this warp touches lst[pos] before the barrier
                 const uint32_t *row = a.adj + (size_t)node * R;
+                if (adj_async) {                          // the row was sent to shared memory when the node was selected
+                    mbar_wait(&s_adjbar[s], (adj_par >> s) & 1u);
+                    adj_par ^= 1u << s;
+                }
                 for (int j0 = 0; j0 < R; j0 += 32) {
                     const int j = j0 + lane;
-                    const uint32_t nb = (j < R) ? __ldg(row + j) : DR_EMPTY;
+                    const uint32_t nb = (j < R) ? (adj_async ? s_adjrow[s * R + j] : __ldg(row + j)) : DR_EMPTY;
                     bool valid = (j < R) && (nb < n32);
 #ifdef DR_PHASE_TIMING
                     asm volatile("" ::"r"(nb));
@@ -436,6 +462,26 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     if (isnew) {
                         s_newid[basepos + __popc(m & lt_mask)] = nb;
                         if (pf & 4) {   // the code row is needed right after the barrier: start its trip now
+                            const uint8_t *cr = a.codes + (size_t)nb * M;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(cr));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(cr + (M > 128 ? 128 : M - 1)));
+                        }
+                    }
+                }
+            }
+            for (int s2 = wid; s2 < nspec; s2 += nw) {
+                const uint32_t *row2 = a.adj + (size_t)key_id(lst[s_sel[s2]]) * R;
+                for (int j0 = 0; j0 < R; j0 += 32) {
+                    const int j = j0 + lane;
+                    const uint32_t nb = (s2 == wid && j0 == 0) ? nb2 : ((j < R) ? __ldg(row2 + j) : DR_EMPTY);
+                    if (j < R && nb < n32) {
+                        bool seen = false;                 // read-only probe (a concurrent claim may be missed: it is only a hint)
+                        for (uint32_t h = fib_slot(nb, hshift);; h = (h + 1) & hmask) {
+                            const uint32_t c = s_hash[h];
+                            if (c == nb) { seen = true; break; }
+                            if (c == DR_EMPTY) break;
+                        }
+                        if (!seen) {
                             const uint8_t *cr = a.codes + (size_t)nb * M;
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(cr));
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(cr + (M > 128 ? 128 : M - 1)));
@@ -560,16 +606,25 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 oth[pos] = key;
                 ur_new[pos] = (uint16_t)rank;
                 if (un) {
-                    if (rank < W) s_sel[W + rank] = (uint32_t)pos;
-                    else if (spec && rank < 2 * W) {     // next in line: likely to be expanded in two steps
-                        for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(key) * R + o));
-                        if (rank == 2 * W - 1) s_pfkey = key;
+                    if (rank < W) {
+                        s_sel[W + rank] = (uint32_t)pos;
+                        if (adj_async) {                 // its adjacency row travels to shared memory under the rest of the merge
+                            mbar_expect_tx(&s_adjbar[rank], (uint32_t)R * 4u);
+                            bulk_g2s(s_adjrow + rank * R, a.adj + (size_t)key_id(key) * R, (uint32_t)R * 4u, &s_adjbar[rank]);
+                        }
+                    } else if (rank < 2 * W) {           // next in line: likely to be expanded in two steps
+                        if (spec_code) s_sel[rank - W] = (uint32_t)pos;
+                        if (spec) {
+                            for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(key) * R + o));
+                            if (rank == 2 * W - 1) s_pfkey = key;
+                        }
                     }
                 }
                 if (pos == nnew - 1) {
                     const int tot = rank + (un ? 1 : 0);
                     ur_new[nnew] = (uint16_t)tot;
                     s_ns = tot < W ? tot : W;
+                    s_nspec = tot < W ? 0 : (tot < 2 * W ? tot - W : W);
                     if (spec && tot < 2 * W) s_pfkey = DR_KEY_MAX;
                 }
             };
@@ -641,10 +696,18 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 for (int x = tid; x < n; x += nt) {
                     const int r = (int)ur_old[x] - ubase;
                     if (!(lst[x] & 1ull)) {
-                        if (r < W) s_sel[W + r] = (uint32_t)x;
-                        else if (spec && r < 2 * W) {
-                            for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(lst[x]) * R + o));
-                            if (r == 2 * W - 1) s_pfkey = lst[x];
+                        if (r < W) {
+                            s_sel[W + r] = (uint32_t)x;
+                            if (adj_async) {
+                                mbar_expect_tx(&s_adjbar[r], (uint32_t)R * 4u);
+                                bulk_g2s(s_adjrow + r * R, a.adj + (size_t)key_id(lst[x]) * R, (uint32_t)R * 4u, &s_adjbar[r]);
+                            }
+                        } else if (r < 2 * W) {
+                            if (spec_code) s_sel[r - W] = (uint32_t)x;
+                            if (spec) {
+                                for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(lst[x]) * R + o));
+                                if (r == 2 * W - 1) s_pfkey = lst[x];
+                            }
                         }
                     }
                 }
@@ -652,6 +715,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     int tot = (int)ur_old[n] - ubase;
                     tot = tot > 0 ? tot : 0;
                     s_ns = tot < W ? tot : W;
+                    s_nspec = tot < W ? 0 : (tot < 2 * W ? tot - W : W);
                     if (spec && tot < 2 * W) s_pfkey = DR_KEY_MAX;
                 }
                 __syncthreads();
@@ -818,10 +882,11 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     DR_CHECK(h->d_codes && h->d_codebook && h->M > 0, "dr_search: the u8-table mode needs PQ codes and the codebook");
     FastArgs a;
     memset(&a, 0, sizeof(a));
-    a.vec = h->d_vec; a.adj = h->d_adj; a.codes = h->d_codes; a.deleted = h->d_deleted;
+    a.vec = h->d_vec; a.adj = h->d_adj; a.codes = h->d_codes; a.deleted = p->ignore_deleted ? nullptr : h->d_deleted;
     a.N = h->N; a.D = h->D; a.R = h->R; a.M = h->M;
     a.k = p->k; a.L = p->L; a.W = p->W; a.rerank = p->rerank; a.sqrt_out = p->sqrt_out; a.prefetch = p->prefetch;
-    a.start = (uint32_t)h->medoid;
+    if ((h->R & 3) != 0 || p->W > 16) a.prefetch &= ~16;   // bulk copies of adjacency rows need 16-byte rows; 16 barriers
+    a.start = (uint32_t)(p->start_plus1 > 0 ? (int64_t)p->start_plus1 - 1 : h->medoid);   // range-checked by launch_search
     const bool word_layout = ((h->M & 3) == 0) && h->M <= 256;
     DR_CHECK(p->lut_fmt != DR_LUT_U8_TC || (word_layout && ((h->D / h->M) & 7) == 0),
              "dr_search: DR_LUT_U8_TC needs M %% 4 == 0, M <= 256 and (D / M) %% 8 == 0 (D=%d M=%d)", h->D, h->M);
@@ -855,6 +920,8 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     a.o_newid = off; off += NC * 4;
     a.o_sel = off; off += ((2 * p->W * 4 + 7) / 8) * 8;
     off = (off + 15) / 16 * 16;
+    a.o_adjrow = off;
+    if (a.prefetch & 16) off += (p->W * h->R * 4 + 15) / 16 * 16;
     a.o_hash = off;
     const int fixed = off;
     // The query vector (rerank only) lives in the visited table's bytes once the traversal is over, behind the rerank
@@ -897,7 +964,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     }
     a.hash_cap = hc;
     if (shape == 3 && hc != (DR_L2V ? 0u : 4096u)) shape = 2;
-    if (shape == 3 && p->prefetch == 5 && !h->d_deleted && p->rerank) shape = 4;
+    if (shape == 3 && p->prefetch == DR_PF_SPEC && !a.deleted && p->rerank) shape = 4;
     kern = pick_fast_kernel(h->M, l2_visited ? 4 : 3, shape);
     const int smem = fixed + (int)hc * 4 + q_extra;
     const int nt = DR_FAST_NT;

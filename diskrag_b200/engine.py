@@ -23,12 +23,14 @@ class SearchResult:
 
 
 def make_params(k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_out=False, hash_cap=0, chunk=0,
-                threads=0, lut="f32", prefetch=False) -> SearchParams:
+                threads=0, lut="f32", prefetch=False, start=None, ignore_deleted=False) -> SearchParams:
+    """start: entry point of the call (the reference's start_idx); None = the index's own (medoid)."""
     return SearchParams(k=k, L=L, W=W, dist={"pq": _lib.DR_DIST_PQ, "cosine": _lib.DR_DIST_COSINE}.get(dist, _lib.DR_DIST_EXACT),
                         adc_order=_lib.DR_ADC_TREE if adc_order == "tree" else _lib.DR_ADC_SEQ,
                         rerank=int(bool(rerank)), sqrt_out=int(bool(sqrt_out)), hash_cap=hash_cap, chunk=chunk,
                         threads=threads, lut_fmt={"u8": _lib.DR_LUT_U8, "u8tc": _lib.DR_LUT_U8_TC}.get(lut, _lib.DR_LUT_F32),
-                        prefetch=int(prefetch))
+                        prefetch=int(prefetch), start_plus1=0 if start is None else int(start) + 1,
+                        ignore_deleted=int(bool(ignore_deleted)))
 
 
 class GpuIndex:
@@ -124,7 +126,8 @@ class GpuIndex:
 
     # ---- search ---------------------------------------------------------------------------------
     def search(self, Q, k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_out=False, lut=None,
-               want_list=False, trace=0, hash_cap=0, chunk=0, threads=0, lut_fmt="f32", prefetch=False) -> SearchResult:
+               want_list=False, trace=0, hash_cap=0, chunk=0, threads=0, lut_fmt="f32", prefetch=False, start=None,
+               ignore_deleted=False) -> SearchResult:
         """Batched search of Q f32[B,D] (host).  Returns host numpy arrays."""
         Q = as_f32(np.atleast_2d(Q))
         B, D = Q.shape
@@ -132,7 +135,7 @@ class GpuIndex:
             raise ValueError(f"query dimension {D} != index dimension {self.D}")
         if dist == "pq" and self.M == 0:
             raise ValueError("index has no PQ codes; use dist='exact'")
-        p = make_params(k, L, W, dist, adc_order, rerank, sqrt_out, hash_cap, chunk, threads, lut_fmt, prefetch)
+        p = make_params(k, L, W, dist, adc_order, rerank, sqrt_out, hash_cap, chunk, threads, lut_fmt, prefetch, start, ignore_deleted)
         if lut is not None:
             lut = as_f32(lut).reshape(B, self.M, 256)
         ids = np.empty((B, k), np.int32); dd = np.empty((B, k), np.float32)
@@ -150,7 +153,7 @@ class GpuIndex:
         return SearchResult(ids=ids, dists=dd, hops=hops, visited=vis, status=st, list_ids=lids, list_dists=ldist,
                             list_len=llen, trace=tr)
 
-    def beam_search_c(self, Q, k=3, beam_width=5, dist="pq", sqrt_out=True) -> SearchResult:
+    def beam_search_c(self, Q, k=3, beam_width=5, dist="pq", sqrt_out=True, start=None) -> SearchResult:
         """Variant C with the reference's own semantics (vamana_graph.py:535-605; csrc/beam_c.cu): the k-capped beam whose
         truncation keeps the beam_width WORST frontier entries.  Results sorted by (dist, id); ids -1 padded."""
         Q = as_f32(np.atleast_2d(Q))
@@ -165,7 +168,7 @@ class GpuIndex:
         hops = np.empty(B, np.int32); vis = np.empty(B, np.int32)
         check(lib().dr_beam_search_c(self._h, ptr(Q), B, int(k), int(beam_width),
                                      _lib.DR_DIST_PQ if dist == "pq" else _lib.DR_DIST_EXACT, int(bool(sqrt_out)),
-                                     ptr(ids), ptr(dd), ptr(hops), ptr(vis)), "dr_beam_search_c")
+                                     -1 if start is None else int(start), ptr(ids), ptr(dd), ptr(hops), ptr(vis)), "dr_beam_search_c")
         return SearchResult(ids=ids, dists=dd, hops=hops, visited=vis, status=np.zeros(B, np.int32), list_ids=None,
                             list_dists=None, list_len=None, trace=None)
 
@@ -182,6 +185,33 @@ class GpuIndex:
         check(lib().dr_search_batch_dev(self._h, d_Q, B, C.byref(params), d_lut, d_ids, d_dist, d_hops, d_visited,
                                         d_list_ids, d_list_dist, d_list_len, None, 0, d_status, stream),
               "dr_search_batch_dev")
+
+    # ---- dynamic updates: O(rows touched) (vamana_graph.py:58-125) ----------------------------------
+    def append(self, vec, codes=None):
+        """n new nodes with ids N .. N+n-1 and empty rows."""
+        vec = as_f32(np.atleast_2d(vec))
+        if codes is not None:
+            codes = np.ascontiguousarray(np.atleast_2d(codes), dtype=np.uint8)
+        check(lib().dr_index_append(self._h, ptr(vec), ptr(codes), vec.shape[0]), "dr_index_append")
+        self.N += vec.shape[0]
+
+    def patch_rows(self, rows, adj):
+        """adj u32[n,R] replaces the adjacency rows `rows`; a slot >= N (0xFFFFFFFF) means "no neighbour"."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        adj = np.ascontiguousarray(adj, dtype=np.uint32).reshape(rows.size, self.R)
+        check(lib().dr_index_patch_rows(self._h, ptr(rows), rows.size, ptr(adj)), "dr_index_patch_rows")
+
+    def patch_vectors(self, rows, vec, codes=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        vec = as_f32(np.atleast_2d(vec))
+        if codes is not None:
+            codes = np.ascontiguousarray(np.atleast_2d(codes), dtype=np.uint8)
+        check(lib().dr_index_patch_vectors(self._h, ptr(rows), rows.size, ptr(vec), ptr(codes)), "dr_index_patch_vectors")
+
+    def set_deleted_rows(self, rows, flags):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        check(lib().dr_index_set_deleted_rows(self._h, ptr(rows), rows.size, ptr(flags)), "dr_index_set_deleted_rows")
 
     def lut(self, Q):
         Q = as_f32(np.atleast_2d(Q))

@@ -49,8 +49,30 @@ class DiskANNPQ:
         self._cb = None
 
     # -- helpers -------------------------------------------------------------------------------------
+    @classmethod
+    def from_codebook(cls, codebook, device: int = 0):
+        """Additive: a fitted model around an existing codebook f32[M, 256, ds] (e.g. one read from pq_model.pkl)."""
+        cb = np.ascontiguousarray(codebook, dtype=np.float32)
+        if cb.ndim != 3 or cb.shape[1] != 256:
+            raise ValueError(f"codebook must be f32[M, 256, ds], got {cb.shape}")
+        pq = cls(cb.shape[0], 256, device)
+        pq.sub_dim = cb.shape[2]
+        pq.kmeans_list = [_wrap_kmeans(cb[i], 42 + i) for i in range(cb.shape[0])]
+        pq._cb = cb
+        pq.is_fitted = True
+        return pq
+
     def _invalidate(self):
         self._cb = None
+
+    def _dim(self) -> int:
+        return self.sub_dim * self.n_subvectors
+
+    def _check_vectors(self, X, what):
+        # the C entry points read 256 * D * 4 bytes of codebook for the D they are told: never pass a caller-derived D that the
+        # model was not trained for (the reference fails in sklearn / numpy broadcasting on the same inputs)
+        if X.ndim != 2 or X.shape[1] != self._dim():
+            raise ValueError(f"{what}: expected vectors of dimension {self._dim()} (= {self.n_subvectors} x {self.sub_dim}), got {X.shape}")
 
     def __getstate__(self):
         st = dict(self.__dict__)
@@ -95,6 +117,7 @@ class DiskANNPQ:
         if not self.is_fitted:
             raise ValueError("模型尚未訓練，請先調用 fit() 方法")
         X = as_f32(np.atleast_2d(vectors))
+        self._check_vectors(X, "encode")
         n, d = X.shape
         codes = np.empty((n, self.n_subvectors), np.uint8)
         check(lib().dr_pq_encode(ptr(self.codebook()), ptr(X), n, d, self.n_subvectors, ptr(codes), self.device),
@@ -105,6 +128,8 @@ class DiskANNPQ:
         if not self.is_fitted:
             raise ValueError("模型尚未訓練")
         codes = np.ascontiguousarray(np.atleast_2d(codes), dtype=np.uint8)
+        if codes.shape[1] != self.n_subvectors:
+            raise ValueError(f"decode: expected codes u8[n, {self.n_subvectors}], got {codes.shape}")
         n = codes.shape[0]
         d = self.sub_dim * self.n_subvectors
         out = np.empty((n, d), np.float32)
@@ -116,6 +141,7 @@ class DiskANNPQ:
         if not self.is_fitted:
             raise ValueError("模型尚未訓練")
         q = as_f32(query_vector).reshape(1, -1)
+        self._check_vectors(q, "compute_distance_table")
         d = self.sub_dim * self.n_subvectors
         out = np.empty((self.n_subvectors, self.n_centroids), np.float32)
         check(lib().dr_pq_lut(ptr(self.codebook()), ptr(q), 1, d, self.n_subvectors, ptr(out), self.device), "dr_pq_lut")
@@ -123,15 +149,21 @@ class DiskANNPQ:
 
     def compute_distance_tables(self, queries: np.ndarray) -> np.ndarray:
         """Batched variant (additive): f32[B, D] -> f32[B, M, 256]."""
+        if not self.is_fitted:
+            raise ValueError("模型尚未訓練")
         Q = as_f32(np.atleast_2d(queries))
+        self._check_vectors(Q, "compute_distance_tables")
         out = np.empty((Q.shape[0], self.n_subvectors, self.n_centroids), np.float32)
-        check(lib().dr_pq_lut(ptr(self.codebook()), ptr(Q), Q.shape[0], Q.shape[1], self.n_subvectors, ptr(out),
+        check(lib().dr_pq_lut(ptr(self.codebook()), ptr(Q), Q.shape[0], self._dim(), self.n_subvectors, ptr(out),
                               self.device), "dr_pq_lut")
         return out
 
     def asymmetric_distance_sq(self, codes: np.ndarray, distance_table: np.ndarray) -> np.ndarray:
         codes = np.ascontiguousarray(np.atleast_2d(codes), dtype=np.uint8)
         T = as_f32(distance_table)
+        if codes.shape[1] != self.n_subvectors or T.shape != (self.n_subvectors, 256):
+            raise ValueError(f"asymmetric_distance_sq: expected codes u8[n, {self.n_subvectors}] and a table f32[{self.n_subvectors}, 256], "
+                             f"got {codes.shape} and {T.shape}")
         out = np.empty(codes.shape[0], np.float32)
         check(lib().dr_adc(ptr(codes), ptr(T), codes.shape[0], self.n_subvectors, ptr(out), self.device), "dr_adc")
         return out

@@ -13,9 +13,17 @@ Reference surface mirrored here:
   robust_prune, robust_prune_with_pq                           :249-355, 402-450, 642-683
 Additive: `search_batch(graph_or_reader, Q, ...)` — the batched entry point the reference lacks.
 
-The graph keeps `vec f32[N,D]`, `adj u32[N,R]` + `deg`, `codes u8[N,M]`, a lazy-delete mask, and mirrors
-them into one device index (GpuIndex) that is rebuilt only after a mutation.  `graph.nodes` is a lazy
-mapping that materialises `Node` objects on demand, so a 1M-node graph does not cost GBs of Python objects.
+The graph keeps `vec f32[N,D]`, `adj u32[N,w]` + `deg` (w >= R: like the reference's neighbour sets, a row may
+outgrow R through the reverse edges of insert_node, :106-114), `codes u8[N,M]`, a lazy-delete mask, and mirrors them
+into one device index (GpuIndex).  The mirror is patched in place after a mutation — appended nodes, changed rows,
+changed delete flags (dr_index_append / dr_index_patch_rows / ...): O(rows touched), not O(N*D) — and rebuilt only
+when the row width or the PQ model changes.  On the device an unused slot of a row holds 0xFFFFFFFF = "no neighbour":
+the reference's in-memory searches iterate `node.neighbors` (true degree, the set's iteration order, no padding;
+:607-640, cython_utils.pyx:108).  The 0-padding that IS a neighbour belongs to the on-disk path only (index.dat rows
+read back by MMapNodeReader: `to_records`, `beam_search_from_disk`, `GpuIndex.from_records`).
+`graph.nodes` is a lazy mapping that materialises `Node` objects on demand, so a 1M-node graph does not cost GBs of
+Python objects; a materialised Node keeps its own `set`, so the iteration order the reference would see is the order
+the device row is written in.
 
 Variant C note: the reference's beam_search_with_pq caps the result heap at k and truncates its frontier
 by popping the *best* entries (:592-593), which yields recall 0.036 on its own benchmark shape (SURVEY
@@ -89,10 +97,10 @@ class _Nodes:
             raise KeyError(f"node ids must be dense: next id is {g._n}, got {idx}")
         node._snapshot = None
         self._live[idx] = node
-        g._dirty = True
 
     def _flush(self):
-        """Write materialised nodes that changed back into the arrays."""
+        """Write materialised nodes that changed back into the arrays (rows in the set's iteration order, never truncated:
+        the arrays widen instead) and note which rows / flags the device mirror has to patch."""
         g = self._g
         changed = False
         for idx, node in self._live.items():
@@ -100,13 +108,20 @@ class _Nodes:
             cur = (frozenset(node.neighbors), bool(node.is_deleted))
             if snap == cur:
                 continue
-            nb = list(node.neighbors)[:g._adj.shape[1]] if len(node.neighbors) > g._adj.shape[1] else list(node.neighbors)
-            g._adj[idx, :len(nb)] = nb
-            g._adj[idx, len(nb):] = 0
-            g._deg[idx] = len(nb)
-            g._deleted[idx] = node.is_deleted
-            if node.pq_code is not None and g._codes is not None:
+            nb = list(node.neighbors)
+            if len(nb) > g._adj.shape[1]:
+                g._widen(len(nb))
+            if snap is None or snap[0] != cur[0]:
+                g._adj[idx, :len(nb)] = nb
+                g._adj[idx, len(nb):] = 0
+                g._deg[idx] = len(nb)
+                g._rows_dirty.add(idx)
+            if snap is None or snap[1] != cur[1]:
+                g._deleted[idx] = node.is_deleted
+                g._del_dirty.add(idx)
+            if node.pq_code is not None and g._codes is not None and not np.array_equal(g._codes[idx], node.pq_code):
                 g._codes[idx] = node.pq_code
+                g._vec_dirty.add(idx)
             node._snapshot = cur
             changed = True
         return changed
@@ -127,8 +142,14 @@ class VamanaGraphWithPQ:
         self._deg = np.zeros(0, np.int32)
         self._codes = None
         self._deleted = np.zeros(0, bool)
-        self._dirty = True
+        self._dirty = True            # the device mirror must be rebuilt from scratch (row width / PQ model / bulk change)
+        self._rows_dirty = set()      # rows whose adjacency changed since the mirror was last patched
+        self._vec_dirty = set()       # rows whose vector / code changed (a deleted id re-enabled with a new vector)
+        self._del_dirty = set()       # rows whose delete flag changed
         self._gpu = None
+        self._gpu_n = 0               # nodes the mirror holds
+        self._vec_store = None; self._codes_store = None
+        self._adj_store, self._deg_store, self._del_store = self._adj, self._deg, self._deleted
         self.nodes = _Nodes(self)
 
     # ---- array plumbing ------------------------------------------------------------------------------
@@ -141,24 +162,72 @@ class VamanaGraphWithPQ:
         g._deg = (np.full(g._n, g._adj.shape[1], np.int32) if deg is None else np.ascontiguousarray(deg, np.int32).copy())
         g._codes = None if codes is None else np.ascontiguousarray(codes, np.uint8).copy()
         g._deleted = np.zeros(g._n, bool)
+        g._adopt()
         g.medoid_idx = int(medoid_idx)
         return g
 
+    def _reserve(self, n, D=None):
+        """Host arrays grow geometrically (amortised O(1) per appended node); [:_n] is the live part."""
+        cap = self._adj_store.shape[0]
+        if self._vec_store is not None and n <= cap:
+            return
+        ncap = max(n, cap + cap // 2 + 64)
+
+        def grow(store, tail, dtype):
+            b = np.zeros((ncap,) + tail, dtype)
+            if store is not None and self._n:
+                b[:self._n] = store[:self._n]
+            return b
+        D = self._vec_store.shape[1] if self._vec_store is not None else D
+        self._vec_store = grow(self._vec_store, (D,), np.float32)
+        self._adj_store = grow(self._adj_store, (self._adj_store.shape[1],), np.uint32)
+        self._deg_store = grow(self._deg_store, (), np.int32)
+        self._del_store = grow(self._del_store, (), bool)
+        if self._codes_store is not None:
+            self._codes_store = grow(self._codes_store, (self._codes_store.shape[1],), np.uint8)
+        self._views()
+
+    def _views(self):
+        n = self._n
+        self._vec = self._vec_store[:n]; self._adj = self._adj_store[:n]; self._deg = self._deg_store[:n]
+        self._deleted = self._del_store[:n]
+        self._codes = None if self._codes_store is None else self._codes_store[:n]
+        for idx, node in self.nodes._live.items():          # Node.vector stays a view of the (possibly moved) array
+            if idx < n:
+                node.vector = self._vec[idx]
+
+    def _adopt(self):
+        """bind the growable stores to freshly assigned arrays"""
+        self._vec_store, self._adj_store, self._deg_store, self._del_store = self._vec, self._adj, self._deg, self._deleted
+        self._codes_store = self._codes
+
+    def _set_codes(self, codes):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        self._codes_store = np.zeros((self._adj_store.shape[0], codes.shape[1]), np.uint8)
+        self._codes_store[:self._n] = codes
+        self._codes = self._codes_store[:self._n]
+
+    def _widen(self, need):
+        """A neighbour set outgrew the row width (reverse edges are never pruned, :106-114): widen every row."""
+        w = max(need, self._adj_store.shape[1] * 2)
+        a = np.zeros((self._adj_store.shape[0], w), np.uint32)
+        a[:, :self._adj_store.shape[1]] = self._adj_store
+        self._adj_store = a
+        self._adj = a[:self._n]
+        self._dirty = True                                   # the device row stride changes: rebuild the mirror
+
     def _append(self, vector, pq_code):
-        v = as_f32(vector).reshape(1, -1)
-        self._vec = v.copy() if self._vec is None or self._n == 0 else np.concatenate([self._vec, v])
-        self._adj = np.concatenate([self._adj, np.zeros((1, self._adj.shape[1]), np.uint32)])
-        self._deg = np.concatenate([self._deg, np.zeros(1, np.int32)])
-        self._deleted = np.concatenate([self._deleted, np.zeros(1, bool)])
-        if pq_code is not None:
-            c = np.asarray(pq_code, np.uint8).reshape(1, -1)
-            if self._codes is None:
-                self._codes = np.zeros((self._n, c.shape[1]), np.uint8)
-            self._codes = np.concatenate([self._codes, c])
-        elif self._codes is not None:
-            self._codes = np.concatenate([self._codes, np.zeros((1, self._codes.shape[1]), np.uint8)])
+        v = as_f32(vector).reshape(-1)
+        if pq_code is not None and self._codes_store is None:
+            self._set_codes(np.zeros((self._n, np.asarray(pq_code).size), np.uint8))
+        self._reserve(self._n + 1, v.size)
+        i = self._n
         self._n += 1
-        self._dirty = True
+        self._views()
+        self._vec[i] = v
+        self._adj[i] = 0; self._deg[i] = 0; self._deleted[i] = False
+        if self._codes is not None:
+            self._codes[i] = 0 if pq_code is None else np.asarray(pq_code, np.uint8).reshape(-1)
 
     def _sync(self):
         if self.nodes._flush():
@@ -177,34 +246,64 @@ class VamanaGraphWithPQ:
         rec[:, D:D + w] = adj
         return rec
 
+    def _device_rows(self, rows=None):
+        """Adjacency rows as the in-memory searches of the reference see them: true degree, unused slots = no neighbour."""
+        adj = (self._adj if rows is None else self._adj[rows]).copy()
+        deg = self._deg if rows is None else self._deg[rows]
+        adj[np.arange(adj.shape[1])[None, :] >= deg[:, None]] = 0xFFFFFFFF
+        return adj
+
     def gpu_index(self) -> GpuIndex:
-        """Device mirror of the arrays.  Rows are uploaded exactly as save_index would write them (0-padded)."""
+        """Device mirror of the arrays, patched in place after mutations (O(rows touched))."""
         self._sync()
+        has_pq = self.pq_model is not None and getattr(self.pq_model, "is_fitted", False) and self._codes is not None
+        if self._gpu is not None and not self._dirty and (self._gpu.M > 0) != bool(has_pq):
+            self._dirty = True
         if self._gpu is None or self._dirty:
             if self._gpu is not None:
                 self._gpu.close()
-            w = self._adj.shape[1]
-            adj = self._adj.copy()
-            adj[np.arange(w)[None, :] >= self._deg[:, None]] = 0
             cb = None
-            if self.pq_model is not None and getattr(self.pq_model, "is_fitted", False):
+            if has_pq:
                 from .io.diskann_persist import codebook_of
                 cb = self.pq_model.codebook() if hasattr(self.pq_model, "codebook") else codebook_of(self.pq_model)
             codes = self._codes if cb is not None else None
-            self._gpu = GpuIndex.from_arrays(self._vec, adj, codes, cb, self.medoid_idx or 0, self.device)
+            self._gpu = GpuIndex.from_arrays(self._vec, self._device_rows(), codes, cb, self.medoid_idx or 0, self.device)
             if self._deleted.any():
                 m = np.ascontiguousarray(self._deleted, np.uint8)
                 check(lib().dr_index_set_deleted(self._gpu._h, ptr(m)), "dr_index_set_deleted")
+            self._gpu_n = self._n
             self._dirty = False
-        return self._gpu
+            self._rows_dirty.clear(); self._vec_dirty.clear(); self._del_dirty.clear()
+            return self._gpu
+        g = self._gpu
+        if self._n > self._gpu_n:                                              # appended nodes
+            lo = self._gpu_n
+            g.append(self._vec[lo:], self._codes[lo:] if g.M > 0 else None)
+            self._rows_dirty.update(i for i in range(lo, self._n) if self._deg[i] > 0)
+            self._del_dirty.update(i for i in range(lo, self._n) if self._deleted[i])
+            self._gpu_n = self._n
+        if self._vec_dirty:
+            rows = np.fromiter(sorted(self._vec_dirty), np.int64)
+            g.patch_vectors(rows, self._vec[rows], self._codes[rows] if g.M > 0 else None)
+            self._vec_dirty.clear()
+        if self._rows_dirty:
+            rows = np.fromiter(sorted(self._rows_dirty), np.int64)
+            g.patch_rows(rows, self._device_rows(rows))
+            self._rows_dirty.clear()
+        if self._del_dirty:
+            rows = np.fromiter(sorted(self._del_dirty), np.int64)
+            g.set_deleted_rows(rows, self._deleted[rows].astype(np.uint8))
+            self._del_dirty.clear()
+        return g
 
     # ---- reference API -----------------------------------------------------------------------------------
     def set_pq_model(self, pq_model):
         self.pq_model = pq_model
         if pq_model and pq_model.is_fitted and self._n > 0:
             print("重新編碼所有向量...")
-            self._codes = pq_model.encode(self._vec)
-            self.nodes._live.clear()
+            self._set_codes(pq_model.encode(self._vec))
+            for idx, node in self.nodes._live.items():
+                node.pq_code = self._codes[idx]
             self._dirty = True
             print(f"完成 {self._n} 個向量的 PQ 編碼")
 
@@ -223,8 +322,12 @@ class VamanaGraphWithPQ:
         self.use_pq_for_search = enable
         print("已啟用 PQ 加速搜索" if enable else "已禁用 PQ 加速搜索，使用精確距離計算")
 
-    def insert_node(self, idx, vector, pq_code=None, L_insert=None):
-        """vamana_graph.py:58-114: search for candidates, RobustPrune(alpha=1.0), add reverse edges (no re-prune)."""
+    def insert_node(self, idx, vector, pq_code=None, L_insert=None, *, robust=False):
+        """vamana_graph.py:58-114: greedy search for L candidates from the medoid, `robust_prune_cython(alpha=1.0)`, reverse
+        edges without a re-prune.  What the reference's prune does there is keep the R NEAREST candidates: its removal loop
+        rebinds the list it is iterating over, so no candidate is ever dropped (cython_utils.pyx:147-165), and the exact
+        distance is compute_distance's l2 branch (the metric string lands in the query_vector slot, vamana_graph.py:273).
+        That is the default here — same neighbour sets as the reference; robust=True runs a real RobustPrune instead."""
         vector = as_f32(vector)
         if idx in self.nodes:
             node = self.nodes[idx]
@@ -234,7 +337,9 @@ class VamanaGraphWithPQ:
                 node.vector = self._vec[idx]
                 node.pq_code = pq_code
                 node.neighbors.clear()
-                self._dirty = True
+                if pq_code is not None and self._codes is not None:
+                    self._codes[idx] = np.asarray(pq_code, np.uint8).reshape(-1)
+                self._vec_dirty.add(int(idx))
                 print(f"節點 {idx} 已重新啟用。")
             else:
                 raise ValueError(f"節點 {idx} 已存在。")
@@ -253,7 +358,10 @@ class VamanaGraphWithPQ:
                 return
         L_val = L_insert if L_insert is not None else self.R * 2
         cands = greedy_search_cython(self, start, self.nodes[idx].vector, L_val, compute_query_distance)
-        robust_prune_cython(self, idx, set(cands), 1.0, self.R, compute_distance)
+        if robust:
+            _graph_prune(self, idx, set(cands), 1.0, self.R)
+        else:
+            _graph_prune_nearest(self, idx, set(cands), self.R)
         for nb in list(self.nodes[idx].neighbors):
             if nb in self.nodes and not self.nodes[nb].is_deleted:
                 self.add_edge(nb, idx)
@@ -279,6 +387,7 @@ class VamanaGraphWithPQ:
                                  distance_metric if distance_metric is not None else self.distance_metric)
         # ids stay sparse in the reference (dict keyed by the old ids); the array form needs dense ids, so the
         # deleted slots stay in place as isolated, masked nodes
+        self.nodes._flush()
         w = self._adj.shape[1]
         self._adj[:] = 0
         self._deg[:] = 0
@@ -289,7 +398,7 @@ class VamanaGraphWithPQ:
         self._deg[live] = np.minimum(t._deg, tw)
         if t._codes is not None:
             if self._codes is None:
-                self._codes = np.zeros((self._n, t._codes.shape[1]), np.uint8)
+                self._set_codes(np.zeros((self._n, t._codes.shape[1]), np.uint8))
             self._codes[live] = t._codes
         self.medoid_idx = int(live[t.medoid_idx]) if t.medoid_idx is not None else None
         self.nodes._live.clear()
@@ -401,49 +510,72 @@ def _live_start(g, start_idx):
     return int(start_idx)
 
 
-def _graph_search(graph, start_idx, q, L):
-    """greedy_search_cython semantics: <= L ids, ascending traversal distance."""
+def _graph_search(graph, start_idx, q, L, ignore_deleted=False):
+    """greedy_search_cython semantics: <= L ids, ascending traversal distance.  ignore_deleted: the Python-level greedy_search /
+    greedy_search_optimized never look at is_deleted (vamana_graph.py:607-640, 762-793)."""
     g = _as_graph(graph)
     if g.distance_metric not in ('l2', 'cosine') and not _pq_on(g):
         raise ValueError(f"unknown distance_metric {g.distance_metric!r}")
-    start = _live_start(g, start_idx)
+    start = int(start_idx) if ignore_deleted else _live_start(g, start_idx)
     if start is None:
         return []
     idx = g.gpu_index()
-    check(lib().dr_index_set_start(idx._h, start))
     # compute_query_distance (:301-329): ADC when PQ search is enabled, else 1 - cos for 'cosine', else squared L2
     dist = "pq" if _pq_on(g) else ("cosine" if g.distance_metric == 'cosine' else "exact")
-    r = idx.search(q[None, :], k=1, L=L, W=1, dist=dist, rerank=False, want_list=True)
+    r = idx.search(q[None, :], k=1, L=L, W=1, dist=dist, rerank=False, want_list=True, start=start,
+                   ignore_deleted=ignore_deleted)
     n = int(r.list_len[0])
     return [int(x) for x in r.list_ids[0, :n]]
 
 
-def _graph_prune(graph, point_idx, candidate_set, alpha, R):
-    """robust_prune_cython semantics (exact distances; the reference's PQ argument-slot bug is not reproduced)."""
+def _prune_inputs(graph, point_idx, candidate_set, keep_self=False):
     g = _as_graph(graph)
     g._sync()
-    cands = np.array(sorted(int(c) for c in candidate_set if 0 <= int(c) < g._n and not g._deleted[int(c)] and int(c) != point_idx),
-                     np.int64)
+    cands = np.array(sorted(int(c) for c in candidate_set
+                            if 0 <= int(c) < g._n and not g._deleted[int(c)] and (keep_self or int(c) != point_idx)), np.int64)
+    return g, cands
+
+
+def _store_neighbors(graph, g, point_idx, new):
+    graph.nodes[point_idx].neighbors = new
+    if g is not graph:
+        g.nodes[point_idx].neighbors = set(new)
+
+
+def _graph_prune(graph, point_idx, candidate_set, alpha, R):
+    """A real RobustPrune (DiskANN alg. 2) on exact squared L2: what robust_prune_cython / robust_prune[_with_pq] are meant to
+    compute.  The reference's own loops never drop a candidate (they rebind the list they iterate over, cython_utils.pyx:147-165,
+    vamana_graph.py:424-441) and so return the R nearest; `_graph_prune_nearest` is that behaviour."""
+    g, cands = _prune_inputs(graph, point_idx, candidate_set)
     sel = np.empty(max(R, 1), np.int32)
-    n_out = np.zeros(1, np.int32)
     import ctypes as C
     cv = np.ascontiguousarray(g._vec[cands]) if cands.size else np.zeros((0, g._vec.shape[1]), np.float32)
     pv = np.ascontiguousarray(g._vec[point_idx])
     cnt = C.c_int32(0)
     check(lib().dr_robust_prune(ptr(pv), ptr(cv), int(cands.size), g._vec.shape[1], float(alpha), int(R), ptr(sel), C.byref(cnt),
                                 g.device), "dr_robust_prune")
-    new = set(int(cands[i]) for i in sel[:cnt.value])
-    graph.nodes[point_idx].neighbors = new
-    if g is not graph:
-        g.nodes[point_idx].neighbors = set(new)
+    _store_neighbors(graph, g, point_idx, set(int(cands[i]) for i in sel[:cnt.value]))
 
 
-def robust_prune_with_pq(graph, point_idx, candidate_set, alpha, R):
-    _graph_prune(graph, point_idx, candidate_set, alpha, R)
+def _graph_prune_nearest(graph, point_idx, candidate_set, R):
+    """The reference's prune as it behaves (see _graph_prune): the R nearest live candidates by squared L2, ties by id
+    (`candidates_with_dist.sort()` on (dist, cid) tuples), inserted into a fresh set in that order."""
+    g, cands = _prune_inputs(graph, point_idx, candidate_set, keep_self=True)   # the reference does not exclude the point itself
+    new = set()
+    if cands.size:
+        d = ops.l2sq_batch(np.ascontiguousarray(g._vec[cands]), np.ascontiguousarray(g._vec[point_idx])[None, :])
+        for i in np.lexsort((cands, d))[:R]:
+            new.add(int(cands[i]))
+    _store_neighbors(graph, g, point_idx, new)
 
 
-def robust_prune(graph, point_idx, candidate_set, alpha, R):
-    _graph_prune(graph, point_idx, candidate_set, alpha, R)
+def robust_prune_with_pq(graph, point_idx, candidate_set, alpha, R, *, reference_semantics=False):
+    (_graph_prune_nearest(graph, point_idx, candidate_set, R) if reference_semantics
+     else _graph_prune(graph, point_idx, candidate_set, alpha, R))
+
+
+def robust_prune(graph, point_idx, candidate_set, alpha, R, *, reference_semantics=False):
+    robust_prune_with_pq(graph, point_idx, candidate_set, alpha, R, reference_semantics=reference_semantics)
 
 
 def generate_initial_neighbors(n_points, R):
@@ -488,11 +620,23 @@ def build_vamana(points, R=16, L=32, alpha=1.2, show_progress=False):
 def greedy_search(graph, start_idx, query_vector, L):
     """Variant B (:607-640).  With PQ enabled the reference dispatches to greedy_search_with_pq, which raises
     NameError (:387); here it runs the PQ traversal."""
+    g = _as_graph(graph)
+    return _graph_search(g, int(start_idx), as_f32(query_vector).ravel(), int(L), ignore_deleted=not _pq_on(g))
+
+
+def greedy_search_optimized(graph, start_idx, query_vector, L):
+    """:762-793: always exact, never looks at is_deleted."""
+    g = _as_graph(graph)
+    was, g.use_pq_for_search = g.use_pq_for_search, False
+    try:
+        return _graph_search(g, int(start_idx), as_f32(query_vector).ravel(), int(L), ignore_deleted=True)
+    finally:
+        g.use_pq_for_search = was
+
+
+def greedy_search_with_pq(graph, start_idx, query_vector, L):
+    """:357-400 (NameError in the reference): the PQ traversal, lazy deletes honoured."""
     return _graph_search(graph, int(start_idx), as_f32(query_vector).ravel(), int(L))
-
-
-greedy_search_optimized = greedy_search
-greedy_search_with_pq = greedy_search
 
 
 def beam_search_with_pq(graph, query_vector, start_idx=None, beam_width=5, k=3, use_pq=True, *, reference_semantics=False):
@@ -507,16 +651,15 @@ def beam_search_with_pq(graph, query_vector, start_idx=None, beam_width=5, k=3, 
         return []
     pq = bool(use_pq and g.pq_model and g.pq_model.is_fitted and g._codes is not None)
     idx = g.gpu_index()
-    check(lib().dr_index_set_start(idx._h, start))
     if reference_semantics:
         if not pq and getattr(g, "distance_metric", "l2") != "l2":
             raise ValueError("reference_semantics=True supports distance_metric='l2' only")
         r = idx.beam_search_c(as_f32(query_vector).reshape(1, -1), k=int(k), beam_width=int(beam_width),
-                              dist="pq" if pq else "exact", sqrt_out=True)
+                              dist="pq" if pq else "exact", sqrt_out=True, start=start)
         return [(r.dists[0, i], int(r.ids[0, i])) for i in range(int(k)) if r.ids[0, i] >= 0]
     L = max(int(k), int(beam_width))
     r = idx.search(as_f32(query_vector).reshape(1, -1), k=int(k), L=L, W=1, dist="pq" if pq else "exact", rerank=False,
-                   sqrt_out=True)
+                   sqrt_out=True, start=start)
     return [(r.dists[0, i], int(r.ids[0, i])) for i in range(int(k)) if r.ids[0, i] >= 0]
 
 
@@ -549,9 +692,9 @@ def beam_search_from_disk(reader, query_vector, start_id, beam_width=8, k=5):
     """Variant D (:719-760): exact search over the index.dat records with list size beam_width; returns the k
     best as (distance, id) with the non-squared distance like np.linalg.norm."""
     idx = _reader_index(reader)
-    check(lib().dr_index_set_start(idx._h, int(start_id)))
     kk = min(int(k), int(beam_width))
-    r = idx.search(as_f32(query_vector).reshape(1, -1), k=kk, L=int(beam_width), W=1, dist="exact", rerank=False, sqrt_out=True)
+    r = idx.search(as_f32(query_vector).reshape(1, -1), k=kk, L=int(beam_width), W=1, dist="exact", rerank=False, sqrt_out=True,
+                   start=int(start_id))
     return [(r.dists[0, i], np.uint32(r.ids[0, i])) for i in range(kk) if r.ids[0, i] >= 0]
 
 
@@ -566,6 +709,5 @@ def search_batch(graph_or_reader, Q, k=10, L=100, W=1, use_pq=None, rerank=True,
         pq = _pq_on(g) if use_pq is None else bool(use_pq)
         if start_idx is None:
             start_idx = g.medoid_idx or 0
-    if start_idx is not None:
-        check(lib().dr_index_set_start(idx._h, int(start_idx)))
-    return idx.search(Q, k=k, L=L, W=W, dist="pq" if pq else "exact", rerank=rerank and pq, **kw)
+    return idx.search(Q, k=k, L=L, W=W, dist="pq" if pq else "exact", rerank=rerank and pq,
+                      start=None if start_idx is None else int(start_idx), **kw)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DR_ABI_VERSION 1
+#define DR_ABI_VERSION 2
 
 typedef struct dr_index dr_index; /* opaque device-resident index (vectors, adjacency, PQ codes, codebook) */
 
@@ -68,7 +68,14 @@ typedef struct dr_search_params {
     int32_t lut_fmt;   /* DR_LUT_F32 (reference arithmetic) | DR_LUT_U8 (throughput: 8-bit table, integer sums) */
     int32_t prefetch;  /* DR_LUT_U8 only, results unchanged; bit mask of L2 prefetches: 1 = the adjacency row of every accepted
                           candidate; 2 = speculative: the rows of the W entries next in line and of accepted candidates ranking
-                          before them; 4 = the PQ code row of a neighbour as soon as it is first seen */
+                          before them; 4 = the PQ code row of a neighbour as soon as it is first seen; 8 = the code rows of the
+                          unseen neighbours of the W entries next in line (one step ahead of the step that needs them);
+                          16 = not an L2 prefetch: the adjacency rows of the W selected entries are bulk-copied to shared memory
+                          while the merge that selected them is still finishing (needs R % 4 == 0 and W <= 16, ignored otherwise) */
+    int32_t start_plus1; /* entry point of THIS call (the reference passes start_idx per call): 0 = the index's own (medoid /
+                          dr_index_set_start), s + 1 = node s.  Per call, so concurrent callers never see each other's start */
+    int32_t ignore_deleted; /* 1: this call does not look at the lazy-delete mask — greedy_search / greedy_search_optimized
+                          (vamana_graph.py:607-640, 762-793) never test is_deleted; greedy_search_cython does (cython_utils.pyx:84-120) */
 } dr_search_params;
 
 /* ---- library ---- */
@@ -101,8 +108,21 @@ int dr_index_info(const dr_index *h, int64_t *N, int32_t *D, int32_t *R, int32_t
 /* lazy deletes (VamanaGraphWithPQ.delete_node, vamana_graph.py:116-125; greedy_search_cython skips is_deleted
  * nodes, cython_utils.pyx:109): mask u8[N] on the host, non-zero = deleted; NULL clears it. */
 int dr_index_set_deleted(dr_index *h, const uint8_t *mask);
-/* change the entry point of the search (the reference passes start_idx per call) */
+/* change the DEFAULT entry point of the search (a per-call start goes in dr_search_params.start_plus1) */
 int dr_index_set_start(dr_index *h, int64_t start);
+/* ---- dynamic updates (VamanaGraphWithPQ.insert_node / delete_node, vamana_graph.py:58-125) ----------------------
+ * O(rows touched) instead of re-uploading the index.  Only for indexes that own their arrays (not dr_index_create_dev).
+ * A row is R slots; a slot holding an id >= N (use 0xFFFFFFFF) is "no neighbour": that is how the live in-memory graph
+ * of the reference looks to its searches (they iterate node.neighbors: true degree, set order, no padding —
+ * vamana_graph.py:607-640, cython_utils.pyx:108), whereas a row read back from index.dat is 0-padded and the padding IS a
+ * neighbour (MMapNodeReader.get_node).  Callers choose by what they write into the unused slots.
+ * dr_index_append: n new nodes (ids N .. N+n-1) with vectors vec f32[n,D], codes u8[n,M] (NULL when the index has none),
+ *   empty rows; storage grows geometrically.  dr_index_patch_rows: adj u32[n,R] replaces rows[i].  dr_index_patch_vectors:
+ *   re-enabling a deleted id with a new vector (:69-74).  dr_index_set_deleted_rows: flags u8[n] for rows[i]. */
+int dr_index_append(dr_index *h, const float *vec, const uint8_t *codes, int64_t n);
+int dr_index_patch_rows(dr_index *h, const int64_t *rows, int64_t n, const uint32_t *adj);
+int dr_index_patch_vectors(dr_index *h, const int64_t *rows, int64_t n, const float *vec, const uint8_t *codes);
+int dr_index_set_deleted_rows(dr_index *h, const int64_t *rows, int64_t n, const uint8_t *flags);
 /* write the index back as an index.dat image (host buffer of N*4*(D+R) bytes) */
 int dr_index_export_records(const dr_index *h, void *records);
 
@@ -122,7 +142,10 @@ int dr_search_batch(dr_index *h, const float *Q, int64_t B, const dr_search_para
                     int32_t *out_ids, float *out_dist, int32_t *out_hops, int32_t *out_visited,
                     int32_t *out_list_ids, float *out_list_dist, int32_t *out_list_len,
                     int32_t *trace, int32_t trace_cap, int32_t *out_status);
-/* device-pointer variant; d_lut NULL = build per chunk in an internal buffer.  Enqueues on stream. */
+/* device-pointer variant; d_lut NULL = build per chunk in an internal buffer.  Enqueues on stream and returns.  The handle's
+ * scratch (ADC tables, work counter, overflow tables) is shared by all calls on the handle: a call enqueued on another stream
+ * first waits (on the device, cudaStreamWaitEvent) for the previous call's kernels, so calls on one handle never overlap each
+ * other; use one handle per concurrent stream to overlap searches. */
 int dr_search_batch_dev(dr_index *h, const float *d_Q, int64_t B, const dr_search_params *p, const float *d_lut,
                         int32_t *d_out_ids, float *d_out_dist, int32_t *d_out_hops, int32_t *d_out_visited,
                         int32_t *d_out_list_ids, float *d_out_list_dist, int32_t *d_out_list_len,
@@ -131,10 +154,11 @@ int dr_search_batch_dev(dr_index *h, const float *d_Q, int64_t B, const dr_searc
  * k-capped beam whose frontier truncation keeps the beam_width WORST entries (:595-596).  dr_search_batch is the search the
  * shims run by default; this entry point returns what the reference's function returns on the same graph, for callers that
  * depend on it (restated in oracle/oracle.c:orc_beam_c and checked against the real reference).  Q f32[B,D] on the host;
- * dist = DR_DIST_PQ (ADC, sequential fp32 sum) or DR_DIST_EXACT (squared L2); the start node is the index's (dr_index_set_start);
+ * dist = DR_DIST_PQ (ADC, sequential fp32 sum) or DR_DIST_EXACT (squared L2); start = the call's start_idx;
  * lazily deleted nodes are skipped like :577-584.  out_ids i32[B,k] (-1 padded) and out_dist f32[B,k] sorted by (dist, id);
  * sqrt_out = 1 reports sqrt(d) like :601.  out_dist / out_hops / out_visited may be NULL. */
 int dr_beam_search_c(dr_index *h, const float *Q, int64_t B, int32_t k, int32_t beam_width, int32_t dist, int32_t sqrt_out,
+                     int64_t start /* -1 = the index's entry point */,
                      int32_t *out_ids, float *out_dist, int32_t *out_hops, int32_t *out_visited);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t dr_launch_count(void);

@@ -260,3 +260,84 @@ def ground_truth(X, Q, k):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+class InMemGraph:
+    """Restatement of the reference's LIVE in-memory graph and its dynamic updates (VamanaGraphWithPQ.insert_node / delete_node,
+    pydiskann/vamana_graph.py:58-125), PQ search off.  Neighbour sets are real Python sets, so their iteration order — the order
+    greedy_search_cython scans a row in (cython_utils.pyx:108) — is CPython's own; the searches see true degrees (rows padded with
+    0xFFFFFFFF, which every search here and on the GPU skips as "no neighbour").
+
+      insert_node(idx, v):  cands = greedy_search_cython(graph, medoid, v, L = 2R, exact)          (:96-99, cython_utils.pyx:72-122)
+                            neighbours = the R nearest live candidates by (l2_distance_fast, id): robust_prune_cython's removal loop
+                            rebinds the list it iterates over, so nothing is ever pruned (cython_utils.pyx:147-165), and the
+                            metric string sits in compute_distance's query_vector slot, leaving its metric at 'l2' (:273)
+                            reverse edges added without a re-prune (:106-114): rows outgrow R
+      delete_node(idx):     lazy flag (:116-125)
+    Distances use l2_distance_fast_cython's compiled summation order (FLAVOR_REFCC).  Pinned against the real reference by
+    tests/test_golden_inmem.py (committed outputs of a 1000-insert script) and tests/test_oracle_vs_reference.py (live)."""
+
+    def __init__(self, vec, rows, deg, medoid, R):
+        self.vec = [np.ascontiguousarray(v, np.float32) for v in vec]
+        self.nbrs = [set() for _ in range(len(self.vec))]
+        for i in range(len(self.vec)):
+            for x in rows[i, :deg[i]]:
+                self.nbrs[i].add(int(x))
+        self.deleted = [False] * len(self.vec)
+        self.medoid, self.R = int(medoid), int(R)
+        self._rows = None
+
+    def rows(self):
+        n = len(self.vec)
+        w = max(1, max(len(s) for s in self.nbrs))
+        if self._rows is None or self._rows.shape[0] < n or self._rows.shape[1] < w:
+            self._rows = np.full((n + 256, max(w, 16) * 2), 0xFFFFFFFF, np.uint32)
+            self._stale = set(range(n))
+        for i in self._stale:
+            nb = list(self.nbrs[i])
+            self._rows[i, :len(nb)] = nb
+            self._rows[i, len(nb):] = 0xFFFFFFFF
+        self._stale = set()
+        return self._rows[:n]
+
+    def _touch(self, i):
+        if self._rows is not None:
+            self._stale.add(i)
+
+    def search(self, q, L, start=None, flavor=FLAVOR_REFCC):
+        start = self.medoid if start is None else start
+        dead = np.array(self.deleted, np.uint8)
+        if dead[start]:                                            # cython_utils.pyx:84-90
+            live = np.flatnonzero(dead == 0)
+            if live.size == 0:
+                return []
+            start = int(live[0])
+        r = search_heap(self.rows(), start, L, vec=np.stack(self.vec), q=q, dist_mode=DIST_L2_SQ, flavor=flavor,
+                        deleted=dead if dead.any() else None)
+        return [int(x) for x in r["ids"]]
+
+    def insert_node(self, idx, v, L_insert=None):
+        assert idx == len(self.vec), "new ids are dense"
+        v = np.ascontiguousarray(v, np.float32)
+        self.vec.append(v); self.nbrs.append(set()); self.deleted.append(False)
+        if self._rows is not None:
+            self._stale.add(idx)
+        if len(self.vec) == 1:
+            self.medoid = idx
+            return
+        cands = self.search(v, L_insert if L_insert is not None else 2 * self.R)
+        scored = sorted((l2sq(self.vec[idx], self.vec[c], FLAVOR_REFCC), c) for c in set(cands) if not self.deleted[c])
+        new = set()
+        for _, c in scored:
+            if len(new) >= self.R:
+                break
+            new.add(c)
+        self.nbrs[idx] = new
+        self._touch(idx)
+        for nb in list(new):
+            if not self.deleted[nb] and nb != idx:
+                self.nbrs[nb].add(idx)
+                self._touch(nb)
+
+    def delete_node(self, idx):
+        self.deleted[idx] = True

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/diskrag_b200.h but not exported"
     assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
-    assert L.dr_abi_version() == 1
+    assert L.dr_abi_version() == 2
 
 
 def test_search_params_layout_matches_header():

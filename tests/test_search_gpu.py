@@ -183,6 +183,19 @@ def test_u8_table_mode_vs_oracle(case, orc, W):
         assert np.array_equal(r2.ids[qi, :min(10, n)], l["ids"][:10])      # no rerank, tiny visited table -> overflow path
 
 
+@pytest.mark.parametrize("W,L", [(8, 100), (4, 48), (12, 48), (16, 20), (1, 32)])
+def test_u8_prefetch_bits_never_change_results(case, W, L):
+    """prefetch bits 8 (next-in-line code rows) and 16 (adjacency rows bulk-copied to shared memory at selection time) move data
+    earlier, nothing else: lists, hops, visited counts and reranked results are those of the oracle-checked mask 5 — also with a
+    tiny visited table (overflow path, where bit 8 switches itself off) and with the visited set in the global table."""
+    c = case
+    ref = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5)
+    for pf, hc in ((13, 0), (21, 0), (29, 0), (31, 0), (29, 256), (29, -1), (16, 0)):
+        r = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=pf, hash_cap=hc)
+        assert np.array_equal(r.list_ids, ref.list_ids) and np.array_equal(r.ids, ref.ids) and np.array_equal(r.dists, ref.dists), (pf, hc)
+        assert np.array_equal(r.hops, ref.hops) and np.array_equal(r.visited, ref.visited), (pf, hc)
+
+
 def test_visited_overflow_table(case, orc):
     """Force a tiny shared-memory visited table so the global overflow table is exercised; results must not change."""
     c = case
@@ -234,7 +247,10 @@ def test_bench_shape_specialisation_vs_oracle(orc):
         r = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=False, lut_fmt="u8", prefetch=5)
         rl = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5)   # generic flags path
         rt = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8tc", prefetch=5)
+        rp = [idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8", prefetch=pf) for pf in (13, 21, 29)]
     assert np.array_equal(r.ids, rl.ids) and np.array_equal(r.dists, rl.dists) and np.array_equal(r.hops, rl.hops)
+    for x in rp:    # the other prefetch masks (one of them is the compiled serving shape, DR_PF_SPEC): same answers
+        assert np.array_equal(r.ids, x.ids) and np.array_equal(r.dists, x.dists) and np.array_equal(r.hops, x.hops) and np.array_equal(r.visited, x.visited)
     for qi in range(c["Q"].shape[0]):
         t8, sc, off = orc.lut_u8(c["codebook"], c["Q"][qi])
         l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False)
