@@ -230,8 +230,8 @@ class VamanaGraphWithPQ:
             self._codes[i] = 0 if pq_code is None else np.asarray(pq_code, np.uint8).reshape(-1)
 
     def _sync(self):
-        if self.nodes._flush():
-            self._dirty = True
+        """Materialised nodes -> arrays; what changed is noted per row (_rows_dirty / _vec_dirty / _del_dirty) for gpu_index()."""
+        self.nodes._flush()
 
     def to_records(self, R=None):
         """index.dat image, u32[N, D+R] (DiskANNPersist.save_index, diskann_persist.py:17-24): short rows 0-padded."""

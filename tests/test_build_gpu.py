@@ -143,7 +143,11 @@ def test_dynamic_updates(data):
     found = vg.greedy_search(g, g.medoid_idx, X[1000], 20)
     assert found[0] == 1000
     g.delete_node(1000)
-    assert 1000 not in vg.greedy_search(g, g.medoid_idx, X[1000], 20)            # deleted nodes are never visited
+    # greedy_search_cython never visits a lazily deleted node (cython_utils.pyx:84-120); the Python-level greedy_search does not
+    # look at is_deleted at all (vamana_graph.py:607-640) and still returns it — both like the reference
+    from diskrag_b200 import cython_utils as cu
+    assert 1000 not in cu.greedy_search_cython(g, g.medoid_idx, X[1000], 20, vg.compute_query_distance)
+    assert vg.greedy_search(g, g.medoid_idx, X[1000], 20)[0] == 1000
     with pytest.raises(ValueError):
         g.delete_node(5000)
     for i in range(0, 100):

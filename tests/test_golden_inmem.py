@@ -30,6 +30,24 @@ def _same_lists(exp_ids, got_ids):
     return len(e) == len(got_ids) and np.array_equal(e, np.asarray(got_ids))
 
 
+def _same_up_to_ties(exp_ids, exp_d, got_ids):
+    """Equal lists, except that ids sharing one distance may come in any order (inside an exact tie the reference's output order
+    is its heap's layout; the device list is ordered by (distance, id))."""
+    n = int((exp_ids >= 0).sum())
+    got = list(got_ids)
+    if len(got) != n:
+        return False
+    i = 0
+    while i < n:
+        j = i
+        while j < n and exp_d[j] == exp_d[i]:
+            j += 1
+        if set(exp_ids[i:j].tolist()) != set(got[i:j]):
+            return False
+        i = j
+    return True
+
+
 def test_fixture_has_short_and_overlong_rows(gi):
     assert gi["deg_built"].min() < gi["R"] and gi["deg_final"].max() > gi["R"]
     assert gi["reenable_raises"] == 1      # the reference cannot re-enable a deleted id (vamana_graph.py:100): not scripted
@@ -91,8 +109,8 @@ def test_gpu_inmemory_searches_equal_the_reference(gi):
         assert okB >= nq - 1, (L, okB)          # exact distances: GPU warp order vs the compiled order, a near-tie may swap two ids
         if True:
             G.use_pq_for_search = True
-            okA = sum(_same_lists(g[f"exp_A_ids_L{L}_built"][qi],
-                                  cu.greedy_search_cython(G, g["medoid"], g["Q"][qi], L, vg.compute_query_distance)) for qi in range(nq))
+            okA = sum(_same_up_to_ties(g[f"exp_A_ids_L{L}_built"][qi], g[f"exp_A_dist_L{L}_built"][qi],
+                                       cu.greedy_search_cython(G, g["medoid"], g["Q"][qi], L, vg.compute_query_distance)) for qi in range(nq))
             assert okA == nq, (L, okA)
     G.close()
 
