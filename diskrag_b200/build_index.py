@@ -20,6 +20,8 @@ from pathlib import Path
 
 import numpy as np
 
+from ._lib import DiskragError
+
 from . import _lib
 from .io.diskann_persist import DiskANNPersist
 from .pq.fast_pq import DiskANNPQ
@@ -121,8 +123,13 @@ def build_index_dir(vectors, index_dir, target_quality: str = "balanced", force_
             if not np.array_equal(pq_model.encode(test), loaded.encode(test)):
                 raise ValueError("PQ 模型保存/加載驗證失敗，請檢查模型序列化問題")
             persist.save_pq_codes(str(index_dir / "pq_codes.bin"), pq_codes)
+        except DiskragError:                                                    # a device failure (out of memory, lost GPU) is not
+            raise                                                               # a PQ-quality problem: never hide it
         except Exception:                                                       # :277-282: PQ failure degrades to exact search
             use_pq, pq_model = False, None
+    if not use_pq:                                                              # no stale / partial PQ files next to use_pq = false
+        for name in ("pq_model.pkl", "pq_codes.bin"):
+            (index_dir / name).unlink(missing_ok=True)
     t_pq = time.time() - t0
 
     graph = build_vamana(vectors, R=R, L=L, alpha=alpha, show_progress=verbose)  # :288 (called WITHOUT the pq model)

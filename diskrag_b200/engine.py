@@ -90,12 +90,24 @@ class GpuIndex:
         N, D, R = int(meta["N"]), int(meta["D"]), int(meta["R"])
         rec = np.memmap(d / "index.dat", dtype=np.uint8, mode="r")
         codes = codebook = None
-        if (d / "pq_codes.bin").exists() and (d / "pq_model.pkl").exists():
+        # search_engine.py:36-70: PQ only when meta says so (default True) and both files are there; anything wrong with them
+        # (stale files of another corpus, wrong size, unreadable pickle) means exact search, as in the reference
+        M = int(meta.get("n_subvectors", 0) or 0)
+        if meta.get("use_pq", True) and M > 0 and (d / "pq_codes.bin").exists() and (d / "pq_model.pkl").exists():
             p = DiskANNPersist(dim=D, R=R)
-            M = int(meta["n_subvectors"])
-            codes = p.load_pq_codes(d / "pq_codes.bin", N, M)
-            codebook = codebook_of(p.load_pq_codebook(d / "pq_model.pkl"))
-        return cls.from_records(rec, N, D, R, codes, codebook, int(meta["medoid_idx"]), device)
+            try:
+                if (d / "pq_codes.bin").stat().st_size != N * M:
+                    raise ValueError(f"pq_codes.bin holds {(d / 'pq_codes.bin').stat().st_size} bytes, expected N*M = {N * M}")
+                codes = p.load_pq_codes(d / "pq_codes.bin", N, M)
+                codebook = codebook_of(p.load_pq_codebook(d / "pq_model.pkl"))
+                if codebook.shape != (M, 256, D // M) or D % M:
+                    raise ValueError(f"pq_model.pkl codebook {codebook.shape} does not match meta (M={M}, D={D})")
+            except _lib.DiskragError:
+                raise
+            except Exception as e:
+                print(f"⚠️  PQ 文件不可用 ({e})，切換到精確搜索模式")
+                codes = codebook = None
+        return cls.from_records(rec, N, D, R, codes, codebook, int(meta.get("medoid_idx", 0)), device)
 
     @classmethod
     def from_device_ptrs(cls, d_vec, d_adj, d_codes, d_codebook, N, D, R, M, medoid, device=0, keepalive=None):

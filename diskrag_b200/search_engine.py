@@ -73,7 +73,8 @@ class GpuSearchEngine:
         t0 = time.time()
         r = self.search_vectors(np.asarray(query_vector, np.float32).reshape(1, -1), k=k, L=L, pq=True)
         dt = time.time() - t0
-        res = [(float(r.dists[0, i]), int(r.ids[0, i])) for i in range(r.ids.shape[1]) if r.ids[0, i] >= 0]
+        # (np.float32 d2, np.uint32 id) like :482-488 (ids come out of MMapNodeReader's uint32 rows there)
+        res = [(np.float32(r.dists[0, i]), np.uint32(r.ids[0, i])) for i in range(r.ids.shape[1]) if r.ids[0, i] >= 0]
         n_pq = int(r.visited[0]); n_exact = int(r.list_len[0])
         self._account(dt, n_exact, n_pq)
         stats = {"search_time": dt, "nodes_visited": n_pq, "exact_distance_computations": n_exact,

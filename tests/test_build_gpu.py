@@ -180,7 +180,7 @@ def test_search_engine_seam(data, tmp_path, orc):
     for throughput in (False, True):
         eng = GpuSearchEngine(tmp_path, throughput=throughput)
         res, stats = eng._pq_accelerated_graph_search(Q[0], k=10, L=60)
-        assert len(res) == 10 and all(res[i][0] <= res[i + 1][0] for i in range(9)) and isinstance(res[0][1], int)
+        assert len(res) == 10 and all(res[i][0] <= res[i + 1][0] for i in range(9)) and isinstance(res[0][1], (int, np.integer))
         assert set(stats) == {"search_time", "nodes_visited", "exact_distance_computations", "pq_distance_computations",
                               "computation_reduction_rate", "search_steps"}
         # returned distances are exact squared L2 (search_engine.py:374-379)

@@ -76,3 +76,36 @@ def test_brute_force_tier_and_force_rebuild(tmp_path):
     assert meta2["use_pq"] and (d / "pq_codes.bin").stat().st_size == 600 * 8
     with pytest.raises(ValueError):
         build_index_dir(X[:10], tmp_path / "tiny")
+
+
+@pytest.mark.gpu
+def test_index_dir_with_unusable_pq_files_falls_back_to_exact_search(tmp_path):
+    """search_engine.py:36-70: use_pq = false in meta, a missing file, or PQ files that do not belong to this index (stale codes of
+    another corpus, wrong size) all mean exact search — never a crash, never a traversal over foreign codes."""
+    import json
+    from diskrag_b200.build_index import build_index_dir
+    from diskrag_b200.engine import GpuIndex
+    from diskrag_b200.search_engine import GpuSearchEngine
+    from diskrag_b200.synth import synth_numpy
+    X = synth_numpy(600, 64, seed=5, K=16, r=8)
+    d = tmp_path / "idx"
+    meta = build_index_dir(X, d, target_quality="balanced", n_subvectors=8, verbose=False)
+    assert meta["use_pq"] and (d / "pq_codes.bin").exists()
+    with GpuIndex.from_dir(d) as idx:
+        assert idx.M == 8
+    # 1. stale codes of another (larger) corpus
+    (d / "pq_codes.bin").write_bytes(b"\0" * (700 * 8))
+    with GpuIndex.from_dir(d) as idx:
+        assert idx.M == 0
+    eng = GpuSearchEngine(d)
+    assert not eng.use_pq and len(eng._exact_graph_search(X[3], k=5)[0]) == 5
+    eng.close()
+    # 2. meta says no PQ although files exist
+    (d / "pq_codes.bin").write_bytes(b"\0" * (600 * 8))
+    m = json.loads((d / "meta.json").read_text()); m["use_pq"] = False
+    (d / "meta.json").write_text(json.dumps(m))
+    with GpuIndex.from_dir(d) as idx:
+        assert idx.M == 0
+    # 3. a rebuild that ends without PQ (too few points) leaves no PQ files behind
+    meta = build_index_dir(X[:200], d, target_quality="balanced", verbose=False, force_rebuild=True)
+    assert not meta["use_pq"] and not (d / "pq_codes.bin").exists() and not (d / "pq_model.pkl").exists()
