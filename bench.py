@@ -8,7 +8,10 @@ One step = one pass of the hot path over one 100k-query batch: ADC-table build +
 
   python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA, through the C ABI)
   python bench.py --impl reference [...]                      the reference's own CPU code (oracle/_ref) on host cores
-Under torchrun each rank drives one GPU; rank 0 prints one JSON line.
+  python bench.py --scaling strong [...]                      configs[2] literally: ONE 100k-query batch split over the N GPUs
+  python bench.py --mode index-sharded [--exchange p2p]       configs[4] shape: every GPU owns a 1.25M x 3072 shard (own graph, PQ),
+                                                              searches all queries on it, partial top-k exchanged and merged
+Under torchrun each rank drives one GPU; rank 0 prints one JSON line (same schema in every mode).
 """
 import argparse
 import ctypes as C
@@ -28,6 +31,10 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "QPS@recall10>=0.95"
 UNIT = "queries/s"
+# the arithmetic the path computes in, per table mode (the final rerank and every reported distance are fp32 in all of them)
+DTYPES = {"f32": "f32 (fp32 ADC table in the reference's operation order, fp32 sums, fp32 rerank)",
+          "u8": "f32 rerank; u8 ADC table (exact fp32 build), integer sums",
+          "u8tc": "f32 rerank; u8 ADC table (tf32 tensor-core build), integer sums"}
 
 
 def parse():
@@ -36,8 +43,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--dim", type=int, default=1536)
+    ap.add_argument("--mode", default="query-sharded", choices=["query-sharded", "index-sharded"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="query-sharded: weak = --queries per GPU; strong = --queries in total, split over the GPUs")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="index-sharded: one packed NCCL all-to-all, or the search kernel's epilogue storing into peer memory")
+    ap.add_argument("--n", type=int, default=None, help="corpus rows per GPU (default 1M; index-sharded: 1.25M per shard)")
+    ap.add_argument("--dim", type=int, default=None, help="default 1536; index-sharded: 3072")
     ap.add_argument("--R", type=int, default=32)
     ap.add_argument("--Lbuild", type=int, default=64)
     ap.add_argument("--M", type=int, default=192)
@@ -54,20 +66,53 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-points", action="store_true", help="skip the other operating points / parity-mode legs (kernel A/B runs)")
     ap.add_argument("--cuda-profile", action="store_true", help="wrap one extra step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.n is None:
+        a.n = 1_250_000 if a.mode == "index-sharded" else 1_000_000
+    if a.dim is None:
+        a.dim = 3072 if a.mode == "index-sharded" else 1536
+    return a
+
+
+def pin_rank_to_local_cpus(local, world):
+    """Each rank on its own cores, on the NUMA node of its GPU when sysfs says which: the pinned host buffers of the end-to-end leg
+    are then allocated node-local and 8 ranks do not fight over one node's memory controllers.  Best effort, silent."""
+    try:
+        import torch
+        cpus = sorted(os.sched_getaffinity(0))
+        node_cpus = None
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        if bus is not None:
+            dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+            p = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node")
+            if p.exists() and int(p.read_text()) >= 0:
+                lst = Path(f"/sys/devices/system/node/node{int(p.read_text())}/cpulist").read_text().strip()
+                node_cpus = []
+                for part in lst.split(","):
+                    lo, _, hi = part.partition("-")
+                    node_cpus += list(range(int(lo), int(hi or lo) + 1))
+                node_cpus = [c for c in node_cpus if c in cpus]
+        pool = node_cpus if node_cpus else cpus
+        per = max(1, len(pool) // max(1, min(world, len(pool))))
+        mine = pool[(local * per) % len(pool):(local * per) % len(pool) + per] or pool
+        os.sched_setaffinity(0, mine)
+        return {"cpus": len(mine), "numa_local": bool(node_cpus)}
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------------
 # setup shared by both arms: synthetic corpus, PQ, graph (all on the GPU, untimed)
 # ------------------------------------------------------------------------------------------------------
-def build_index(a, dev):
+def build_index(a, dev, data_seed=20242, sample_seed=None, build_seed=1234):
     import torch
     from diskrag_b200._lib import check, lib
     from diskrag_b200.synth import synth_torch
     st = torch.cuda.current_stream(dev).cuda_stream
     N, D, R, M = a.n, a.dim, a.R, a.M
     t0 = time.time()
-    X = synth_torch(N, D, seed=20242, device=dev)
+    X = synth_torch(N, D, seed=data_seed, device=dev) if sample_seed is None else synth_torch(N, D, seed=data_seed, sample_seed=sample_seed, device=dev)
     # medoid: sampled, as compute_approximate_medoid_cython does (1000 samples), through our kernel
     g = torch.Generator(device=dev); g.manual_seed(77)
     smp = torch.randperm(N, generator=g, device=dev)[:1000].to(torch.int32).cpu().numpy()
@@ -84,7 +129,7 @@ def build_index(a, dev):
     t2 = time.time()
     adj = torch.empty((N, R), dtype=torch.int32, device=dev)
     deg = torch.empty(N, dtype=torch.int32, device=dev)
-    check(lib().dr_vamana_build_dev(X.data_ptr(), N, D, R, a.Lbuild, 1.2, med, 1234, adj.data_ptr(), deg.data_ptr(), dev.index, st),
+    check(lib().dr_vamana_build_dev(X.data_ptr(), N, D, R, a.Lbuild, 1.2, med, build_seed, adj.data_ptr(), deg.data_ptr(), dev.index, st),
           "dr_vamana_build_dev")
     torch.cuda.synchronize(dev)
     t3 = time.time()
@@ -197,6 +242,7 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    affinity = pin_rank_to_local_cpus(local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if a.lut == "u8tc" and ((a.dim // a.M) % 8 != 0 or a.M % 4 != 0):
@@ -204,8 +250,19 @@ def run_ours(a):
     X, adj, deg, codes, cb, med, info = build_index(a, dev)
     idx = engine.GpuIndex.from_device_ptrs(X.data_ptr(), adj.data_ptr(), codes.data_ptr(), cb.data_ptr(), a.n, a.dim, a.R, a.M,
                                            med, local, keepalive=(X, adj, codes, cb))
-    B, k = a.queries, a.k
-    Q = synth_torch(B, a.dim, seed=20242, sample_seed=1000 + rank, device=dev)     # each rank: its own query shard
+    k = a.k
+    if a.scaling == "strong":
+        # BASELINE configs[2] literally: ONE --queries batch, query-sharded over the ranks (contiguous slices); the index is
+        # replicated, there is no exchange on the data path, the slices' results are concatenated by the caller
+        from diskrag_b200.dist import query_slice
+        qlo, qhi = query_slice(a.queries, rank, world)
+        B = qhi - qlo
+        Q = synth_torch(a.queries, a.dim, seed=20242, sample_seed=1000, device=dev)[qlo:qhi].contiguous()
+        total_queries = a.queries
+    else:
+        B = a.queries
+        Q = synth_torch(B, a.dim, seed=20242, sample_seed=1000 + rank, device=dev)     # each rank: its own query shard
+        total_queries = world * B
     p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut, hash_cap=a.hash_cap,
                            prefetch=int(a.prefetch))
     ids = torch.empty((B, k), dtype=torch.int32, device=dev); dd = torch.empty((B, k), dtype=torch.float32, device=dev)
@@ -253,7 +310,7 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    value = world * B * a.steps / (ms_total / 1e3)
+    value = total_queries * a.steps / (ms_total / 1e3)
 
     # ---- roofline of the search kernel: algorithmic bytes / its own launch durations (CUDA events in the library)
     h_np, v_np, l_np = hops.cpu().numpy(), vis.cpu().numpy(), llen.cpu().numpy()
@@ -267,18 +324,27 @@ def run_ours(a):
     per_launch_bytes = abytes * 2 / max(1, k_launches)
     per_launch_ms = k_ms / max(1, k_launches)
     achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
-    traffic = None
+    traffic = traffic_src = None
     tf = ROOT / "profiles" / "search_kernel_traffic.json"
-    if tf.exists():
+    if tf.exists() and a.lut != "f32":
         try:
-            # one ncu --set full capture (scripts/profile.sh + scripts/summarize_profile.py), scaled to this launch size
-            traffic = round(json.loads(tf.read_text())["dram_bytes_per_query"] * (B * 2 / max(1, k_launches)))
+            # NOT measured in this run: one ncu --set full capture of this kernel (scripts/profile.sh + scripts/summarize_profile.py),
+            # dram__bytes_read.sum + dram__bytes_write.sum per query, scaled to this launch size; the file says which capture
+            tj = json.loads(tf.read_text())
+            traffic = round(tj["dram_bytes_per_query"] * (B * 2 / max(1, k_launches)))
+            traffic_src = tj.get("source", "profiles/search_kernel_traffic.json")
         except Exception:
-            traffic = None
+            traffic = traffic_src = None
+    tab_b = a.M * (256 if a.lut != "f32" else 1024)       # the ADC table of one query: written by the table kernels, read back by the search
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "kernel": "search_fast_kernel" if a.lut != "f32" else "search_kernel",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "search_fast_kernel" if a.lut != "f32" else "search_kernel",
                 "kernel_ms_per_launch": round(per_launch_ms, 3), "launches_per_step": k_launches // 2,
-                "algorithmic_bytes_per_query": round(abytes / B, 1), "kernel_share_of_step": round((k_ms / 2) / (ms_total / a.steps), 3)}
+                "algorithmic_bytes_per_query": round(abytes / B, 1), "kernel_share_of_step": round((k_ms / 2) / (ms_total / a.steps), 3),
+                # NOT in the algorithmic bytes (SURVEY §8d excludes table traffic): the table's round trip through HBM
+                "adc_table_bytes_per_query": {"written_by_table_kernels": tab_b, "read_by_search_kernel": tab_b},
+                "frac_counting_table_read": round((abytes / B + tab_b) * (B * 2 / max(1, k_launches)) / (per_launch_ms / 1e3) / 1e9 / peak, 4),
+                "step_level_frac": round(abytes / (ms_total / a.steps / 1e3) / 1e9 / peak, 4)}
 
     # ---- e2e: host buffers through the public API (H2D of the queries and D2H of the results inside) ------
     Qh = torch.empty((B, a.dim), dtype=torch.float32, pin_memory=True); Qh.copy_(Q)
@@ -300,14 +366,37 @@ def run_ours(a):
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * a.steps / float(te.item())
+    e2e_val = total_queries * a.steps / float(te.item())
     assert np.array_equal(idn, ids.cpu().numpy()), "host-API results differ from the device-API results"
     e2e = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(B * a.dim * 4),
            "d2h_bytes_per_step": int(B * k * 8 + 3 * B * 4)}
 
     # ---- the recall / throughput trade-off around the named configuration (context for "QPS at recall >= 0.95"; 1 GPU only)
-    points = None
+    points = parity = None
     if world == 1 and not a.no_points:
+        # ---- the reference-identical mode on the same index: variant A (f32 table in the reference's operation order, sequential
+        # ADC, W = 1: bit-exact with cython_utils.pyx:72-122 by tests/) + the exact rerank of search_engine.py:374-379 — its own
+        # throughput and roofline fraction, and how many of the bench mode's top-k id SETS equal its answer
+        npar = min(B, 20000)
+        bench_ids = ids[:npar].cpu().numpy().copy()
+        pr = engine.make_params(k=k, L=a.L, W=1, dist="pq", adc_order="seq", rerank=True, lut="f32")
+        runp = lambda: idx.search_dev(Q.data_ptr(), npar, pr, ids.data_ptr(), dd.data_ptr(), hops.data_ptr(), vis.data_ptr(),
+                                      d_list_len=llen.data_ptr(), d_status=stat.data_ptr(), stream=stream)
+        runp(); torch.cuda.synchronize(dev)
+        ref_ids = ids[:npar].cpu().numpy().copy()
+        pbytes = algorithmic_bytes(a, hops[:npar].cpu().numpy(), vis[:npar].cpu().numpy(), llen[:npar].cpu().numpy())
+        idx.kernel_timing(True)
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        f0.record(); runp(); runp(); f1.record(); torch.cuda.synchronize(dev)
+        pk_ms, pk_n = idx.kernel_timing(False)
+        same = np.array([set(bench_ids[i].tolist()) == set(ref_ids[i].tolist()) for i in range(npar)])
+        parity = {"reference_mode": "variant A: f32 table (reference operation order), sequential ADC, W=1, L=%d + exact rerank" % a.L,
+                  "queries": npar, "qps": round(2 * npar / (f0.elapsed_time(f1) / 1e3), 1),
+                  "recall_at_10": round(recall(ref_ids[:ngt], gt, k), 4),
+                  "kernel": "search_kernel", "kernel_ms_per_launch": round(pk_ms / max(1, pk_n), 3),
+                  "roofline_frac": round(pbytes * 2 / max(1, pk_n) / (pk_ms / max(1, pk_n) / 1e3) / 1e9 / peak, 4),
+                  "bench_mode_top%d_sets_equal_to_reference_mode" % k: f"{int(same.sum())}/{npar}",
+                  "fraction": round(float(same.mean()), 4)}
         points = []
         for Lp in (50, 64, 80):
             pp = engine.make_params(k=k, L=Lp, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut,
@@ -326,16 +415,167 @@ def run_ours(a):
         cpu_base = cpu_baseline_port(a, X, adj, codes, cb, med, Q, idn)
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-               "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic",
+               "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+               "dtype": DTYPES[a.lut], "data": "synthetic",
                "config": {"workload": f"{a.n}x{a.dim} synthetic unit-norm, Vamana R={a.R} (GPU-built, Lbuild={a.Lbuild}, alpha=1.2), "
-                                      f"PQ M={a.M}, L={a.L}, W={a.W}, adc={a.adc}, table={a.lut}, rerank, top-{a.k}",
-                          "queries_per_gpu_per_step": B, "index": "replicated", "queries": "sharded", "recall_at_10": round(rec, 4),
+                                      f"PQ M={a.M}, L={a.L}, W={a.W}, adc={a.adc}, table={a.lut}, rerank, top-{a.k}"
+                                      + (f"; ONE {a.queries}-query batch split over the GPUs" if a.scaling == "strong" else ""),
+                          "queries_per_gpu_per_step": B, "queries_per_step_total": total_queries, "index": "replicated",
+                          "queries": "sharded", "recall_at_10": round(rec, 4), "parity_mode": parity, "cpu_affinity": affinity,
                           "recall_queries": ngt, "l2_flush": f"inputs larger than L2 (index {(a.n * (a.dim * 4 + a.R * 4 + a.M)) / 1e9:.1f} GB, per-step ADC tables {B * a.M * (256 if a.lut != 'f32' else 1024) / 1e9:.1f} GB, queries {B * a.dim * 4 / 1e9:.2f} GB)",
                           "mean_hops": round(float(h_np.mean()), 1), "mean_visited": round(float(v_np.mean()), 1), "setup": info,
                           "other_operating_points": points},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
         emit(out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_index_sharded(a):
+    """BASELINE configs[4] shape under the same contract: rank r owns shard r (a.n x a.dim rows, its OWN Vamana graph, medoid and PQ),
+    every rank searches ALL --queries queries on its shard (throughput kernel, fused exact rerank), the per-shard top-k lists are
+    exchanged as packed 64-bit keys and k-way merged on the rank that owns the query slice.  Exchange: one NCCL all-to-all of a
+    device-packed buffer (--exchange nccl) or none at all — the search kernel's epilogue stores into the owner's buffer over
+    NVLink peer memory (--exchange p2p).  value = queries answered over the WHOLE corpus per second; "weak": the corpus grows with N."""
+    import torch
+    import torch.distributed as dist
+    from diskrag_b200 import dist as DD, engine
+    from diskrag_b200.synth import synth_torch
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local); torch.cuda.set_device(dev)
+    affinity = pin_rank_to_local_cpus(local, world)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if a.lut == "u8tc" and ((a.dim // a.M) % 8 != 0 or a.M % 4 != 0):
+        a.lut = "u8"
+    a_shard = argparse.Namespace(**vars(a))
+    X, adj, deg, codes, cb, med, info = build_index(a_shard, dev, data_seed=20245, sample_seed=rank, build_seed=1234 + rank)
+    idx = engine.GpuIndex.from_device_ptrs(X.data_ptr(), adj.data_ptr(), codes.data_ptr(), cb.data_ptr(), a.n, a.dim, a.R, a.M, med, local,
+                                           keepalive=(X, adj, codes, cb))
+    B, k = a.queries, a.k
+    Q = synth_torch(B, a.dim, seed=20245, sample_seed=100_000, device=dev)          # the SAME batch on every rank
+    p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, lut=a.lut, prefetch=int(a.prefetch))
+    ids = torch.empty((B, k), dtype=torch.int32, device=dev); dd = torch.empty((B, k), dtype=torch.float32, device=dev)
+    hops = torch.empty(B, dtype=torch.int32, device=dev); vis = torch.empty(B, dtype=torch.int32, device=dev)
+    llen = torch.empty(B, dtype=torch.int32, device=dev); stat = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    offset = rank * a.n
+    qlo, qhi = DD.query_slice(B, rank, world)
+    peer = DD.PeerExchange(idx, B, k, offset, local) if (world > 1 and a.exchange == "p2p") else None
+
+    def search(qptr=None):
+        idx.search_dev(qptr or Q.data_ptr(), B, p, ids.data_ptr(), dd.data_ptr(), hops.data_ptr(), vis.data_ptr(),
+                       d_list_len=llen.data_ptr(), d_status=stat.data_ptr(), stream=stream)
+
+    def step(qptr=None):
+        search(qptr)
+        if world == 1:
+            return ids, dd
+        if peer is not None:
+            return peer.merge()
+        return DD.index_sharded_topk(ids, dd, offset, gather=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    mi, md = step(); torch.cuda.synchronize(dev)
+    assert int(stat.abs().sum().item()) == 0, "search reported a non-zero status"
+    # global exact ground truth for the first queries: per-shard exact top-k, the same packed exchange (NCCL path)
+    ng = min(a.gt_queries, B)
+    xn = (X * X).sum(1)
+    prev = torch.backends.cuda.matmul.allow_tf32; torch.backends.cuda.matmul.allow_tf32 = False
+    ei = torch.empty((ng, k), dtype=torch.int32, device=dev); ed = torch.empty((ng, k), dtype=torch.float32, device=dev)
+    for s0 in range(0, ng, 100):
+        d = xn[None, :] - 2.0 * (Q[s0:s0 + 100] @ X.T) + 1.0
+        t = d.topk(k, largest=False)
+        ei[s0:s0 + 100] = t.indices.to(torch.int32); ed[s0:s0 + 100] = t.values
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    if world > 1:
+        ti, _ = DD.index_sharded_topk(ei, ed, offset, gather=True)
+        ai, _ = DD.index_sharded_topk(ids[:ng].contiguous(), dd[:ng].contiguous(), offset, gather=True)
+        ti, ai = ti.cpu().numpy(), ai.cpu().numpy()
+        if peer is not None:                       # the peer-routed exchange must give exactly what the NCCL exchange gives
+            ni, nd = DD.index_sharded_topk(ids, dd, offset, gather=False)
+            assert torch.equal(ni, mi) and torch.equal(nd, md), "p2p exchange differs from the NCCL exchange"
+    else:
+        ti, ai = ei.cpu().numpy(), ids[:ng].cpu().numpy()
+    rec = recall(ai, ti, k)
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    l0 = engine.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = engine.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = B * a.steps / (ms_total / 1e3)
+    h_np, v_np, l_np = hops.cpu().numpy(), vis.cpu().numpy(), llen.cpu().numpy()
+    abytes = algorithmic_bytes(a, h_np, v_np, l_np)
+    idx.kernel_timing(True)
+    for _ in range(2):
+        search()
+    torch.cuda.synchronize(dev)
+    k_ms, k_launches = idx.kernel_timing(False)
+    peak, peak_src = measured_peak()
+    per_launch_ms = k_ms / max(1, k_launches)
+    achieved = abytes * 2 / max(1, k_launches) / (per_launch_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "peak_source": peak_src, "kernel": "search_fast_kernel (this rank's shard)", "kernel_ms_per_launch": round(per_launch_ms, 3),
+                "algorithmic_bytes_per_query": round(abytes / B, 1), "kernel_share_of_step": round((k_ms / 2) / (ms_total / a.steps), 3)}
+    # e2e: the batch arrives from pinned host memory every step, this rank's merged slice goes back to the host
+    Qh = torch.empty((B, a.dim), dtype=torch.float32, pin_memory=True); Qh.copy_(Q)
+    Qd = torch.empty_like(Q)
+    oi_h = torch.empty((qhi - qlo, k), dtype=torch.int32, pin_memory=True); od_h = torch.empty((qhi - qlo, k), dtype=torch.float32, pin_memory=True)
+
+    def step_e2e():
+        Qd.copy_(Qh, non_blocking=True)
+        ri, rd = step(Qd.data_ptr())
+        oi_h.copy_(ri[:qhi - qlo], non_blocking=True); od_h.copy_(rd[:qhi - qlo], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": round(B * a.steps / float(te.item()), 1), "unit": UNIT, "h2d_bytes_per_step": int(B * a.dim * 4),
+           "d2h_bytes_per_step": int((qhi - qlo) * k * 8)}
+    if rank == 0:
+        emit({"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+              "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": DTYPES[a.lut], "data": "synthetic",
+              "config": {"workload": f"index-sharded (BASELINE configs[4] shape): {world} shard(s) x {a.n} x {a.dim} synthetic unit-norm = corpus "
+                                     f"{world * a.n}, per-shard Vamana R={a.R} (GPU-built) + PQ M={a.M}, L={a.L}, W={a.W}, table={a.lut}, rerank, "
+                                     f"top-{k}; every GPU searches the whole {B}-query batch on its shard",
+                         "exchange": ("none (1 shard)" if world == 1 else
+                                      ("search-kernel epilogue stores packed (dist,id) keys into the owner rank's buffer over NVLink peer memory, "
+                                       "barrier, k-way merge kernel" if peer is not None else
+                                       "device-packed (dist,id) keys, ONE NCCL all_to_all_single, k-way merge kernel")),
+                         "exchange_bytes_per_rank_per_step": 0 if world == 1 else B * k * 8,
+                         "queries_per_step_total": B, "index": "sharded", "queries": "replicated", "recall_at_10": round(rec, 4),
+                         "recall_is": "global: merged top-10 vs the exact top-10 over the whole sharded corpus", "recall_queries": ng,
+                         "l2_flush": f"inputs larger than L2 (shard {(a.n * (a.dim * 4 + a.R * 4 + a.M)) / 1e9:.1f} GB per GPU)",
+                         "mean_hops": round(float(h_np.mean()), 1), "mean_visited": round(float(v_np.mean()), 1), "setup": info,
+                         "cpu_affinity": affinity},
+              "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+              "cpu_baseline": None})
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -470,5 +710,7 @@ if __name__ == "__main__":
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "index-sharded":
+        run_index_sharded(args)
     else:
         run_ours(args)

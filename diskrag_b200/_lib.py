@@ -72,6 +72,15 @@ SIGNATURES = {
     "dr_index_patch_vectors": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "dr_index_set_deleted_rows": (C.c_int, [_vp, _vp, _i64, _vp]),
     "dr_topk_merge_dev": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, C.c_int, _vp]),
+    "dr_topk_pack_dev": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, C.c_int, _vp]),
+    "dr_topk_merge_keys_dev": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, C.c_int, _vp]),
+    "dr_index_set_peer_route": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _i64]),
+    "dr_dev_alloc": (C.c_int, [C.c_int, _i64, _PP(_vp), _vp]),
+    "dr_dev_free": (C.c_int, [C.c_int, _vp]),
+    "dr_ipc_open": (C.c_int, [C.c_int, _vp, _PP(_vp)]),
+    "dr_ipc_close": (C.c_int, [C.c_int, _vp]),
+    "dr_dev_memset": (C.c_int, [C.c_int, _vp, C.c_int, _i64, _vp]),
+    "dr_dev_upload": (C.c_int, [C.c_int, _vp, _vp, _i64]),
 }
 
 _lib = None

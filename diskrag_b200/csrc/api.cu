@@ -35,6 +35,8 @@ int launch_pq_decode(const float *, const uint8_t *, int64_t, int, int, float *,
 int launch_rowdist(const float *, const float *, int64_t, int64_t, int, int, float *, cudaStream_t);
 int launch_sdc(const float *, const uint8_t *, const uint8_t *, int64_t, int, int, float *, cudaStream_t);
 int launch_topk_merge(const int32_t *, const float *, int, int64_t, int, int32_t *, float *, cudaStream_t);
+int launch_topk_pack(const int32_t *, const float *, int64_t, int, int64_t, int, u64 *, cudaStream_t);
+int launch_topk_merge_keys(const u64 *, int, int64_t, int, int32_t *, float *, cudaStream_t);
 int launch_medoid(const float *, int64_t, int, const int32_t *, int, int, double *, cudaStream_t);
 int launch_vamana_build(const float *, int64_t, int, int, int, float, int64_t, uint64_t, uint32_t *, int32_t *, int, cudaStream_t);
 int launch_deinterleave(const void *, int64_t, int, int, float *, uint32_t *, cudaStream_t);
@@ -740,6 +742,70 @@ int dr_topk_merge_dev(const int32_t *d_ids, const float *d_dist, int32_t G, int6
                       float *d_out_dist, int device, void *stream) {
     if (use_device(device)) return 3;
     return launch_topk_merge(d_ids, d_dist, G, B, k, d_out_ids, d_out_dist, (cudaStream_t)stream);
+}
+
+int dr_topk_pack_dev(const int32_t *d_ids, const float *d_dist, int64_t B, int32_t k, int64_t id_offset, int32_t G, uint64_t *d_out_keys,
+                     int device, void *stream) {
+    if (use_device(device)) return 3;
+    return launch_topk_pack(d_ids, d_dist, B, k, id_offset, G, (u64 *)d_out_keys, (cudaStream_t)stream);
+}
+
+int dr_topk_merge_keys_dev(const uint64_t *d_keys, int32_t G, int64_t Bq, int32_t k, int32_t *d_out_ids, float *d_out_dist, int device,
+                           void *stream) {
+    if (use_device(device)) return 3;
+    return launch_topk_merge_keys((const u64 *)d_keys, G, Bq, k, d_out_ids, d_out_dist, (cudaStream_t)stream);
+}
+
+int dr_index_set_peer_route(dr_index *h, const uint64_t *d_peer_ptrs, int32_t G, int32_t rank, int64_t B_total, int64_t id_offset) {
+    DR_CHECK(h, "dr_index_set_peer_route: null handle");
+    DR_LOCK(h);
+    if (!d_peer_ptrs) { h->d_peer_recv = nullptr; h->peer_G = 0; return 0; }
+    DR_CHECK(G >= 1 && rank >= 0 && rank < G && B_total >= 1 && id_offset >= 0, "dr_index_set_peer_route: bad G / rank / batch / offset");
+    h->d_peer_recv = reinterpret_cast<u64 *const *>(d_peer_ptrs);
+    h->peer_G = G; h->peer_rank = rank; h->peer_B = B_total; h->peer_id_offset = id_offset;
+    return 0;
+}
+
+// plain device allocations with a process-portable handle: symmetric receive buffers for the peer-routed exchange
+int dr_dev_alloc(int device, int64_t bytes, void **out_ptr, void *out_ipc_handle64) {
+    if (use_device(device)) return 3;
+    DR_CHECK(out_ptr && bytes > 0, "dr_dev_alloc: bad argument");
+    DR_CUDA(cudaMalloc(out_ptr, (size_t)bytes));
+    if (out_ipc_handle64) {
+        cudaIpcMemHandle_t hd;
+        DR_CUDA(cudaIpcGetMemHandle(&hd, *out_ptr));
+        static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(out_ipc_handle64, &hd, 64);
+    }
+    return 0;
+}
+int dr_dev_free(int device, void *ptr) {
+    if (use_device(device)) return 3;
+    if (ptr) DR_CUDA(cudaFree(ptr));
+    return 0;
+}
+int dr_ipc_open(int device, const void *ipc_handle64, void **out_ptr) {
+    if (use_device(device)) return 3;
+    DR_CHECK(ipc_handle64 && out_ptr, "dr_ipc_open: null argument");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle64, 64);
+    DR_CUDA(cudaIpcOpenMemHandle(out_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int dr_ipc_close(int device, void *ptr) {
+    if (use_device(device)) return 3;
+    if (ptr) DR_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+int dr_dev_memset(int device, void *ptr, int value, int64_t bytes, void *stream) {
+    if (use_device(device)) return 3;
+    DR_CUDA(cudaMemsetAsync(ptr, value, (size_t)bytes, (cudaStream_t)stream));
+    return 0;
+}
+int dr_dev_upload(int device, void *dst, const void *src_host, int64_t bytes) {
+    if (use_device(device)) return 3;
+    DR_CUDA(cudaMemcpy(dst, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+    return 0;
 }
 
 }  // extern "C"

@@ -68,6 +68,10 @@ struct dr_index {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // last use of the shared scratch: a search enqueued on a different stream waits for it on the device
     cudaEvent_t ev_scratch = nullptr; cudaStream_t scratch_stream = nullptr; bool scratch_used = false;
+    // index-sharded exchange fused into the search kernel's epilogue (dr_index_set_peer_route): every query's top-k goes, as packed
+    // keys, straight into the receive buffer of the rank that reduces it (peer memory over NVLink), in addition to the local output
+    u64 *const *d_peer_recv = nullptr;  // device array of G pointers: rank g's receive buffer [G][Bq][k]
+    int peer_G = 0, peer_rank = 0; int64_t peer_B = 0, peer_id_offset = 0;
     // host-pointer API pipeline (copy-in / compute / copy-out streams)
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[DR_PIPE_EVENTS] = {}, ev_done[DR_PIPE_EVENTS] = {};

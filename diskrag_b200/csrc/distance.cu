@@ -126,6 +126,68 @@ int launch_topk_merge(const int32_t *d_ids, const float *d_dist, int G, int64_t 
     return 0;
 }
 
+// Index-sharded exchange, packed: one 64-bit key per (query, rank-in-list) = f2ord(dist) << 32 | global id; empty = all ones.
+// Send layout [G][Bq][k]: block g holds the lists of the queries rank g reduces (contiguous slices of the batch, the first B % G
+// ranks own one query more), rows past the slice are empty.  One all-to-all of this buffer replaces two (ids, distances).
+__global__ void topk_pack_kernel(const int32_t *__restrict__ ids, const float *__restrict__ dist, long long B, int k, long long id_offset,
+                                 int G, long long Bq, u64 *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)G * Bq * k) return;
+    const int j = (int)(t % k);
+    const long long r = (t / k) % Bq;
+    const int g = (int)(t / ((long long)k * Bq));
+    const long long per = B / G, extra = B % G;
+    const long long lo = g * per + (g < extra ? g : extra), cnt = per + (g < extra ? 1 : 0);
+    u64 key = DR_KEY_MAX;
+    if (r < cnt) {
+        const int32_t id = ids[(size_t)(lo + r) * k + j];
+        if (id >= 0) key = ((u64)f2ord(dist[(size_t)(lo + r) * k + j] + 0.0f) << 32) | (u64)(uint32_t)(id + id_offset);
+    }
+    out[t] = key;
+}
+// k-way merge of G packed lists per query, keys [G][Bq][k] -> out [Bq][k]; one warp per query, G*k <= 1024
+__global__ void __launch_bounds__(128) topk_merge_keys_kernel(const u64 *__restrict__ keys_in, int G, long long Bq, int k,
+                                                              int32_t *__restrict__ out_ids, float *__restrict__ out_dist) {
+    extern __shared__ u64 s_keys[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + wl;
+    if (q >= Bq) return;
+    const int n = G * k;
+    u64 *keys = s_keys + (size_t)wl * n;
+    for (int i = lane; i < n; i += 32) {
+        const int g = i / k, j = i - g * k;
+        keys[i] = keys_in[((size_t)g * Bq + q) * k + j];
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const u64 key = keys[i];
+        int pos = 0;
+        for (int j = 0; j < n; ++j) pos += (keys[j] < key || (keys[j] == key && j < i)) ? 1 : 0;
+        if (pos < k) {
+            const bool empty = key == DR_KEY_MAX;
+            out_ids[(size_t)q * k + pos] = empty ? -1 : (int32_t)(key & 0xFFFFFFFFull);
+            out_dist[(size_t)q * k + pos] = empty ? __int_as_float(0x7f800000) : ord2f((uint32_t)(key >> 32));
+        }
+    }
+}
+int launch_topk_pack(const int32_t *d_ids, const float *d_dist, int64_t B, int k, int64_t id_offset, int G, u64 *d_out, cudaStream_t s) {
+    DR_CHECK(G >= 1 && k >= 1, "dr_topk_pack: bad G / k");
+    const long long Bq = (B + G - 1) / G, tot = (long long)G * Bq * k;
+    if (tot == 0) return 0;
+    topk_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_ids, d_dist, B, k, id_offset, G, Bq, d_out);
+    DR_LAUNCHED();
+    return 0;
+}
+int launch_topk_merge_keys(const u64 *d_keys, int G, int64_t Bq, int k, int32_t *d_out_ids, float *d_out_dist, cudaStream_t s) {
+    DR_CHECK(G >= 1 && k >= 1 && G * k <= 1024, "dr_topk_merge_keys: need G*k <= 1024 (G=%d k=%d)", G, k);
+    if (Bq == 0) return 0;
+    const int warps = 4;
+    topk_merge_keys_kernel<<<(unsigned)((Bq + warps - 1) / warps), warps * 32, (size_t)warps * G * k * 8, s>>>(d_keys, G, Bq, k, d_out_ids,
+                                                                                                               d_out_dist);
+    DR_LAUNCHED();
+    return 0;
+}
+
 // medoid (cython_utils.pyx:210-263): sums[s] = sum_j ||x_sample_s - x_j||  (fp32 inner, fp64 outer).
 // grid (ns, chunks over N); one warp per (sample, point) pair inside, double atomics per CTA.
 __global__ void __launch_bounds__(256) medoid_kernel(const float *__restrict__ X, long long N, int D,

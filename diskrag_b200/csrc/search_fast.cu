@@ -29,7 +29,17 @@ struct FastArgs {
     uint32_t *ovf; uint32_t ovf_cap; uint32_t hash_cap;
     int o_q, o_rrk, o_list0, o_list1, o_ur0, o_ur1, o_newk, o_newid, o_sel, o_adjrow, o_hash;
     int rr_slots;   // rerank staging slots available in the table region (the query vector may occupy the last one)
+    // index-sharded exchange in the epilogue: rank g = owner of global query qb reduces it; its buffer is [G][Bq][k] packed keys
+    u64 *const *peer_recv; int peer_G, peer_rank; long long peer_B, peer_id_offset, peer_q0;
 };
+
+// where global query qb of a peer_B-query batch goes: owner rank (contiguous slices, the first peer_B % G ranks hold one more) and
+// the row inside the owner's slice
+__device__ __forceinline__ void peer_slot(long long qb, long long B, int G, int &g, long long &r) {
+    const long long per = B / G, extra = B % G, cut = extra * (per + 1);
+    if (qb < cut) { g = (int)(qb / (per + 1)); r = qb - (long long)g * (per + 1); }
+    else { g = (int)(extra + (qb - cut) / (per > 0 ? per : 1)); r = qb - cut - (long long)(g - extra) * per; }
+}
 
 __device__ __forceinline__ u64 make_ikey(uint32_t sum, uint32_t id) { return ((u64)sum << 32) | ((u64)id << 1); }
 
@@ -734,6 +744,13 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             }
         }
         const int k = a.k;
+        u64 *peer_dst = nullptr;      // this query's k slots in the owner rank's receive buffer (peer memory)
+        if (a.peer_recv) {
+            int g; long long r;
+            peer_slot(a.peer_q0 + b, a.peer_B, a.peer_G, g, r);
+            const long long Bq = (a.peer_B + a.peer_G - 1) / a.peer_G;
+            peer_dst = a.peer_recv[g] + ((size_t)a.peer_rank * Bq + r) * k;
+        }
         if (do_rerank) {
             // Exact rerank of the whole list.  The table is dead now: its bytes stage full-precision rows, one slot per
             // warp, filled by bulk async copies (TMA engine, evict-first in L2) in two pieces so that the second half of a
@@ -821,6 +838,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     float d2 = ord2f((uint32_t)(key >> 32));
                     a.out_ids[(size_t)b * k + pos] = (int32_t)key_id(lst[i]);
                     if (a.out_dist) a.out_dist[(size_t)b * k + pos] = a.sqrt_out ? sqrtf(d2) : d2;
+                    if (peer_dst) peer_dst[pos] = (key & 0xFFFFFFFF00000000ull) | (u64)(uint32_t)(key_id(lst[i]) + a.peer_id_offset);
                 }
             }
         } else {
@@ -833,6 +851,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
         for (int i = n + tid; i < k; i += nt) {
             a.out_ids[(size_t)b * k + i] = -1;
             if (a.out_dist) a.out_dist[(size_t)b * k + i] = __int_as_float(0x7f800000);
+            if (peer_dst) peer_dst[i] = DR_KEY_MAX;
         }
         if (tid == 0) {
             if (a.out_hops) a.out_hops[b] = hops;
@@ -886,6 +905,11 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     a.N = h->N; a.D = h->D; a.R = h->R; a.M = h->M;
     a.k = p->k; a.L = p->L; a.W = p->W; a.rerank = p->rerank; a.sqrt_out = p->sqrt_out; a.prefetch = p->prefetch;
     if ((h->R & 3) != 0 || p->W > 16) a.prefetch &= ~16;   // bulk copies of adjacency rows need 16-byte rows; 16 barriers
+    if (h->d_peer_recv) {
+        DR_CHECK(p->rerank && !p->sqrt_out && B <= h->peer_B, "dr_search: the peer-routed exchange needs rerank = 1, sqrt_out = 0 and B <= the routed batch");
+        a.peer_recv = h->d_peer_recv; a.peer_G = h->peer_G; a.peer_rank = h->peer_rank; a.peer_B = h->peer_B;
+        a.peer_id_offset = h->peer_id_offset;
+    }
     a.start = (uint32_t)(p->start_plus1 > 0 ? (int64_t)p->start_plus1 - 1 : h->medoid);   // range-checked by launch_search
     const bool word_layout = ((h->M & 3) == 0) && h->M <= 256;
     DR_CHECK(p->lut_fmt != DR_LUT_U8_TC || (word_layout && ((h->D / h->M) & 7) == 0),
@@ -1019,6 +1043,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
         }
         a.Q = d_Q + (size_t)c0 * h->D; a.lut8 = d_tab; a.lut_scale = d_scale; a.lut_offset = d_off; a.B = cb;
         a.out_ids = ids + (size_t)c0 * p->k;
+        a.peer_q0 = c0;
         a.out_dist = dist ? dist + (size_t)c0 * p->k : nullptr;
         a.out_hops = hops ? hops + c0 : nullptr;
         a.out_visited = visited ? visited + c0 : nullptr;

@@ -232,6 +232,28 @@ int dr_robust_prune(const float *p, const float *cand, int32_t n, int32_t D, flo
 int dr_topk_merge_dev(const int32_t *d_ids, const float *d_dist, int32_t G, int64_t B, int32_t k,
                       int32_t *d_out_ids, float *d_out_dist, int device, void *stream);
 
+/* The same exchange with ONE 64-bit key per entry (f2ord(dist) << 32 | global id, all ones = empty), so that one all-to-all moves
+ * ids and distances together.  dr_topk_pack_dev: this rank's [B,k] shard-local lists (ids + id_offset = global) -> send buffer
+ * u64[G][Bq][k], Bq = ceil(B / G), block g = the slice of queries rank g reduces.  dr_topk_merge_keys_dev: received u64[G][Bq][k]
+ * -> i32[Bq,k], f32[Bq,k]. */
+int dr_topk_pack_dev(const int32_t *d_ids, const float *d_dist, int64_t B, int32_t k, int64_t id_offset, int32_t G,
+                     uint64_t *d_out_keys, int device, void *stream);
+int dr_topk_merge_keys_dev(const uint64_t *d_keys, int32_t G, int64_t Bq, int32_t k, int32_t *d_out_ids, float *d_out_dist,
+                           int device, void *stream);
+/* The exchange fused into the search kernel: with a peer route set, the throughput kernel's epilogue also writes every query's
+ * top-k as packed keys straight into the receive buffer of the rank that reduces that query — peer memory over NVLink / NVSwitch,
+ * no collective on the data path — at [rank][row in the owner's slice][k] of the owner's u64[G][Bq][k] buffer.  d_peer_ptrs is a
+ * DEVICE array of G pointers (entry g = rank g's receive buffer as mapped into this process: its own allocation for g == rank,
+ * dr_ipc_open of the peer's handle otherwise); NULL switches routing off.  Needs rerank = 1, sqrt_out = 0, DR_LUT_U8*. */
+int dr_index_set_peer_route(dr_index *h, const uint64_t *d_peer_ptrs, int32_t G, int32_t rank, int64_t B_total, int64_t id_offset);
+/* device allocations that can be shared between the ranks of one node (cudaIpc): out_ipc_handle64 receives 64 opaque bytes */
+int dr_dev_alloc(int device, int64_t bytes, void **out_ptr, void *out_ipc_handle64);
+int dr_dev_free(int device, void *ptr);
+int dr_ipc_open(int device, const void *ipc_handle64, void **out_ptr);
+int dr_ipc_close(int device, void *ptr);
+int dr_dev_memset(int device, void *ptr, int value, int64_t bytes, void *stream);
+int dr_dev_upload(int device, void *dst, const void *src_host, int64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

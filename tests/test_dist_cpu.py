@@ -34,12 +34,13 @@ def _worker(rank, world, port, tmp):
     N, Dm, B, k = 999, 16, 37, 5                      # ragged on purpose: neither divides by 2
     X = synth_numpy(N, Dm, seed=3, K=16, r=8); Q = synth_numpy(B, Dm, seed=3, sample_seed=1, K=16, r=8)
     gt = O.ground_truth(X, Q, k)
-    merge = lambda i, d: tuple(torch.from_numpy(a) for a in D.merge_topk_numpy(i.numpy(), d.numpy()))
+    merge = lambda keys: tuple(torch.from_numpy(a) for a in D.merge_keys_numpy(keys.numpy()))
+    pack = lambda i, d, off, w: torch.from_numpy(D.pack_topk_numpy(i.numpy(), d.numpy(), off, w))
     # ---- index-sharded: every rank searches all queries on its rows, one exchange, k-way merge ----------
     lo, hi = D.shard_rows(N, rank, world)
     loc = O.ground_truth(X[lo:hi], Q, k)                                  # shard-local row numbers
     dd = np.stack([((X[lo:hi][loc[b]] - Q[b]) ** 2).sum(1) for b in range(B)]).astype(np.float32)
-    ids, dists = D.index_sharded_topk(torch.from_numpy(loc.astype(np.int32)), torch.from_numpy(dd), lo, merge=merge)
+    ids, dists = D.index_sharded_topk(torch.from_numpy(loc.astype(np.int32)), torch.from_numpy(dd), lo, pack=pack, merge=merge)
     assert ids.shape == (B, k)
     for b in range(B):
         assert set(ids[b].tolist()) == set(gt[b].tolist()), (rank, b)
@@ -48,7 +49,7 @@ def _worker(rank, world, port, tmp):
     loc2 = loc.copy().astype(np.int32); dd2 = dd.copy()
     if rank == 1:
         loc2[:, 2:] = -1; dd2[:, 2:] = np.inf
-    ids2, _ = D.index_sharded_topk(torch.from_numpy(loc2), torch.from_numpy(dd2), lo, merge=merge)
+    ids2, _ = D.index_sharded_topk(torch.from_numpy(loc2), torch.from_numpy(dd2), lo, pack=pack, merge=merge)
     assert (ids2 >= 0).all()
     # ---- query-sharded: replicated index, each rank answers its slice, results all-gathered ---------------
     qlo, qhi = D.query_slice(B, rank, world)

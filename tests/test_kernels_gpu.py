@@ -130,3 +130,26 @@ def test_topk_merge(orc):
         keep = flat_i >= 0
         o = np.lexsort((flat_i[keep], flat_d[keep]))[:k]
         assert np.array_equal(oi[b], flat_i[keep][o]) and np.array_equal(od[b], flat_d[keep][o])
+
+
+def test_packed_exchange_kernels_equal_their_numpy_statement():
+    """dr_topk_pack_dev / dr_topk_merge_keys_dev (the single-exchange form of the index-sharded merge) against
+    dist.pack_topk_numpy / merge_keys_numpy, ragged slices, short lists, negative-zero and tied distances included."""
+    import torch
+    from diskrag_b200 import dist as D
+    rs = np.random.RandomState(4)
+    for G, B, k in ((1, 9, 4), (2, 37, 5), (8, 1001, 10), (3, 2, 7)):
+        d = np.sort(rs.rand(B, k).astype(np.float32), axis=1)
+        ids = rs.randint(0, 1 << 20, size=(B, k)).astype(np.int32)
+        ids[::3, k - 2:] = -1; d[::3, k - 2:] = np.inf
+        d[0, 0] = -0.0
+        off = 123456
+        send = D._pack_gpu(torch.from_numpy(ids).cuda(), torch.from_numpy(d).cuda(), off, G)
+        assert np.array_equal(send.cpu().numpy(), D.pack_topk_numpy(ids, d, off, G))
+        # pretend G ranks sent their blocks: merge G lists per query
+        keys = np.stack([D.pack_topk_numpy(np.where(ids >= 0, (ids + 7 * g) % (1 << 20), -1).astype(np.int32), np.sort(d + np.float32(0.01 * g), axis=1), off, 1)[0]
+                         for g in range(G)])
+        keys[1 % G, 0, 0] = keys[0, 0, 0]                                 # an exact duplicate key: both copies survive the merge
+        oi, od = D._merge_keys_gpu(torch.from_numpy(keys).cuda())
+        ei, ed = D.merge_keys_numpy(keys)
+        assert np.array_equal(oi.cpu().numpy(), ei) and np.array_equal(od.cpu().numpy(), ed)

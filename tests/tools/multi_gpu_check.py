@@ -1,16 +1,21 @@
-"""NCCL check of both partitionings on real GPUs:  torchrun --nproc-per-node G tests/tools/multi_gpu_check.py
-index-sharded: every rank builds its own Vamana shard on its GPU, searches all queries, all-to-all + k-way merge kernel."""
-import os, sys, time
+"""NCCL / NVLink check of both partitionings on real GPUs:  torchrun --nproc-per-node G tests/tools/multi_gpu_check.py
+index-sharded: every rank builds its own Vamana shard (+ PQ) on its GPU, searches all queries (throughput kernel, fused rerank), then
+  (a) one packed NCCL all-to-all + k-way merge kernel, and
+  (b) no collective: the search kernel's epilogue stores the packed keys into the owner rank's buffer over peer memory (PeerExchange)
+  — (b) must return exactly what (a) returns, and both the global recall.
+query-sharded: replicated index, slices gathered: identical to the single-GPU result."""
+import os, sys
 sys.path.insert(0, "."); sys.path.insert(0, "oracle")
 import numpy as np, torch, torch.distributed as dist
 from diskrag_b200 import dist as D, ops
 from diskrag_b200.engine import GpuIndex
+from diskrag_b200.pq.fast_pq import DiskANNPQ
 from diskrag_b200.synth import synth_numpy
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
-N, Dm, B, k = 40000, 96, 1000, 10
+N, Dm, B, k, M = 40000, 96, 1003, 10, 24                                   # B ragged on purpose
 X = synth_numpy(N, Dm, seed=9, K=256, r=24); Q = synth_numpy(B, Dm, seed=9, sample_seed=1, K=256, r=24)
 Xt = torch.from_numpy(X).to(dev); Qt = torch.from_numpy(Q).to(dev)
 d = (Xt * Xt).sum(1)[None, :] - 2.0 * Qt @ Xt.T
@@ -19,15 +24,28 @@ lo, hi = D.shard_rows(N, rank, world)
 Xs = X[lo:hi]
 med = ops.medoid(Xs, np.arange(0, hi - lo, max(1, (hi - lo) // 500), dtype=np.int32)[:500], device=local)
 adj, deg = ops.vamana_build(Xs, 24, 48, 1.2, med, seed=5 + rank, device=local)
-with GpuIndex.from_arrays(Xs, adj, medoid=med, device=local) as idx:
-    r = idx.search(Q, k=k, L=64, W=1, dist="exact", rerank=False)
-ids, dd = D.index_sharded_topk(torch.from_numpy(r.ids).to(dev), torch.from_numpy(r.dists).to(dev), lo)
-ids = ids.cpu().numpy()
+pq = DiskANNPQ(M, 256, device=local); pq.fit(Xs)
+codes = pq.encode(Xs)
+qlo, qhi = D.query_slice(B, rank, world)
+with GpuIndex.from_arrays(Xs, adj, codes, pq.codebook(), medoid=med, device=local) as idx:
+    r = idx.search(Q, k=k, L=64, W=4, dist="pq", rerank=True, lut_fmt="u8")
+    ids_t, dd_t = torch.from_numpy(r.ids).to(dev), torch.from_numpy(r.dists).to(dev)
+    ai, ad = D.index_sharded_topk(ids_t, dd_t, lo, gather=False)                       # (a) packed NCCL exchange
+    gi_all, _ = D.index_sharded_topk(ids_t, dd_t, lo, gather=True)
+    peer = D.PeerExchange(idx, B, k, lo, local)                                         # (b) peer-routed epilogue
+    for _ in range(3):                                                                  # repeated steps reuse the buffers
+        r2 = idx.search(Q, k=k, L=64, W=4, dist="pq", rerank=True, lut_fmt="u8", chunk=300)   # chunked launches route by global row
+        bi, bd = peer.merge()
+        same_p2p = bool(torch.equal(ai, bi) and torch.equal(ad, bd)) and np.array_equal(r2.ids, r.ids)
+        assert same_p2p, f"rank {rank}: peer-routed exchange differs from the NCCL exchange"
+    peer.close()
+    r3 = idx.search(Q[:5], k=k, L=64, W=4, dist="pq", rerank=True, lut_fmt="u8")          # route cleared: plain search again
+    assert np.array_equal(r3.ids, r.ids[:5])
+ids = gi_all.cpu().numpy()
 rec = np.mean([len(set(ids[b].tolist()) & set(gt[b].tolist())) / k for b in range(B)])
 # query-sharded on a replicated index
 med_all = ops.medoid(X, np.arange(0, N, N // 500, dtype=np.int32)[:500], device=local)
 adj_all, _ = ops.vamana_build(X, 24, 48, 1.2, med_all, seed=5, device=local)
-qlo, qhi = D.query_slice(B, rank, world)
 with GpuIndex.from_arrays(X, adj_all, medoid=med_all, device=local) as idx:
     full = idx.search(Q, k=k, L=64, dist="exact", rerank=False)
     mine = idx.search(Q[qlo:qhi], k=k, L=64, dist="exact", rerank=False)
@@ -35,7 +53,7 @@ gi, gd = D.gather_query_sharded(torch.from_numpy(mine.ids).to(dev), torch.from_n
 same = bool(np.array_equal(gi.cpu().numpy(), full.ids))
 rec_t = torch.tensor([rec], device=dev); dist.all_reduce(rec_t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"world={world} index-sharded recall@10 after NCCL all-to-all + merge kernel: {rec_t.item():.4f}; "
-          f"query-sharded gather identical to single-GPU result: {same}")
-    assert rec_t.item() > 0.97 and same
+    print(f"world={world} index-sharded global recall@10 {rec_t.item():.4f} (packed NCCL all-to-all + merge kernel); "
+          f"peer-routed epilogue exchange identical to it: {same_p2p}; query-sharded gather identical to single-GPU result: {same}")
+    assert rec_t.item() > 0.95 and same
 dist.destroy_process_group()
