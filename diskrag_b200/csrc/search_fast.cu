@@ -88,33 +88,33 @@ __device__ __forceinline__ uint32_t tab_sum4(uint32_t tb, uint32_t w, int stride
 template <int G>
 struct RowWords { uint32_t wf[2][G]; uint32_t wt[G]; };
 
+// base_lane = codes + 4 * lane (word `lane` of row 0), base_tail = codes + 128 * nfull + 4 * (lane & 15): the callers keep both in
+// registers (one 32 x 32 + 64-bit multiply-add per row address instead of a 64-bit add chain on a uniform base)
 template <int WORDS, int G>
-__device__ __forceinline__ void rows_load(const uint8_t *__restrict__ codes, int M, const uint32_t (&ids)[G], int lane,
-                                          RowWords<G> &w) {
+__device__ __forceinline__ void rows_load(const uint8_t *__restrict__ base_lane, const uint8_t *__restrict__ base_tail, int M,
+                                          const uint32_t (&ids)[G], int lane, RowWords<G> &w) {
     const int words = WORDS ? WORDS : (M >> 2);
     const uint32_t Mc = WORDS ? (uint32_t)(WORDS * 4) : (uint32_t)M;   // row stride in bytes
     const int nfull = words >> 5, rem = words & 31;
     const bool pair = rem > 0 && rem <= 16;
     const int hl = lane & 15;
-    const uint8_t *base_lane = codes + lane * 4;                       // word `lane` of row 0
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        const uint32_t *rp = reinterpret_cast<const uint32_t *>(base_lane + (size_t)ids[g] * Mc);
+        const uint32_t *rp = reinterpret_cast<const uint32_t *>(base_lane + (unsigned long long)ids[g] * Mc);
 #pragma unroll
         for (int k = 0; k < 2; ++k)
             if (k < nfull) w.wf[k][g] = __ldg(rp + 32 * k);
     }
     if (pair) {
-        const uint8_t *base_tail = codes + 128 * nfull + hl * 4;
 #pragma unroll
         for (int p = 0; p < G / 2; ++p) {
             const uint32_t id = (lane < 16) ? ids[2 * p] : ids[2 * p + 1];
-            w.wt[p] = (hl < rem) ? __ldg(reinterpret_cast<const uint32_t *>(base_tail + (size_t)id * Mc)) : 0u;
+            w.wt[p] = (hl < rem) ? __ldg(reinterpret_cast<const uint32_t *>(base_tail + (unsigned long long)id * Mc)) : 0u;
         }
     } else if (rem) {
 #pragma unroll
         for (int g = 0; g < G; ++g)
-            w.wt[g] = (lane < rem) ? __ldg(reinterpret_cast<const uint32_t *>(base_lane + (size_t)ids[g] * Mc) + 32 * nfull) : 0u;
+            w.wt[g] = (lane < rem) ? __ldg(reinterpret_cast<const uint32_t *>(base_lane + (unsigned long long)ids[g] * Mc) + 32 * nfull) : 0u;
     }
 }
 
@@ -160,7 +160,8 @@ template <int WORDS, int G>
 __device__ __forceinline__ void adc_u8_rows(const uint8_t *__restrict__ codes, int M, const uint8_t *__restrict__ tab,
                                             const uint32_t (&ids)[G], int lane, uint32_t (&out)[G]) {
     RowWords<G> w;
-    rows_load<WORDS, G>(codes, M, ids, lane, w);
+    const int words_ = WORDS ? WORDS : (M >> 2);
+    rows_load<WORDS, G>(codes + lane * 4, codes + 128 * (words_ >> 5) + (lane & 15) * 4, M, ids, lane, w);
     rows_sum<WORDS, G>(M, smem_u32(tab), w, G / 2, lane, out);
 }
 
@@ -199,6 +200,9 @@ global_table:
 #ifndef DR_RR_UNROLL
 #define DR_RR_UNROLL 2
 #endif
+#ifndef DR_RR_FULL
+#define DR_RR_FULL 6   // D = 1536 specialisations: each half-row piece is 768 elements = 6 float4 per lane, fully unrolled (0 = loop)
+#endif
 // Rerank rows beyond the staging slots: 0 = fetched only when a slot frees up (48 KB in flight per CTA); 1 = all of them are
 // started on their trip to L2 (cp.async.bulk.prefetch.L2, one instruction per 6 KB row) as soon as the traversal ends, so only
 // the first round of staged copies waits for DRAM; N >= 2 = a rolling window of N rounds ahead of the staged copies
@@ -210,8 +214,24 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes
 }
 // One piece [e0, e1) of the canonical warp L2^2 (common.cuh:warp_l2sq: lane l owns elements base = 4 l + 128 j, fmaf in
 // increasing j), the row read from shared memory where a bulk copy staged it.  e0 is a multiple of 128.
+// FULL > 0: the piece is exactly FULL iterations (compile-time dimension): fully unrolled
+template <int FULL>
 __device__ __forceinline__ float l2sq_piece_smem(const float *__restrict__ row, const float *__restrict__ q, int e0, int e1,
                                                  int lane, float acc) {
+    if (FULL > 0) {
+        const float *r0 = row + e0 + lane * 4, *q0 = q + e0 + lane * 4;
+#pragma unroll
+        for (int it = 0; it < FULL; ++it) {
+            const float4 x = *reinterpret_cast<const float4 *>(r0 + it * 128);
+            const float4 y = *reinterpret_cast<const float4 *>(q0 + it * 128);
+            const float d0 = __fsub_rn(x.x, y.x), d1 = __fsub_rn(x.y, y.y), d2 = __fsub_rn(x.z, y.z), d3 = __fsub_rn(x.w, y.w);
+            acc = __fmaf_rn(d0, d0, acc);
+            acc = __fmaf_rn(d1, d1, acc);
+            acc = __fmaf_rn(d2, d2, acc);
+            acc = __fmaf_rn(d3, d3, acc);
+        }
+        return acc;
+    }
     constexpr int kUnroll = DR_RR_UNROLL;
 #pragma unroll kUnroll
     for (int base = e0 + lane * 4; base < e1; base += 128) {
@@ -307,6 +327,10 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     asm volatile("" : "+r"(lane), "+r"(wid));    // opaque: keep them in registers instead of re-reading %tid in the loops
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tab32 = smem_u32(s_lut);
+    // this lane's word of code row 0 (full chunk / tail chunk): kept in registers, see rows_load
+    const uint8_t *code_lane = a.codes + lane * 4;
+    const uint8_t *code_tail = a.codes + 128 * (((WORDS > 0 ? WORDS : (a.M >> 2))) >> 5) + (lane & 15) * 4;
+    asm volatile("" : "+l"(code_lane), "+l"(code_tail));
     const int D = RW8 >= 2 ? 1536 : a.D, M = a.M, L = RW8 >= 3 ? 100 : a.L;
     const uint32_t hcap = RW8 >= 3 ? (DR_L2V ? 0u : 4096u) : a.hash_cap;
     const int pf = RW8 == 4 ? DR_PF_SPEC : a.prefetch;
@@ -535,35 +559,37 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                         uint32_t gid[4];
 #pragma unroll
                         for (int g = 0; g < 4; ++g) gid[g] = __shfl_sync(DR_FULL, myid, g);    // lanes >= cntw hold row 0: valid
-                        rows_load<KW, 4>(a.codes, M, gid, lane, wa);
+                        rows_load<KW, 4>(code_lane, code_tail, M, gid, lane, wa);
                     }
                     for (int r = 0; r < rounds; r += 2) {
                         if (r + 1 < rounds) {
                             uint32_t gid[4];
 #pragma unroll
                             for (int g = 0; g < 4; ++g) gid[g] = __shfl_sync(DR_FULL, myid, (r + 1) * 4 + g);
-                            rows_load<KW, 4>(a.codes, M, gid, lane, wb);
+                            rows_load<KW, 4>(code_lane, code_tail, M, gid, lane, wb);
                         }
                         uint32_t gs[4];
                         rows_sum<KW, 4>(M, tab32, wa, (cntw - r * 4) > 2 ? 2 : 1, lane, gs);
 #ifdef DR_PHASE_TIMING
                         if (r == 0) { asm volatile("" ::"r"(gs[0])); DR_PT(8); }   // (timing build) first group of code rows summed
 #endif
-                        if ((lane >> 2) == r) {
-                            const int g = lane & 3;
-                            mysum = g == 0 ? gs[0] : (g == 1 ? gs[1] : (g == 2 ? gs[2] : gs[3]));
+                        {   // lane 4 r + g keeps row g of this round (two selects on loop-invariant predicates, one on r)
+                            const uint32_t lo2 = (lane & 1) ? gs[1] : gs[0], hi2 = (lane & 1) ? gs[3] : gs[2];
+                            const uint32_t pick = (lane & 2) ? hi2 : lo2;
+                            mysum = ((lane >> 2) == r) ? pick : mysum;
                         }
                         if (r + 1 < rounds) {
                             if (r + 2 < rounds) {
                                 uint32_t gid[4];
 #pragma unroll
                                 for (int g = 0; g < 4; ++g) gid[g] = __shfl_sync(DR_FULL, myid, (r + 2) * 4 + g);
-                                rows_load<KW, 4>(a.codes, M, gid, lane, wa);
+                                rows_load<KW, 4>(code_lane, code_tail, M, gid, lane, wa);
                             }
                             rows_sum<KW, 4>(M, tab32, wb, (cntw - (r + 1) * 4) > 2 ? 2 : 1, lane, gs);
-                            if ((lane >> 2) == r + 1) {
-                                const int g = lane & 3;
-                                mysum = g == 0 ? gs[0] : (g == 1 ? gs[1] : (g == 2 ? gs[2] : gs[3]));
+                            {
+                                const uint32_t lo2 = (lane & 1) ? gs[1] : gs[0], hi2 = (lane & 1) ? gs[3] : gs[2];
+                                const uint32_t pick = (lane & 2) ? hi2 : lo2;
+                                mysum = ((lane >> 2) == r + 1) ? pick : mysum;
                             }
                         }
                     }
@@ -800,12 +826,12 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                         float acc = 0.0f;
                         if (by0) {
                             mbar_wait(bar0, rr_ph0); rr_ph0 ^= 1u;
-                            acc = l2sq_piece_smem(buf, s_q, 0, e0, lane, acc);
+                            acc = l2sq_piece_smem<(RW8 >= 2 ? DR_RR_FULL : 0)>(buf, s_q, 0, e0, lane, acc);
                             __syncwarp();
                             if (lane == 0 && rown) { mbar_expect_tx(bar0, by0); bulk_g2s_hint(buf, rown, by0, bar0, pol_stream); }
                         }
                         mbar_wait(bar1, rr_ph1); rr_ph1 ^= 1u;
-                        acc = l2sq_piece_smem(buf, s_q, e0, D, lane, acc);
+                        acc = l2sq_piece_smem<(RW8 >= 2 ? DR_RR_FULL : 0)>(buf, s_q, e0, D, lane, acc);
                         __syncwarp();
                         if (lane == 0 && rown) { mbar_expect_tx(bar1, by1); bulk_g2s_hint(buf + e0, rown + e0, by1, bar1, pol_stream); }
                         const float d2 = warp_sum_butterfly(acc);
