@@ -513,6 +513,13 @@ typedef struct { float d; int32_t id; int expanded; } lent_t;
 
 static inline int key_lt(float da, int32_t ia, float db, int32_t ib) { return da < db || (da == db && ia < ib); }
 
+/* Throughput-mode option (DR "empty-step doubling", csrc/search_fast.cu): after a step none of whose newcomers entered the list, the
+ * next step expands up to g_w_after_empty entries instead of W (0 = off).  Process-wide; set before a batch, read-only during it. */
+static int g_w_after_empty = 0;
+void orc_set_w_after_empty(int w2) { g_w_after_empty = w2; }
+static int g_steps_total = 0, g_steps_empty = 0;   /* statistics of the last single-threaded calls (experiments) */
+void orc_step_stats(int *total, int *empty, int reset) { *total = g_steps_total; *empty = g_steps_empty; if (reset) g_steps_total = g_steps_empty = 0; }
+
 static int search_list_impl(const uint32_t *adj, int R, long N,
                     const uint8_t *codes, int M, const float *lut,
                     const float *vec, int D, const float *q, int flavor,
@@ -525,8 +532,10 @@ static int search_list_impl(const uint32_t *adj, int R, long N,
     lent_t *lst = (lent_t *)malloc(sizeof(lent_t) * (size_t)(L + 1));
     int gcap = 64, ng = 0;
     lent_t *ghost = (lent_t *)malloc(sizeof(lent_t) * (size_t)gcap); /* evicted, unexpanded, d == worst d */
-    lent_t *nw = (lent_t *)malloc(sizeof(lent_t) * (size_t)(W * R + 1));
+    const int W2 = (!strict_ties && g_w_after_empty > W) ? g_w_after_empty : W;
+    lent_t *nw = (lent_t *)malloc(sizeof(lent_t) * (size_t)(W2 * R + 1));
     int n = 0, hops = 0, nvis = 0;
+    int Wcur = W;                   /* expansions allowed in the coming step */
 
     float d0 = node_dist(&c, start);
     visited[start] = 1;
@@ -541,7 +550,7 @@ static int search_list_impl(const uint32_t *adj, int R, long N,
         if (strict_ties && ng > 0) {
             if (ghost[0].d > lst[n - 1].d) ng = 0; /* worst improved: ghosts can no longer be popped before the break */
         }
-        for (int i = 0; i < n && np_ < W; ++i)
+        for (int i = 0; i < n && np_ < Wcur; ++i)
             if (!lst[i].expanded) picked[np_++] = i;
         if (strict_ties && ng > 0) {
             /* W == 1 here.  the ghost with the smallest id vs the first unexpanded list entry */
@@ -595,6 +604,13 @@ static int search_list_impl(const uint32_t *adj, int R, long N,
             }
         } else {
             /* pure key-order merge: best L of old ∪ new */
+            int entered = 0;
+            const int full0 = n >= L;
+            const lent_t worst0 = lst[n - 1];
+            for (int t = 0; t < nn; ++t)
+                if (!full0 || key_lt(nw[t].d, nw[t].id, worst0.d, worst0.id)) ++entered;   /* the kernel's survivor test (worst of the step's start) */
+            Wcur = (entered == 0) ? W2 : W;
+            ++g_steps_total; g_steps_empty += (entered == 0);
             for (int t = 0; t < nn; ++t) {
                 if (n >= L && !key_lt(nw[t].d, nw[t].id, lst[n - 1].d, lst[n - 1].id)) continue;
                 int pos = n;

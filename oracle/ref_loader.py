@@ -50,3 +50,16 @@ def load():
                  "pydiskann.io.diskann_persist"):
         mods[name.split(".")[-1]] = importlib.import_module(name)
     return mods
+
+
+def load_dataset_benchmark():
+    """The reference's dataset_benchmark.py (its run_benchmark(args) prints the recall / latency / QPS table), or None."""
+    f = _REF / "dataset_benchmark.pycbin"
+    if not f.exists():
+        return None
+    load()                                   # pydiskann must resolve to oracle/_ref first
+    loader = importlib.machinery.SourcelessFileLoader("_reference_dataset_benchmark", str(f))
+    spec = importlib.util.spec_from_file_location("_reference_dataset_benchmark", str(f), loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod

@@ -1,4 +1,6 @@
 """the reference's dataset_benchmark.py protocol (dataset_benchmark.py:75-176) on the GPU path."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -36,3 +38,44 @@ def test_benchmark_table_on_sift_like_vectors():
     assert rec[0] - 0.02 <= out["disk"][1]["recall"] <= rec[1] + 0.02
     assert all(r["batched_qps"] > r["qps"] for r in out["in_memory"])
     assert 16 <= out["avg_degree"] <= 32
+
+
+def test_dimension_gate_admits_3072_and_the_patch_applies(tmp_path):
+    """f4: text-embedding-3-large collections.  The drop-in gate accepts what the reference accepts plus 3072, every admitted
+    dimension gets a usable PQ sub-vector count, and the shipped patch turns the reference's own gate (when the tree is here)."""
+    import importlib.util
+    import subprocess
+    from diskrag_b200 import config_gate as gate
+    assert all(gate.validate_vector_dimension(d) for d in (128, 256, 768, 960, 1536, 3072)) and not gate.validate_vector_dimension(100)
+    for d in sorted(gate.SUPPORTED_DIMENSIONS):
+        m = gate.pq_subvectors_for(d)
+        assert m > 0 and d % m == 0
+    src = Path("/root/reference/preprocessing/config.py")
+    if not src.exists():
+        return
+    work = tmp_path / "preprocessing"
+    work.mkdir()
+    (work / "config.py").write_text(src.read_text())
+    patch = Path(__file__).resolve().parents[1] / "integration" / "0001-accept-3072-dimensional-collections.patch"
+    subprocess.check_call(["patch", "-p1", "-s", "-d", str(tmp_path), "-i", str(patch)])
+    text = (work / "config.py").read_text()
+    ns = {}
+    exec(compile("SUPPORTED" + text.split("SUPPORTED", 1)[1].split("def get_text_hash", 1)[0], "patched_config", "exec"), ns)
+    assert ns["validate_vector_dimension"](3072) and ns["validate_vector_dimension"](1536) and not ns["validate_vector_dimension"](100)
+
+
+@pytest.mark.gpu
+def test_parquet_protocol_against_the_reference_driver():
+    """f4: the reference's own benchmark driver and this package on the same parquet files (SIFT-like, reference column layout):
+    same table shape, GPU recall within 2 points of the reference's on every row (its graph is built by another algorithm)."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "tools"))
+    import dataset_benchmark_ab as ab
+    out = ab.run(3000, 100, R=16, L=32)
+    g = out["gpu"]
+    assert [r["L"] for r in g["in_memory"]] == [50, 100, 200] and [r["beam"] for r in g["disk"]] == [24, 32, 48, 64]
+    if out["reference"] is not None:
+        r = out["reference"]
+        assert [x["param"] for x in r["in_memory"]] == [50, 100, 200] and [x["param"] for x in r["disk"]] == [24, 32, 48, 64]
+        for a, b in zip(g["in_memory"] + g["disk"], r["in_memory"] + r["disk"]):
+            assert a["recall"] >= b["recall"] - 0.02, (a, b)
