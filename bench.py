@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--M", type=int, default=192)
     ap.add_argument("--L", type=int, default=100)
     ap.add_argument("--W", type=int, default=8)
+    ap.add_argument("--W2", type=int, default=16, help="expansions of a step that follows a step without survivors (0 = off; results restated by the oracle)")
     ap.add_argument("--adc", default="tree", choices=["seq", "tree"])
     ap.add_argument("--lut", default="u8tc", choices=["f32", "u8", "u8tc"], help="ADC table: f32 reference arithmetic, u8 exact 8-bit, u8tc 8-bit built on tensor cores")
     ap.add_argument("--prefetch", type=int, default=5, help="L2 prefetch bit mask of the throughput kernel (include/diskrag_b200.h); results are unchanged")
@@ -264,7 +265,7 @@ def run_ours(a):
         Q = synth_torch(B, a.dim, seed=20242, sample_seed=1000 + rank, device=dev)     # each rank: its own query shard
         total_queries = world * B
     p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut, hash_cap=a.hash_cap,
-                           prefetch=int(a.prefetch))
+                           prefetch=int(a.prefetch), w2=a.W2 if a.lut != "f32" else 0)
     ids = torch.empty((B, k), dtype=torch.int32, device=dev); dd = torch.empty((B, k), dtype=torch.float32, device=dev)
     hops = torch.empty(B, dtype=torch.int32, device=dev); vis = torch.empty(B, dtype=torch.int32, device=dev)
     llen = torch.empty(B, dtype=torch.int32, device=dev); stat = torch.empty(B, dtype=torch.int32, device=dev)
@@ -400,7 +401,7 @@ def run_ours(a):
         points = []
         for Lp in (50, 64, 80):
             pp = engine.make_params(k=k, L=Lp, W=a.W, dist="pq", adc_order=a.adc, rerank=True, threads=a.threads, lut=a.lut,
-                                    hash_cap=a.hash_cap, prefetch=int(a.prefetch))
+                                    hash_cap=a.hash_cap, prefetch=int(a.prefetch), w2=a.W2 if a.lut != "f32" else 0)
             run = lambda: idx.search_dev(Q.data_ptr(), B, pp, ids.data_ptr(), dd.data_ptr(), hops.data_ptr(), vis.data_ptr(),
                                          d_list_len=llen.data_ptr(), d_status=stat.data_ptr(), stream=stream)
             run(); torch.cuda.synchronize(dev)
@@ -418,7 +419,8 @@ def run_ours(a):
                "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                "dtype": DTYPES[a.lut], "data": "synthetic",
                "config": {"workload": f"{a.n}x{a.dim} synthetic unit-norm, Vamana R={a.R} (GPU-built, Lbuild={a.Lbuild}, alpha=1.2), "
-                                      f"PQ M={a.M}, L={a.L}, W={a.W}, adc={a.adc}, table={a.lut}, rerank, top-{a.k}"
+                                      f"PQ M={a.M}, L={a.L}, W={a.W}" + (f" ({a.W2} after a step without survivors)" if a.W2 > a.W and a.lut != "f32" else "")
+                                      + f", adc={a.adc}, table={a.lut}, rerank, top-{a.k}"
                                       + (f"; ONE {a.queries}-query batch split over the GPUs" if a.scaling == "strong" else ""),
                           "queries_per_gpu_per_step": B, "queries_per_step_total": total_queries, "index": "replicated",
                           "queries": "sharded", "recall_at_10": round(rec, 4), "parity_mode": parity, "cpu_affinity": affinity,
@@ -454,7 +456,8 @@ def run_index_sharded(a):
                                            keepalive=(X, adj, codes, cb))
     B, k = a.queries, a.k
     Q = synth_torch(B, a.dim, seed=20245, sample_seed=100_000, device=dev)          # the SAME batch on every rank
-    p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, lut=a.lut, prefetch=int(a.prefetch))
+    p = engine.make_params(k=k, L=a.L, W=a.W, dist="pq", adc_order=a.adc, rerank=True, lut=a.lut, prefetch=int(a.prefetch),
+                           w2=a.W2 if a.lut != "f32" else 0)
     ids = torch.empty((B, k), dtype=torch.int32, device=dev); dd = torch.empty((B, k), dtype=torch.float32, device=dev)
     hops = torch.empty(B, dtype=torch.int32, device=dev); vis = torch.empty(B, dtype=torch.int32, device=dev)
     llen = torch.empty(B, dtype=torch.int32, device=dev); stat = torch.empty(B, dtype=torch.int32, device=dev)
@@ -593,7 +596,7 @@ def cpu_baseline_port(a, X, adj, codes, cb, med, Q, ids_gpu):
     ids, d, hops, vis = O.search_batch(adjh, Xh, Qs, med, a.L, a.k, codes=ch, codebook=cbh,
                                        dist_mode=O.DIST_ADC_U8 if a.lut != "f32" else (O.DIST_ADC_TREE if a.adc == "tree" else O.DIST_ADC_SEQ),
                                        flavor=O.FLAVOR_WARP,
-                                       W=a.W, rerank_=True)
+                                       W=a.W, rerank_=True, w_after_empty=a.W2 if a.lut != "f32" else 0)
     dt = time.perf_counter() - t
     same = float(np.mean(np.all(ids == ids_gpu[:n], axis=1)))
     return {"value": round(n / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",

@@ -23,7 +23,7 @@ class SearchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("L", C.c_int32), ("W", C.c_int32), ("dist", C.c_int32),
                 ("adc_order", C.c_int32), ("rerank", C.c_int32), ("sqrt_out", C.c_int32),
                 ("hash_cap", C.c_int32), ("chunk", C.c_int32), ("threads", C.c_int32), ("lut_fmt", C.c_int32),
-                ("prefetch", C.c_int32), ("start_plus1", C.c_int32), ("ignore_deleted", C.c_int32)]
+                ("prefetch", C.c_int32), ("start_plus1", C.c_int32), ("w_after_empty", C.c_int32), ("ignore_deleted", C.c_int32)]
 
 
 _vp, _i32, _i64, _u64, _f32, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double

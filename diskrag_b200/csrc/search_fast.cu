@@ -21,6 +21,7 @@ struct FastArgs {
     const float *Q; const uint8_t *lut8; const float *lut_scale; const float *lut_offset;
     long long N; int D, R, M;
     long long B; int k, L, W;
+    int W2;         // expansions of a step that follows a step without survivors (>= W; == W: off)
     int rerank, sqrt_out, prefetch;
     uint32_t start;
     int32_t *out_ids; float *out_dist; int32_t *out_hops; int32_t *out_visited;
@@ -287,6 +288,10 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #ifndef DR_PF_SPEC
 #define DR_PF_SPEC 5
 #endif
+// "empty-step doubling" of the serving-shape specialisations (RW8 >= 1 fixes W = 8): dr_search_params.w_after_empty they are compiled for
+#ifndef DR_W2_SPEC
+#define DR_W2_SPEC 16
+#endif
 #ifndef DR_L2V
 #define DR_L2V 0   // experiment (scripts/build_variants.py): 1 = the serving-shape specialisations keep the visited set in the
 #endif             // CTA's L2-resident table (no shared-memory hash) so that four CTAs fit on an SM; pair with DR_FAST_NT=192
@@ -340,6 +345,9 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     const uint8_t *deleted = RW8 == 4 ? nullptr : a.deleted;
     const bool do_rerank = RW8 == 4 ? true : (a.rerank != 0);
     const int R = RW8 ? 32 : a.R, W = RW8 ? 8 : a.W;
+    // A step none of whose newcomers entered the list leaves the list as it was, so the entries the NEXT steps expand are already
+    // known: the following step expands up to W2 of them at once (same expansions, same claims, fewer barrier-separated steps)
+    const int W2 = RW8 ? DR_W2_SPEC : a.W2;
     const int words = WORDS > 0 ? WORDS : (M >> 2);
     const uint32_t hmask = hcap ? hcap - 1u : 0u, ovf_mask = a.ovf_cap - 1u;
     const uint32_t hshift = 32u - (uint32_t)__popc(hmask), ovf_shift = 32u - (uint32_t)__popc(ovf_mask);
@@ -446,8 +454,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             int *p_nn = &s_nn2[step & 1];
             const int ns = s_ns;
             if (ns == 0) break;
-            const bool use_ovf_now = (s_hcount + W * R > hlimit);   // same value for every thread (read after the last barrier)
-            if (use_ovf_now && (s_ovfcount + W * R > ovf_limit)) {
+            const bool use_ovf_now = (s_hcount + W2 * R > hlimit);   // same value for every thread (read after the last barrier)
+            if (use_ovf_now && (s_ovfcount + W2 * R > ovf_limit)) {
                 if (tid == 0) s_status |= DR_ST_VISITED_OVERFLOW;
                 if (adj_async)      // rows already on their way: consume their barrier phases so the next query starts in step
                     for (int s = wid; s < ns; s += nw) { mbar_wait(&s_adjbar[s], (adj_par >> s) & 1u); adj_par ^= 1u << s; }
@@ -732,13 +740,13 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 for (int x = tid; x < n; x += nt) {
                     const int r = (int)ur_old[x] - ubase;
                     if (!(lst[x] & 1ull)) {
-                        if (r < W) {
+                        if (r < W2) {
                             s_sel[W + r] = (uint32_t)x;
                             if (adj_async) {
                                 mbar_expect_tx(&s_adjbar[r], (uint32_t)R * 4u);
                                 bulk_g2s(s_adjrow + r * R, a.adj + (size_t)key_id(lst[x]) * R, (uint32_t)R * 4u, &s_adjbar[r]);
                             }
-                        } else if (r < 2 * W) {
+                        } else if (W2 == W && r < 2 * W) {
                             if (spec_code) s_sel[r - W] = (uint32_t)x;
                             if (spec) {
                                 for (int o = 0; o < R; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + (size_t)key_id(lst[x]) * R + o));
@@ -750,8 +758,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 if (tid == 0) {
                     int tot = (int)ur_old[n] - ubase;
                     tot = tot > 0 ? tot : 0;
-                    s_ns = tot < W ? tot : W;
-                    s_nspec = tot < W ? 0 : (tot < 2 * W ? tot - W : W);
+                    s_ns = tot < W2 ? tot : W2;
+                    s_nspec = (W2 != W || tot < W) ? 0 : (tot < 2 * W ? tot - W : W);
                     if (spec && tot < 2 * W) s_pfkey = DR_KEY_MAX;
                 }
                 __syncthreads();
@@ -929,7 +937,10 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     memset(&a, 0, sizeof(a));
     a.vec = h->d_vec; a.adj = h->d_adj; a.codes = h->d_codes; a.deleted = p->ignore_deleted ? nullptr : h->d_deleted;
     a.N = h->N; a.D = h->D; a.R = h->R; a.M = h->M;
-    a.k = p->k; a.L = p->L; a.W = p->W; a.rerank = p->rerank; a.sqrt_out = p->sqrt_out; a.prefetch = p->prefetch;
+    a.W2 = p->w_after_empty > p->W ? p->w_after_empty : p->W;
+    DR_CHECK(a.W2 <= 32, "dr_search: w_after_empty must be <= 32 (got %d)", p->w_after_empty);
+    // (the next-in-line prefetch bits 2 / 8 / 16 assume a fixed W: cleared below when the doubling is on; they are off by default)
+    a.k = p->k; a.L = p->L; a.W = p->W; a.rerank = p->rerank; a.sqrt_out = p->sqrt_out; a.prefetch = (a.W2 > p->W) ? (p->prefetch & ~(2 | 8 | 16)) : p->prefetch;
     if ((h->R & 3) != 0 || p->W > 16) a.prefetch &= ~16;   // bulk copies of adjacency rows need 16-byte rows; 16 barriers
     if (h->d_peer_recv) {
         DR_CHECK(p->rerank && !p->sqrt_out && B <= h->peer_B, "dr_search: the peer-routed exchange needs rerank = 1, sqrt_out = 0 and B <= the routed batch");
@@ -943,7 +954,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     // hash_cap < 0: the visited set lives entirely in the CTA's global table (L2-resident, 32 KB per CTA): no shared-memory
     // hash, so a fourth CTA fits on the SM next to three 48 KB tables (the kernel is bound by resident queries)
     const bool l2_visited = p->hash_cap < 0 || (DR_L2V && p->hash_cap == 0);
-    int shape = (h->R == 32 && p->W == 8) ? (h->D == 1536 ? 2 : 1) : 0;
+    int shape = (h->R == 32 && p->W == 8 && a.W2 == DR_W2_SPEC) ? (h->D == 1536 ? 2 : 1) : 0;
     if (shape == 2 && p->L == 100 && p->hash_cap == 0) shape = 3;   // confirmed below once the table size is known
     fast_kernel_t kern = nullptr;
     // Region 0 holds the ADC table during the traversal and the rerank's row staging slots afterwards.  A small table
@@ -965,10 +976,10 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     a.o_list1 = off; off += LC * 8;
     a.o_ur0 = off; off += ((LC + 2) * 2 + 7) / 8 * 8;
     a.o_ur1 = off; off += ((LC + 2) * 2 + 7) / 8 * 8;
-    const int NC = (p->W * h->R + 1) & ~1;
+    const int NC = (a.W2 * h->R + 1) & ~1;
     a.o_newk = off; off += NC * 8;
     a.o_newid = off; off += NC * 4;
-    a.o_sel = off; off += ((2 * p->W * 4 + 7) / 8) * 8;
+    a.o_sel = off; off += (((p->W + a.W2) * 4 + 7) / 8) * 8;
     off = (off + 15) / 16 * 16;
     a.o_adjrow = off;
     if (a.prefetch & 16) off += (p->W * h->R * 4 + 15) / 16 * 16;
@@ -995,7 +1006,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     } else if (p->hash_cap > 0) hc = (uint32_t)p->hash_cap;
     else {
         uint32_t want = 1024;
-        long long target = (long long)(p->L + 2 * p->W) * h->R;
+        long long target = (long long)(p->L + 2 * a.W2) * h->R;
         while ((long long)want * 3 / 4 < target && want < 65536) want <<= 1;
         hc = want;
         // prefer three CTAs per SM: shrink the table down to 4096 slots to get there (the overflow table takes the tail)
@@ -1026,7 +1037,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     a.ovf_cap = 65536;
     if (l2_visited) {   // sized for the visit count (<= 1/2 load), small enough that all CTAs' tables stay in L2
         uint32_t want = 8192;
-        while ((long long)want / 2 < (long long)(p->L + 2 * p->W) * h->R && want < 65536) want <<= 1;
+        while ((long long)want / 2 < (long long)(p->L + 2 * a.W2) * h->R && want < 65536) want <<= 1;
         a.ovf_cap = want;
     }
     size_t need = (size_t)max_grid * a.ovf_cap * 4;

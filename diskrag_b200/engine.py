@@ -23,14 +23,14 @@ class SearchResult:
 
 
 def make_params(k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_out=False, hash_cap=0, chunk=0,
-                threads=0, lut="f32", prefetch=False, start=None, ignore_deleted=False) -> SearchParams:
+                threads=0, lut="f32", prefetch=False, start=None, ignore_deleted=False, w2=0) -> SearchParams:
     """start: entry point of the call (the reference's start_idx); None = the index's own (medoid)."""
     return SearchParams(k=k, L=L, W=W, dist={"pq": _lib.DR_DIST_PQ, "cosine": _lib.DR_DIST_COSINE}.get(dist, _lib.DR_DIST_EXACT),
                         adc_order=_lib.DR_ADC_TREE if adc_order == "tree" else _lib.DR_ADC_SEQ,
                         rerank=int(bool(rerank)), sqrt_out=int(bool(sqrt_out)), hash_cap=hash_cap, chunk=chunk,
                         threads=threads, lut_fmt={"u8": _lib.DR_LUT_U8, "u8tc": _lib.DR_LUT_U8_TC}.get(lut, _lib.DR_LUT_F32),
                         prefetch=int(prefetch), start_plus1=0 if start is None else int(start) + 1,
-                        ignore_deleted=int(bool(ignore_deleted)))
+                        ignore_deleted=int(bool(ignore_deleted)), w_after_empty=int(w2))
 
 
 class GpuIndex:
@@ -139,7 +139,7 @@ class GpuIndex:
     # ---- search ---------------------------------------------------------------------------------
     def search(self, Q, k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, sqrt_out=False, lut=None,
                want_list=False, trace=0, hash_cap=0, chunk=0, threads=0, lut_fmt="f32", prefetch=False, start=None,
-               ignore_deleted=False) -> SearchResult:
+               ignore_deleted=False, w2=0) -> SearchResult:
         """Batched search of Q f32[B,D] (host).  Returns host numpy arrays."""
         Q = as_f32(np.atleast_2d(Q))
         B, D = Q.shape
@@ -147,7 +147,7 @@ class GpuIndex:
             raise ValueError(f"query dimension {D} != index dimension {self.D}")
         if dist == "pq" and self.M == 0:
             raise ValueError("index has no PQ codes; use dist='exact'")
-        p = make_params(k, L, W, dist, adc_order, rerank, sqrt_out, hash_cap, chunk, threads, lut_fmt, prefetch, start, ignore_deleted)
+        p = make_params(k, L, W, dist, adc_order, rerank, sqrt_out, hash_cap, chunk, threads, lut_fmt, prefetch, start, ignore_deleted, w2)
         if lut is not None:
             lut = as_f32(lut).reshape(B, self.M, 256)
         ids = np.empty((B, k), np.int32); dd = np.empty((B, k), np.float32)

@@ -74,6 +74,10 @@ typedef struct dr_search_params {
                           while the merge that selected them is still finishing (needs R % 4 == 0 and W <= 16, ignored otherwise) */
     int32_t start_plus1; /* entry point of THIS call (the reference passes start_idx per call): 0 = the index's own (medoid /
                           dr_index_set_start), s + 1 = node s.  Per call, so concurrent callers never see each other's start */
+    int32_t w_after_empty; /* DR_LUT_U8* only.  0 / <= W: off.  Otherwise a step that follows a step WITHOUT survivors (no newcomer
+                          entered the list, so the list and hence the next entries to expand are unchanged) expands up to this many
+                          entries instead of W: the same expansions in fewer barrier-separated steps ("empty-step doubling").
+                          Restated by the oracle (orc_set_w_after_empty); <= 32 */
     int32_t ignore_deleted; /* 1: this call does not look at the lazy-delete mask — greedy_search / greedy_search_optimized
                           (vamana_graph.py:607-640, 762-793) never test is_deleted; greedy_search_cython does (cython_utils.pyx:84-120) */
 } dr_search_params;

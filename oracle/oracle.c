@@ -610,7 +610,7 @@ static int search_list_impl(const uint32_t *adj, int R, long N,
             for (int t = 0; t < nn; ++t)
                 if (!full0 || key_lt(nw[t].d, nw[t].id, worst0.d, worst0.id)) ++entered;   /* the kernel's survivor test (worst of the step's start) */
             Wcur = (entered == 0) ? W2 : W;
-            ++g_steps_total; g_steps_empty += (entered == 0);
+            __atomic_fetch_add(&g_steps_total, 1, __ATOMIC_RELAXED); __atomic_fetch_add(&g_steps_empty, entered == 0, __ATOMIC_RELAXED);
             for (int t = 0; t < nn; ++t) {
                 if (n >= L && !key_lt(nw[t].d, nw[t].id, lst[n - 1].d, lst[n - 1].id)) continue;
                 int pos = n;

@@ -146,10 +146,15 @@ def search_heap(adj, start, L, *, codes=None, lut_=None, vec=None, q=None, dist_
 
 
 def search_list(adj, start, L, *, codes=None, lut_=None, vec=None, q=None, dist_mode=DIST_ADC_SEQ,
-                flavor=FLAVOR_WARP, W=1, strict_ties=True, trace=0, deleted=None):
-    """Sorted-L-list form with W expansions per step: the exact statement of the GPU kernel."""
-    return _search("orc_search_list", adj, codes, lut_, vec, q, flavor, dist_mode,
-                   (C.c_int(W), C.c_int(int(strict_ties))), start, L, trace, deleted)
+                flavor=FLAVOR_WARP, W=1, strict_ties=True, trace=0, deleted=None, w_after_empty=0):
+    """Sorted-L-list form with W expansions per step: the exact statement of the GPU kernel.  w_after_empty > W (throughput mode,
+    strict_ties = False): a step that follows a step without survivors expands up to that many entries (dr_search_params)."""
+    lib().orc_set_w_after_empty(C.c_int(int(w_after_empty)))
+    try:
+        return _search("orc_search_list", adj, codes, lut_, vec, q, flavor, dist_mode,
+                       (C.c_int(W), C.c_int(int(strict_ties))), start, L, trace, deleted)
+    finally:
+        lib().orc_set_w_after_empty(C.c_int(0))
 
 
 def beam_c(adj, start, beam_width, k, *, codes=None, lut_=None, vec=None, q=None, dist_mode=DIST_ADC_SEQ,
@@ -217,7 +222,7 @@ def rerank(vec, q, ids, k, flavor=FLAVOR_WARP):
 
 
 def search_batch(adj, vec, Q, start, L, k, *, codes=None, codebook=None, dist_mode=DIST_ADC_SEQ,
-                 flavor=FLAVOR_WARP, W=1, rerank_=True, nthreads=0):
+                 flavor=FLAVOR_WARP, W=1, rerank_=True, nthreads=0, w_after_empty=0):
     adj = np.ascontiguousarray(adj, np.uint32); vec = _f32(vec); Q = _f32(Q)
     N, R = adj.shape; B, D = Q.shape
     M = 0
@@ -225,10 +230,12 @@ def search_batch(adj, vec, Q, start, L, k, *, codes=None, codebook=None, dist_mo
         codes = np.ascontiguousarray(codes, np.uint8); M = codes.shape[1]; codebook = _f32(codebook)
     ids = np.empty((B, k), np.int32); d = np.empty((B, k), np.float32)
     hops = np.empty(B, np.int32); nvis = np.empty(B, np.int32)
+    lib().orc_set_w_after_empty(C.c_int(int(w_after_empty)))      # read-only inside the (OpenMP) batch
     lib().orc_search_batch(_p(adj), C.c_int(R), C.c_long(N), _p(codes), C.c_int(M), _p(codebook),
                            _p(vec), C.c_int(D), _p(Q), C.c_long(B), C.c_int(dist_mode), C.c_int(flavor),
                            C.c_int(W), C.c_int(int(start)), C.c_int(L), C.c_int(k), C.c_int(int(rerank_)),
                            _p(ids), _p(d), _p(hops), _p(nvis), C.c_int(nthreads))
+    lib().orc_set_w_after_empty(C.c_int(0))
     return ids, d, hops, nvis
 
 

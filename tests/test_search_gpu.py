@@ -196,6 +196,26 @@ def test_u8_prefetch_bits_never_change_results(case, W, L):
         assert np.array_equal(r.hops, ref.hops) and np.array_equal(r.visited, ref.visited), (pf, hc)
 
 
+@pytest.mark.parametrize("W,W2,L", [(8, 16, 100), (4, 8, 48), (2, 32, 64), (8, 16, 20), (1, 4, 32)])
+def test_u8_empty_step_doubling_vs_oracle(case, orc, W, W2, L):
+    """w_after_empty: a step that follows a step without survivors expands up to W2 entries.  Bit-for-bit against the oracle's
+    restatement of the rule (lists, hops, visited, reranked results), also through the overflow path of a tiny visited table."""
+    c = case
+    r = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5, w2=W2)
+    r2 = c["idx"].search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5, w2=W2, hash_cap=256)
+    assert np.array_equal(r.list_ids, r2.list_ids) and np.array_equal(r.ids, r2.ids) and np.array_equal(r.hops, r2.hops)
+    fewer = 0
+    for qi in range(c["Q"].shape[0]):
+        t8, sc, off = orc.lut_u8(c["codebook"], c["Q"][qi])
+        l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False,
+                            w_after_empty=W2)
+        n = r.list_len[qi]
+        assert np.array_equal(l["ids"], r.list_ids[qi, :n]), (qi, W, W2)
+        assert (r.hops[qi], r.visited[qi]) == (l["hops"], l["visited"])
+        oi, od = orc.rerank(c["X"], c["Q"][qi], l["ids"], 10, flavor=orc.FLAVOR_WARP)
+        assert np.array_equal(oi, r.ids[qi, :len(oi)]) and np.array_equal(od, r.dists[qi, :len(od)])
+
+
 def test_visited_overflow_table(case, orc):
     """Force a tiny shared-memory visited table so the global overflow table is exercised; results must not change."""
     c = case
@@ -237,23 +257,29 @@ def test_export_records_roundtrip(golden, gidx):
 
 
 def test_bench_shape_specialisation_vs_oracle(orc):
-    """The compile-time-specialised instantiation the bench runs (D = 1536, M = 192, R = 32, W = 8, L = 100, 4096-slot visited
-    table, prefetch mask 5, rerank): bit-for-bit against the restatement with the exact 8-bit table, and the same ids with
+    """The compile-time-specialised instantiation the bench runs (D = 1536, M = 192, R = 32, W = 8 doubling to 16 after an empty step,
+    L = 100, 4096-slot visited table, prefetch mask 5, rerank): bit-for-bit against the restatement with the exact 8-bit table, and the same ids with
     the tensor-core table on all but near-tie queries."""
     from diskrag_b200.engine import GpuIndex
     c = make_case(orc, 2500, 1536, 192, 32, 48, 31, nq=16)
     L, W = 100, 8
     with GpuIndex.from_arrays(c["X"], c["adj"], c["codes"], c["codebook"], c["medoid"]) as idx:
-        r = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=False, lut_fmt="u8", prefetch=5)
-        rl = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5)   # generic flags path
-        rt = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8tc", prefetch=5)
+        r = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=False, lut_fmt="u8", prefetch=5, w2=16)
+        rl = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5, w2=16)   # generic flags path
+        rt = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8tc", prefetch=5, w2=16)
         rp = [idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8", prefetch=pf) for pf in (13, 21, 29)]
+        r0 = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8", prefetch=5)
     assert np.array_equal(r.ids, rl.ids) and np.array_equal(r.dists, rl.dists) and np.array_equal(r.hops, rl.hops)
-    for x in rp:    # the other prefetch masks (one of them is the compiled serving shape, DR_PF_SPEC): same answers
-        assert np.array_equal(r.ids, x.ids) and np.array_equal(r.dists, x.dists) and np.array_equal(r.hops, x.hops) and np.array_equal(r.visited, x.visited)
+    for x in rp:    # the prefetch masks change nothing (fixed W: the generic instantiation)
+        assert np.array_equal(r0.ids, x.ids) and np.array_equal(r0.dists, x.dists) and np.array_equal(r0.hops, x.hops) and np.array_equal(r0.visited, x.visited)
     for qi in range(c["Q"].shape[0]):
         t8, sc, off = orc.lut_u8(c["codebook"], c["Q"][qi])
-        l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False)
+        l0 = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False)
+        assert (r0.hops[qi], r0.visited[qi]) == (l0["hops"], l0["visited"])
+        oi0, od0 = orc.rerank(c["X"], c["Q"][qi], l0["ids"], 10, flavor=orc.FLAVOR_WARP)
+        assert np.array_equal(oi0, r0.ids[qi, :len(oi0)]) and np.array_equal(od0, r0.dists[qi, :len(od0)])
+        l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False,
+                            w_after_empty=16)
         assert (r.hops[qi], r.visited[qi]) == (l["hops"], l["visited"])
         assert np.array_equal(l["ids"], rl.list_ids[qi, :rl.list_len[qi]])
         oi, od = orc.rerank(c["X"], c["Q"][qi], l["ids"], 10, flavor=orc.FLAVOR_WARP)

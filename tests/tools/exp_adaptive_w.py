@@ -2,7 +2,7 @@
 and what expanding more entries after such a step would change (steps, hops, rows evaluated, recall)."""
 import ctypes as C, sys, argparse
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
 import numpy as np, torch
 import bench, oracle as O
