@@ -69,8 +69,23 @@ __device__ __forceinline__ uint32_t lds_u8_off(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(J));
     return v;
 }
+// One byte-wise multiply-add forms each lookup address: dp4a(w, stride in byte k, tb) = tb + stride * code byte k (IDP.4A), so a
+// lookup is address + LDS.U8 (+ its share of the adds) instead of extract (PRMT) + scale-add (IMAD) + LDS.U8.  stride <= 255.
+#ifndef DR_DP4A_ADDR
+#define DR_DP4A_ADDR 1
+#endif
 template <int STRIDE>
 __device__ __forceinline__ uint32_t tab_sum4(uint32_t tb, uint32_t w, int stride_rt) {
+#if DR_DP4A_ADDR
+    if (STRIDE == 128) {
+        return lds_u8_off<0>(__dp4a(w, 0x00000080u, tb)) + lds_u8_off<1>(__dp4a(w, 0x00008000u, tb)) +
+               lds_u8_off<2>(__dp4a(w, 0x00800000u, tb)) + lds_u8_off<3>(__dp4a(w, 0x80000000u, tb));
+    } else {
+        const uint32_t st = (uint32_t)stride_rt;     // <= 64: the tail chunk holds at most 16 words per centroid
+        return lds_u8_off<0>(__dp4a(w, st, tb)) + lds_u8_off<1>(__dp4a(w, st << 8, tb)) + lds_u8_off<2>(__dp4a(w, st << 16, tb)) +
+               lds_u8_off<3>(__dp4a(w, st << 24, tb));
+    }
+#else
     const uint32_t c0 = __byte_perm(w, 0u, 0x4440), c1 = __byte_perm(w, 0u, 0x4441), c2 = __byte_perm(w, 0u, 0x4442),
                    c3 = __byte_perm(w, 0u, 0x4443);
     if (STRIDE == 128) {
@@ -80,6 +95,7 @@ __device__ __forceinline__ uint32_t tab_sum4(uint32_t tb, uint32_t w, int stride
         const uint32_t st = (uint32_t)stride_rt;
         return lds_u8_off<0>(tb + c0 * st) + lds_u8_off<1>(tb + c1 * st) + lds_u8_off<2>(tb + c2 * st) + lds_u8_off<3>(tb + c3 * st);
     }
+#endif
 }
 
 // G code rows per warp (G even): lane l owns word 32 k + l of every full chunk; the tail words (rem <= 16) of TWO
