@@ -117,8 +117,6 @@ def build_index(a, dev, data_seed=20242, sample_seed=None, build_seed=1234):
     # medoid: sampled, as compute_approximate_medoid_cython does (1000 samples), through our kernel
     g = torch.Generator(device=dev); g.manual_seed(77)
     smp = torch.randperm(N, generator=g, device=dev)[:1000].to(torch.int32).cpu().numpy()
-    # dr_medoid takes host pointers; at 1M x 1536 use the device build path instead: nearest point to the sample centroid
-    # of distances is what the medoid approximates; we evaluate the exact sums on the device in chunks with torch-free C ABI
     med = medoid_dev(X, smp, dev)
     cb = torch.empty((M, 256, D // M), dtype=torch.float32, device=dev)
     codes = torch.empty((N, M), dtype=torch.uint8, device=dev)
@@ -140,21 +138,15 @@ def build_index(a, dev, data_seed=20242, sample_seed=None, build_seed=1234):
 
 
 def medoid_dev(X, samples, dev):
-    """argmin over samples of sum_j ||x_s - x_j|| (cython_utils.pyx:210-263) with device-resident X."""
+    """argmin over the samples of sum_j ||x_s - x_j|| (compute_approximate_medoid_cython, cython_utils.pyx:210-263) on the
+    device-resident corpus, through the library (dr_medoid_dev): no torch arithmetic in the setup either."""
     import torch
-    from diskrag_b200._lib import lib
-    # the host-pointer dr_medoid would copy 6 GB; evaluate the same sums with the library's distance kernel per sample
-    # block instead: here a torch reduction is plumbing for SETUP only (not timed, not the hot path)
-    s = torch.from_numpy(samples.astype(np.int64)).to(dev)
-    xs = X[s]
-    xn = (X * X).sum(1)
-    best, bi = None, 0
-    sums = torch.zeros(len(samples), dtype=torch.float64, device=dev)
-    for c0 in range(0, X.shape[0], 262144):
-        blk = X[c0:c0 + 262144]
-        d2 = (xs * xs).sum(1)[:, None] + xn[c0:c0 + 262144][None, :] - 2.0 * (xs @ blk.T)
-        sums += d2.clamp_min(0).sqrt().double().sum(1)
-    return int(samples[int(sums.argmin().item())])
+    from diskrag_b200._lib import check, lib
+    smp = torch.from_numpy(np.ascontiguousarray(samples, np.int32)).to(dev)
+    out = C.c_int64(0)
+    check(lib().dr_medoid_dev(X.data_ptr(), X.shape[0], X.shape[1], smp.data_ptr(), int(smp.numel()), C.byref(out), dev.index,
+                              torch.cuda.current_stream(dev).cuda_stream), "dr_medoid_dev")
+    return int(out.value)
 
 
 def ground_truth(X, Q, k):

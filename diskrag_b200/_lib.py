@@ -62,8 +62,10 @@ SIGNATURES = {
     "dr_cosine_batch": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, C.c_int]),
     "dr_pq_sdc_batch": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, C.c_int]),
     "dr_medoid": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _PP(_i64), C.c_int]),
+    "dr_medoid_dev": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _PP(_i64), C.c_int, _vp]),
     "dr_vamana_build": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _f32, _i64, _u64, _vp, _vp, C.c_int]),
     "dr_vamana_build_dev": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _f32, _i64, _u64, _vp, _vp, C.c_int, _vp]),
+    "dr_vamana_build_last_truncated": (_i64, []),
     "dr_robust_prune": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _i32, _vp, _PP(_i32), C.c_int]),
     "dr_index_set_deleted": (C.c_int, [_vp, _vp]),
     "dr_index_set_start": (C.c_int, [_vp, _i64]),

@@ -43,6 +43,8 @@ int launch_deinterleave(const void *, int64_t, int, int, float *, uint32_t *, cu
 int launch_prune_one(const float *, int, int, float, int, uint32_t *, int32_t *, cudaStream_t);
 int launch_interleave(const float *, const uint32_t *, int64_t, int, int, void *, cudaStream_t);
 
+extern std::atomic<long long> g_build_truncated;   // build.cu
+
 // small RAII device buffer for the host-pointer entry points
 struct DevBuf {
     void *p = nullptr;
@@ -621,6 +623,25 @@ int dr_medoid(const float *X, int64_t N, int32_t D, const int32_t *samples, int3
     return 0;
 }
 
+int dr_medoid_dev(const float *d_X, int64_t N, int32_t D, const int32_t *d_samples, int32_t ns, int64_t *out_medoid, int device,
+                  void *stream) {
+    if (use_device(device)) return 3;
+    DR_CHECK(d_X && d_samples && out_medoid && ns >= 1 && ns <= N, "dr_medoid_dev: need device arrays and 1 <= ns <= N");
+    DevBuf sums;
+    if (sums.alloc((size_t)ns * 8)) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (launch_medoid(d_X, N, D, d_samples, ns, N <= ns ? 1 : 0, sums.as<double>(), s)) return 1;
+    std::vector<double> hs(ns);
+    std::vector<int32_t> smp(ns);
+    DR_CUDA(cudaMemcpyAsync(hs.data(), sums.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, s));
+    DR_CUDA(cudaMemcpyAsync(smp.data(), d_samples, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
+    DR_CUDA(cudaStreamSynchronize(s));
+    int best = 0;
+    for (int i = 1; i < ns; ++i) if (hs[i] < hs[best]) best = i;
+    *out_medoid = smp[best];
+    return 0;
+}
+
 int dr_vamana_build_dev(const float *d_X, int64_t N, int32_t D, int32_t R, int32_t L, float alpha, int64_t medoid,
                         uint64_t seed, uint32_t *d_out_adj, int32_t *d_out_deg, int device, void *stream) {
     if (use_device(device)) return 3;
@@ -639,6 +660,8 @@ int dr_vamana_build(const float *X, int64_t N, int32_t D, int32_t R, int32_t L, 
     if (out_deg) DR_CUDA(cudaMemcpy(out_deg, deg.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
+
+int64_t dr_vamana_build_last_truncated(void) { return g_build_truncated.load(); }
 
 int dr_robust_prune(const float *p, const float *cand, int32_t n, int32_t D, float alpha, int32_t R, int32_t *out_sel,
                     int32_t *out_n, int device) {

@@ -33,7 +33,9 @@ struct PruneArgs {
     // mode 1
     const uint32_t *rkeys; const uint32_t *rvals; const int32_t *heads; const int32_t *n_heads; int n_pairs;
     int n_items;
+    int *truncated;   // mode 1: targets whose incoming run did not fit PR_CMAX candidates (the rest of the run is dropped); may be NULL
 };
+std::atomic<long long> g_build_truncated{0};   // of the last dr_vamana_build in this process (dr_vamana_build_last_truncated)
 
 __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
     extern __shared__ __align__(16) float s_vecs[];  // [D] point p, [D] current p*
@@ -79,7 +81,9 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
             // incoming run: pairs h0.. while the key stays the same
             if (tid == 0) {
                 int m = dg;
-                for (int i = h0; i < a.n_pairs && a.rkeys[i] == node && m < PR_CMAX; ++i) { s_id[m] = a.rvals[i]; s_flag[m] = 0; ++m; }
+                int i = h0;
+                for (; i < a.n_pairs && a.rkeys[i] == node && m < PR_CMAX; ++i) { s_id[m] = a.rvals[i]; s_flag[m] = 0; ++m; }
+                if (a.truncated && i < a.n_pairs && a.rkeys[i] == node) atomicAdd(a.truncated, 1);   // reverse edges beyond the capacity
                 s_n = m;
             }
         }
@@ -229,7 +233,8 @@ int launch_vamana_build(const float *d_X, int64_t N, int D, int R, int L, float 
     DR_CUDA(cudaMalloc(&b.keys2, (size_t)max_pairs * 4));
     DR_CUDA(cudaMalloc(&b.vals2, (size_t)max_pairs * 4));
     DR_CUDA(cudaMalloc(&b.heads, (size_t)max_pairs * 4));
-    DR_CUDA(cudaMalloc(&b.n_heads, 4));
+    DR_CUDA(cudaMalloc(&b.n_heads, 8));      // [0] head count of the batch, [1] truncated-run counter of the whole build
+    DR_CUDA(cudaMemsetAsync(b.n_heads, 0, 8, s));
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, b.keys, b.keys2, b.vals, b.vals2, max_pairs, 0, 32, s);
     DR_CUDA(cudaMalloc(&b.cub_tmp, cub_bytes));
@@ -284,6 +289,7 @@ int launch_vamana_build(const float *d_X, int64_t N, int D, int R, int L, float 
             DR_LAUNCHED();
             PruneArgs pr = pa;
             pr.mode = 1; pr.rkeys = b.keys2; pr.rvals = b.vals2; pr.heads = b.heads; pr.n_heads = b.n_heads; pr.n_pairs = np;
+            pr.truncated = b.n_heads + 1;
             prune_kernel<<<(int)std::min<int64_t>(np, prune_grid_max), PR_THREADS, prune_smem, s>>>(pr);
             DR_LAUNCHED();
             start += bs;
@@ -292,7 +298,10 @@ int launch_vamana_build(const float *d_X, int64_t N, int D, int R, int L, float 
     const long long tot = (long long)N * R;
     finalize_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_adj, d_deg, N, R);
     DR_LAUNCHED();
+    int trunc = 0;
+    DR_CUDA(cudaMemcpyAsync(&trunc, b.n_heads + 1, 4, cudaMemcpyDeviceToHost, s));
     DR_CUDA(cudaStreamSynchronize(s));
+    g_build_truncated.store(trunc);
     return 0;
 }
 

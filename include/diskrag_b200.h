@@ -220,10 +220,18 @@ int dr_pq_sdc_batch(const float *codebook, const uint8_t *c1, const uint8_t *c2,
  *   The batched order differs from the reference's sequential insertion, so graphs are compared by
  *   recall, not bit-for-bit. */
 int dr_medoid(const float *X, int64_t N, int32_t D, const int32_t *samples, int32_t ns, int64_t *out_medoid, int device);
+/* device-pointer form (X and the sample ids already in HBM: indexes generated or built on the GPU) */
+int dr_medoid_dev(const float *d_X, int64_t N, int32_t D, const int32_t *d_samples, int32_t ns, int64_t *out_medoid, int device,
+                  void *stream);
 int dr_vamana_build(const float *X, int64_t N, int32_t D, int32_t R, int32_t L, float alpha, int64_t medoid,
                     uint64_t seed, uint32_t *out_adj, int32_t *out_deg, int device);
 int dr_vamana_build_dev(const float *d_X, int64_t N, int32_t D, int32_t R, int32_t L, float alpha, int64_t medoid,
                         uint64_t seed, uint32_t *d_out_adj, int32_t *d_out_deg, int device, void *stream);
+
+/* Status of the last dr_vamana_build[_dev] of this process: how many times a node's incoming reverse-edge run of one batch did not
+ * fit the prune kernel's candidate capacity (320) and its tail was dropped (quality only: the dropped edges are reverse edges of
+ * hub nodes; 0 on every configuration tested, reported so that it cannot happen silently).  L + R > 320 is refused outright. */
+int64_t dr_vamana_build_last_truncated(void);
 
 /* dr_robust_prune replaces robust_prune_cython (cython_utils.pyx:124-167) for one point: p f32[D], cand f32[n,D]
  *   given in ascending id order (n <= 320) -> out_sel i32[<=R] positions into cand in selection order, *out_n. */
