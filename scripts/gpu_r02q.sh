@@ -1,0 +1,4 @@
+set -x
+(cd oracle && gcc -O2 -fPIC -shared -fopenmp -ffp-contract=off oracle.c -o liboracle.so -lm)
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -4
+bash scripts/gpu_profile_misc.sh
