@@ -24,6 +24,7 @@
 #include "tc_common.cuh"
 
 #define TC_ROWS 128      // queries per CTA tile = TMEM lanes
+#define TC_THREADS 256   // two threads per query row: warps 0-3 take the first half of a stage's centroids, warps 4-7 the second
 #ifndef TC_NQ
 #define TC_NQ 32         // centroids per stage
 #endif
@@ -41,7 +42,9 @@ struct LutTcArgs {
     int words_per_cta;
 };
 
-// One stage: operands are in shared memory; thread 0 issues 4 x (nks + 1) MMAs and commits; everybody waits.
+// One stage: operands are in shared memory; thread 0 issues 4 x (nks + 1) MMAs and commits; stage_wait: everybody waits.
+// (Measured and dropped: fetching the next stage's B operand into a second buffer between issue and wait — the staging warps then
+// reach the epilogue late and the step gets 5 % slower; the other CTAs of the SM already cover the codebook loads.)
 __device__ __forceinline__ void stage_mma(uint32_t tmem, uint32_t a_base, uint32_t b_base, int nks1, uint64_t *bar, uint32_t &phase,
                                           int tid) {
     fence_proxy_async();          // this thread's generic-proxy operand writes -> visible to the tensor core (async proxy)
@@ -56,6 +59,8 @@ __device__ __forceinline__ void stage_mma(uint32_t tmem, uint32_t a_base, uint32
                           umma_desc(b_base + (uint32_t)((j * nks1 + ks) * (TC_NQ * 32))), idesc, ks > 0 ? 1u : 0u);
         umma_commit(bar);
     }
+}
+__device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t &phase) {
     mbar_wait(bar, phase);
     phase ^= 1u;
     tc_fence_after();
@@ -82,12 +87,13 @@ __device__ __forceinline__ void stage_B(const float *__restrict__ codebook, int 
     }
 }
 
-// grid (query tiles, word groups), 128 threads (thread = query = TMEM lane).
+// grid (query tiles, word groups), 256 threads: two per query row (= TMEM lane), each reducing half of a stage's centroids, so that
+// eight warps per CTA (32 per SM) cover the TMEM round trips and the store latency.
 // PHASE 1: lo[b][m] = min_c t and range_bits[b] = max(range_bits[b], max_c t - lo)        (then lut_u8_finalize_kernel)
 // PHASE 2: out32[b][w][c] = the four subspaces' quantised entries, packed
 // Dynamic shared memory: A blocks 4 * (nks+1) * 4 KB, then B blocks 4 * (nks+1) * TC_NQ * 32 B.
 template <int PHASE, int DS>   // DS: compile-time sub-dimension (8 / 16 / 24), 0 = runtime
-__global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS) lut_u8_tc_kernel(const LutTcArgs a) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
     const int ds = DS ? DS : a.ds, nks = ds >> 3, nks1 = nks + 1, words = a.M >> 2, D = a.D, M = a.M;
     unsigned char *sA = tc_smem;
     unsigned char *sB = tc_smem + 4 * nks1 * (TC_ROWS * 32);
-    uint32_t *sT = reinterpret_cast<uint32_t *>(sB + 4 * nks1 * (TC_NQ * 32));   // 4 warps x 32 rows x 20 words: store transposition
+    float *sS = reinterpret_cast<float *>(sB + 4 * nks1 * (TC_NQ * 32));           // phase 1: [128 rows][8] lo / hi of the upper half
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
 
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
@@ -104,11 +110,14 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t tlane = tmem + ((uint32_t)(wid * 32) << 16);    // this warp's 32-lane quarter of TMEM
+    const int half = wid >> 2, row = tid & (TC_ROWS - 1);
+    const bool owner = tid < TC_ROWS;                                   // stages the A operand of its row, owns its statistics
+    constexpr int HQ = TC_NQ / 2;                                       // centroids of a stage per thread (per subspace)
+    const uint32_t tlane = tmem + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)(half * HQ);   // this thread's lane quarter / column half
     uint32_t phase = 0;
 
     const long long b0 = (long long)blockIdx.x * TC_ROWS;
-    const long long b = b0 + tid;
+    const long long b = b0 + row;
     const bool live = b < a.B;
     const float *qrow = a.Q + (size_t)(live ? b : b0) * D;     // dead rows recompute row b0 and are never stored
     const int w_begin = blockIdx.y * a.words_per_cta;
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
         const float scale = range > 0.0f ? __fdiv_rn(range, 255.0f) : 1.0f;
         inv = __fdiv_rn(1.0f, scale);
         inv_hi = tf32_hi(inv); inv_lo = inv - inv_hi; mul = -2.0f * inv;
-        if (blockIdx.y == 0 && live) {
+        if (blockIdx.y == 0 && live && owner) {
             float acc = 0.0f, qn = 0.0f;
             for (int m = 0; m < M; ++m) acc = __fadd_rn(acc, a.lo[(size_t)b * M + m]);
             if ((D & 3) == 0) {       // same element order as the scalar loop, 16-byte loads
@@ -141,54 +150,55 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
     float rmax = 0.0f;
     for (int w = w_begin; w < w_end; ++w) {
         // A for this word: the row's 4 * ds query elements times -2 (phase 2: -2 inv), then the extra K-step
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4 && owner; ++j) {
             const float *src = qrow + (size_t)(4 * w + j) * ds;
             for (int kc = 0; kc < (ds >> 2); ++kc) {
                 float4 v = ldg_f4(src + kc * 4);
                 v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
-                *reinterpret_cast<float4 *>(sA + (j * nks1 + (kc >> 1)) * (TC_ROWS * 32) + core_off(tid, kc & 1)) = tf32_rna4(v);
+                *reinterpret_cast<float4 *>(sA + (j * nks1 + (kc >> 1)) * (TC_ROWS * 32) + core_off(row, kc & 1)) = tf32_rna4(v);
             }
             unsigned char *x = sA + (j * nks1 + nks) * (TC_ROWS * 32);
             if (PHASE == 1) {
-                *reinterpret_cast<float4 *>(x + core_off(tid, 0)) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
-                *reinterpret_cast<float4 *>(x + core_off(tid, 1)) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                *reinterpret_cast<float4 *>(x + core_off(row, 0)) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+                *reinterpret_cast<float4 *>(x + core_off(row, 1)) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             } else {
                 const float k0 = -__fmul_rn(a.lo[(size_t)(live ? b : b0) * M + 4 * w + j], inv);
                 const float kh = tf32_hi(k0);
-                *reinterpret_cast<float4 *>(x + core_off(tid, 0)) = make_float4(inv_hi, inv_hi, inv_lo, kh);
-                *reinterpret_cast<float4 *>(x + core_off(tid, 1)) = make_float4(k0 - kh, 0.0f, 0.0f, 0.0f);
+                *reinterpret_cast<float4 *>(x + core_off(row, 0)) = make_float4(inv_hi, inv_hi, inv_lo, kh);
+                *reinterpret_cast<float4 *>(x + core_off(row, 1)) = make_float4(k0 - kh, 0.0f, 0.0f, 0.0f);
             }
         }
         float lo[4], hi[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { lo[j] = __int_as_float(0x7f800000); hi[j] = -__int_as_float(0x7f800000); }
         for (int c0 = 0; c0 < 256; c0 += TC_NQ) {
-            stage_B(a.codebook, w, c0, ds, nks, sB, wid, lane);
+            if (wid < 4) stage_B(a.codebook, w, c0, ds, nks, sB, wid, lane);
             stage_mma(tmem, a_base, b_base, nks1, &s_bar, phase, tid);
+            stage_wait(&s_bar, phase);
             if (PHASE == 1) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                    for (int ch = 0; ch < TC_NQ / 16; ++ch) {
-                        float v[16];
-                        tmem_ld16(tlane + (uint32_t)(j * TC_NQ + ch * 16), v);
+                    for (int i8 = 0; i8 < HQ / 8; ++i8) {
+                        float v[8];
+                        tmem_ld8(tlane + (uint32_t)(j * TC_NQ + i8 * 8), v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { lo[j] = fminf(lo[j], v[i]); hi[j] = fmaxf(hi[j], v[i]); }
+                        for (int i = 0; i < 8; ++i) { lo[j] = fminf(lo[j], v[i]); hi[j] = fmaxf(hi[j], v[i]); }
                     }
                 }
             } else {
 #pragma unroll
-                for (int ch = 0; ch < TC_NQ / 16; ++ch) {
-                    float v0[16], v1[16], v2[16], v3[16];
-                    tmem_ld16(tlane + (uint32_t)(0 * TC_NQ + ch * 16), v0);
-                    tmem_ld16(tlane + (uint32_t)(1 * TC_NQ + ch * 16), v1);
-                    tmem_ld16(tlane + (uint32_t)(2 * TC_NQ + ch * 16), v2);
-                    tmem_ld16(tlane + (uint32_t)(3 * TC_NQ + ch * 16), v3);
+                for (int i8 = 0; i8 < HQ / 8; ++i8) {
+                    float v0[8], v1[8], v2[8], v3[8];
+                    tmem_ld8(tlane + (uint32_t)(0 * TC_NQ + i8 * 8), v0);
+                    tmem_ld8(tlane + (uint32_t)(1 * TC_NQ + i8 * 8), v1);
+                    tmem_ld8(tlane + (uint32_t)(2 * TC_NQ + i8 * 8), v2);
+                    tmem_ld8(tlane + (uint32_t)(3 * TC_NQ + i8 * 8), v3);
                     tmem_ld_wait();
-                    uint32_t pk[16];
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         uint32_t q0, q1, q2, q3;
                         asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q0) : "f"(v0[i]));
                         asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q1) : "f"(v1[i]));
@@ -196,35 +206,46 @@ __global__ void __launch_bounds__(TC_ROWS, TC_CTAS) lut_u8_tc_kernel(const LutTc
                         asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q3) : "f"(v3[i]));
                         pk[i] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
                     }
-                    // A lane holds 64 contiguous bytes of ITS row; written directly, one warp store would touch 32 rows x 16 B.
-                    // Transposed through a per-warp tile (row stride 80 B: conflict-free 16-byte stores), four lanes share a row
-                    // and one warp store covers 8 rows x 64 contiguous bytes (full 32-byte sectors).
-                    uint32_t *tile = sT + wid * (32 * 20);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<uint4 *>(tile + lane * 20 + i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
-                    __syncwarp();
+                    // A lane holds 32 contiguous bytes (one sector) of ITS row.  Lane pairs trade halves so that one store instruction
+                    // writes whole sectors: first the even lane's row (even lane: words 0-3, odd lane: words 4-7), then the odd lane's.
+                    const bool odd = lane & 1;
+                    uint32_t s0[4], s1[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int r = i * 8 + (lane >> 2), c4 = (lane & 3) * 4;
-                        const uint4 v = *reinterpret_cast<const uint4 *>(tile + r * 20 + c4);
-                        const long long br = b0 + wid * 32 + r;
-                        if (br < a.B)
-                            *reinterpret_cast<uint4 *>(a.out32 + ((size_t)br * words + w) * 256 + c0 + ch * 16 + c4) = v;
+                        s0[i] = __shfl_xor_sync(DR_FULL, odd ? pk[i] : pk[4 + i], 1);   // even gives A[4..7], odd gives B[0..3]
                     }
+                    const long long br = b0 + (row & ~1);                                // the even lane's row; the odd lane's is br + 1
+                    uint32_t *o = a.out32 + ((size_t)br * words + w) * 256 + c0 + half * HQ + i8 * 8;
+                    const size_t rstride = (size_t)words * 256;
+                    // instruction 1: row br      <- even lane: its own words 0-3 at +0; odd lane: the even lane's words 4-7 at +4
+                    // instruction 2: row br + 1  <- even lane: the odd lane's words 0-3 at +0; odd lane: its own words 4-7 at +4
+                    if (br < a.B)
+                        *reinterpret_cast<uint4 *>(o + (odd ? 4 : 0)) = odd ? make_uint4(s0[0], s0[1], s0[2], s0[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if (br + 1 < a.B)
+                        *reinterpret_cast<uint4 *>(o + rstride + (odd ? 4 : 0)) = odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(s0[0], s0[1], s0[2], s0[3]);
+                    (void)s1;
                 }
             }
         }
         if (PHASE == 1) {
+            // the upper half's minima / maxima of the word join the lower half's through shared memory
+            __syncthreads();
+            if (!owner) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                rmax = fmaxf(rmax, hi[j] - lo[j]);
-                if (live) a.lo[(size_t)b * M + 4 * w + j] = lo[j];
+                for (int j = 0; j < 4; ++j) { sS[row * 8 + j] = lo[j]; sS[row * 8 + 4 + j] = hi[j]; }
+            }
+            __syncthreads();
+            if (owner) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float l = fminf(lo[j], sS[row * 8 + j]), h = fmaxf(hi[j], sS[row * 8 + 4 + j]);
+                    rmax = fmaxf(rmax, h - l);
+                    if (live) a.lo[(size_t)b * M + 4 * w + j] = l;
+                }
             }
         }
     }
-    if (PHASE == 1 && live) atomicMax(a.range_bits + b, __float_as_uint(rmax));   // a non-negative float orders like its bits
+    if (PHASE == 1 && live && owner) atomicMax(a.range_bits + b, __float_as_uint(rmax));   // a non-negative float orders like its bits
     tc_fence_before();
     __syncthreads();
     if (wid == 0) tmem_dealloc(tmem, TC_COLS);
@@ -244,7 +265,7 @@ int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B,
              "dr_lut_build(u8, tensor cores): needs M %% 4 == 0 and a sub-dimension that is a multiple of 8 (D=%d M=%d)", D, M);
     if (B == 0) return 0;
     const int ds = D / M, nks1 = ds / 8 + 1, words = M / 4;
-    const int smem = 4 * nks1 * (TC_ROWS * 32) + 4 * nks1 * (TC_NQ * 32) + 4 * 32 * 20 * 4;
+    const int smem = 4 * nks1 * (TC_ROWS * 32) + 4 * nks1 * (TC_NQ * 32) + TC_ROWS * 8 * 4;
     DR_CHECK(smem <= 200 * 1024, "dr_lut_build(u8, tensor cores): sub-dimension %d too large", ds);   // fewer CTAs per SM when large
     void (*k1)(const LutTcArgs) = lut_u8_tc_kernel<1, 0>;
     void (*k2)(const LutTcArgs) = lut_u8_tc_kernel<2, 0>;
@@ -269,9 +290,9 @@ int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B,
     DR_CHECK(tiles <= 2147483647LL, "dr_lut_build(u8, tensor cores): batch too large");
     dim3 grid((unsigned)tiles, (unsigned)groups);
     DR_CUDA(cudaMemsetAsync(d_range, 0, (size_t)B * 4, s));
-    k1<<<grid, TC_ROWS, smem, s>>>(a);
+    k1<<<grid, TC_THREADS, smem, s>>>(a);
     DR_LAUNCHED();
-    k2<<<grid, TC_ROWS, smem, s>>>(a);
+    k2<<<grid, TC_THREADS, smem, s>>>(a);
     DR_LAUNCHED();
     return 0;
 }
