@@ -51,6 +51,7 @@ SIGNATURES = {
     "dr_pq_lut": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, C.c_int]),
     "dr_pq_lut_u8": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int]),
     "dr_pq_train_tensor_cores": (C.c_int, [C.c_int]),
+    "dr_pq_train_kmeanspp": (C.c_int, [C.c_int]),
     "dr_pq_train": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _u64, _vp, _PP(_dbl), C.c_int]),
     "dr_pq_train_dev": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _u64, _vp, _PP(_dbl), C.c_int, _vp]),
     "dr_pq_encode": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, C.c_int]),

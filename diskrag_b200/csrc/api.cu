@@ -511,6 +511,11 @@ int dr_pq_lut_u8(const float *codebook, const float *Q, int64_t B, int32_t D, in
     return 0;
 }
 
+int dr_pq_train_kmeanspp(int enable) {
+    pq_train_set_kmeanspp(enable);
+    return 0;
+}
+
 int dr_pq_train_tensor_cores(int enable) {
     pq_train_set_tensor_cores(enable);
     return 0;

@@ -100,6 +100,7 @@ int launch_lut_build_u8(const float *d_codebook, const float *d_Q, int64_t B, in
                         float *d_offset, float *d_mn, unsigned *d_range, int word_layout, cudaStream_t s);  // pq.cu
 int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B, int D, int M, uint8_t *d_out8, float *d_scale,
                            float *d_offset, float *d_mn, unsigned *d_range, int sms, cudaStream_t s);   // lut_tc.cu (tcgen05)
+void pq_train_set_kmeanspp(int enable);        // pq.cu: k-means++ seeding (default) or evenly spaced rows
 void pq_train_set_tensor_cores(int enable);   // pq.cu: k-means assignment on tcgen05 (default) or exact fp32
 int launch_lut_u8_unpermute(const uint8_t *d_words, int64_t B, int M, uint8_t *d_plain, cudaStream_t s);  // pq.cu
 

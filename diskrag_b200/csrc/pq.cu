@@ -502,6 +502,63 @@ __global__ void init_codebook_kernel(float *__restrict__ codebook, const float *
     for (int j = threadIdx.x; j < ds; j += blockDim.x) codebook[(size_t)mc * ds + j] = X[(size_t)row * D + m * ds + j];
 }
 
+// ---- k-means++ seeding (sklearn's KMeans(init="k-means++") at fast_pq.py:232-240; Arthur & Vassilvitskii 2007) -------------
+// All M subspaces at once, one centroid per round: every (row, subspace) keeps its squared distance to the nearest centre chosen
+// so far; the next centre of a subspace is a row drawn with probability proportional to that distance, drawn as the argmax of
+// mind_i / E_i with E_i ~ Exp(1) (the exponential-race form of weighted sampling: one max-reduction, no prefix sums).
+__device__ __forceinline__ float kpp_exp1(unsigned long long seed, int round, int m, long long i) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)i * 257ull + (unsigned long long)m * 65537ull + (unsigned long long)round + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    const float u = ((float)(unsigned)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);     // (0, 1)
+    return -__logf(u);
+}
+// grid (ceil(n / 256), M): distances of every row to the centre chosen in the previous round, running minimum, race key
+__global__ void __launch_bounds__(256) kpp_round_kernel(const float *__restrict__ X, long long n, long long stride, int D, int M,
+                                                        const float *__restrict__ codebook, int round, float *__restrict__ mind,
+                                                        unsigned long long *__restrict__ best, unsigned long long seed) {
+    const int ds = D / M, m = blockIdx.y;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    unsigned long long key = 0ull;
+    if (i < n) {
+        const float *x = X + (size_t)(i * stride) * D + (size_t)m * ds;
+        const float *c = codebook + ((size_t)m * 256 + (round - 1)) * ds;         // the centre picked last
+        float d = 0.0f;
+        for (int j = 0; j < ds; ++j) { const float t = x[j] - __ldg(c + j); d = __fmaf_rn(t, t, d); }
+        float md = d;
+        if (round > 1) md = fminf(md, mind[(size_t)m * n + i]);
+        mind[(size_t)m * n + i] = md;
+        const float r = md / kpp_exp1(seed, round, m, i);
+        key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(unsigned)i;   // r >= 0: bits order like the value
+    }
+    // block max, one atomic per block
+    for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(DR_FULL, key, off); key = o > key ? o : key; }
+    __shared__ unsigned long long s_k[8];
+    if ((threadIdx.x & 31) == 0) s_k[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) key = s_k[w] > key ? s_k[w] : key;
+        atomicMax(best + m, key);
+    }
+}
+// M blocks: centre `round` of subspace m = the winning row (round 0: a uniformly drawn row); resets the race
+__global__ void kpp_pick_kernel(const float *__restrict__ X, long long n, long long stride, int D, int M, float *__restrict__ codebook,
+                                int round, unsigned long long *__restrict__ best, unsigned long long seed) {
+    const int ds = D / M, m = blockIdx.x;
+    long long row;
+    if (round == 0) {
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(m + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        row = (long long)(z % (unsigned long long)n);
+    } else {
+        row = (long long)(best[m] & 0xFFFFFFFFull);
+    }
+    for (int j = threadIdx.x; j < ds; j += blockDim.x) codebook[((size_t)m * 256 + round) * ds + j] = X[(size_t)(row * stride) * D + m * ds + j];
+    __syncthreads();
+    if (threadIdx.x == 0) best[m] = 0ull;
+}
+static std::atomic<int> g_kmeans_pp{1};
+void pq_train_set_kmeanspp(int enable) { g_kmeans_pp.store(enable ? 1 : 0); }
+
 static size_t assign_smem(int ds, bool accum) { return (size_t)256 * ds * 4 * (accum ? 2 : 1) + (accum ? 1024 : 0); }
 
 int launch_pq_encode(const float *d_codebook, const float *d_X, int64_t N, int D, int M, uint8_t *d_codes, cudaStream_t s) {
@@ -537,8 +594,29 @@ int launch_pq_train(const float *d_X, int64_t N, int D, int M, int iters, uint64
     DR_CUDA(cudaMalloc(&d_sums, (size_t)M * 256 * ds * 4));
     DR_CUDA(cudaMalloc(&d_counts, (size_t)M * 256 * 4));
     DR_CUDA(cudaMalloc(&d_sse, 8));
-    init_codebook_kernel<<<M * 256, 32, 0, s>>>(d_codebook, d_X, N, D, M, seed);
-    DR_LAUNCHED();
+    if (g_kmeans_pp.load()) {
+        // k-means++ over a subsample of at most 65536 training rows (every kstride-th training row)
+        long long kn = ntrain, kstride = stride;
+        if (kn > 65536) { const long long f = kn / 65536; kstride = stride * f; kn = ntrain / f; }
+        float *d_mind = nullptr; unsigned long long *d_best = nullptr;
+        DR_CUDA(cudaMalloc(&d_mind, (size_t)M * kn * 4));
+        DR_CUDA(cudaMalloc(&d_best, (size_t)M * 8));
+        DR_CUDA(cudaMemsetAsync(d_best, 0, (size_t)M * 8, s));
+        dim3 kgrid((unsigned)((kn + 255) / 256), M);
+        for (int round = 0; round < 256; ++round) {
+            if (round > 0) {
+                kpp_round_kernel<<<kgrid, 256, 0, s>>>(d_X, kn, kstride, D, M, d_codebook, round, d_mind, d_best, seed);
+                DR_LAUNCHED();
+            }
+            kpp_pick_kernel<<<M, 32, 0, s>>>(d_X, kn, kstride, D, M, d_codebook, round, d_best, seed);
+            DR_LAUNCHED();
+        }
+        DR_CUDA(cudaStreamSynchronize(s));
+        cudaFree(d_mind); cudaFree(d_best);
+    } else {
+        init_codebook_kernel<<<M * 256, 32, 0, s>>>(d_codebook, d_X, N, D, M, seed);
+        DR_LAUNCHED();
+    }
     size_t smem = assign_smem(ds, true);
     DR_CUDA(cudaFuncSetAttribute(assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((ntrain + 255) / 256), M);

@@ -187,6 +187,8 @@ int dr_pq_lut_u8(const float *codebook, const float *Q, int64_t B, int32_t D, in
 /* k-means assignment on the tensor cores (tcgen05, TF32) when D / M is a multiple of 8: on by default; 0 forces the exact
  * fp32 CUDA-core assignment (tests compare the two by quantisation error).  The final encode is always exact. */
 int dr_pq_train_tensor_cores(int enable);
+/* seeding of the codebooks: k-means++ on the device (default; sklearn's init at fast_pq.py:232-240) or, with 0, 256 evenly spaced rows */
+int dr_pq_train_kmeanspp(int enable);
 int dr_pq_train(const float *X, int64_t N, int32_t D, int32_t M, int32_t iters, uint64_t seed,
                 float *out_codebook, double *out_mse, int device);
 int dr_pq_train_dev(const float *d_X, int64_t N, int32_t D, int32_t M, int32_t iters, uint64_t seed,

@@ -104,7 +104,7 @@ def test_kmeans_quality_vs_sklearn(golden):
     mse_gpu = float(((pq.decode(codes) - g["vec"]) ** 2).mean())
     ref_dec = np.concatenate([g["codebook"][m][g["codes"][:, m]] for m in range(g["M"])], axis=1)
     mse_ref = float(((ref_dec - g["vec"]) ** 2).mean())
-    assert mse_gpu <= 1.10 * mse_ref, (mse_gpu, mse_ref)      # within 10 % of sklearn (n_init=10, k-means++)
+    assert mse_gpu <= 1.05 * mse_ref, (mse_gpu, mse_ref)      # sklearn: k-means++, n_init=10; here k-means++ on the device, one run (the configs[0] A/B in test_golden_config0.py gates at 1.03)
     assert abs(pq.train_mse_ - mse_gpu) <= 0.05 * mse_gpu
     assert 0.5 < pq.estimate_selectivity(g["vec"]) <= 1.0
 
