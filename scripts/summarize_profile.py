@@ -23,6 +23,7 @@ rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
 info = {"profile": f"profiles/{tag}_search_kernel_ncu.txt", "kernel": d["Kernel Name"][0] if "Kernel Name" in d else kname,
         "queries_in_profiled_launch": nq, "dram_bytes_read": rd, "dram_bytes_write": wr,
         "dram_bytes_per_query": (rd + wr) / nq, "duration_ms": float(d["gpu__time_duration.sum"][0]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[d["gpu__time_duration.sum"][1]],
+        "source": f"ncu --set full capture profiles/{tag}_search_kernel_ncu.txt (commit " + subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=root).stdout.strip() + "), scaled per query",
         "note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture; bench.py scales it to its own launch size"}
 (out / "search_kernel_traffic.json").write_text(json.dumps(info, indent=1))
 print(json.dumps(info, indent=1))
