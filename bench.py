@@ -75,30 +75,61 @@ def parse():
     return a
 
 
+def _gpu_numa_node(local):
+    """NUMA node of GPU `local` from sysfs, via its PCI bus id (NVML, else nvidia-smi); None when the box does not say."""
+    bus = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+    except Exception:
+        try:
+            bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+        except Exception:
+            bus = None
+    if not bus:
+        return None
+    bus = bus.lower()
+    if len(bus.split(":")[0]) == 8:                      # NVML prints an 8-digit domain, sysfs a 4-digit one
+        bus = bus[4:]
+    p = Path(f"/sys/bus/pci/devices/{bus}/numa_node")
+    try:
+        node = int(p.read_text())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
 def pin_rank_to_local_cpus(local, world):
     """Each rank on its own cores, on the NUMA node of its GPU when sysfs says which: the pinned host buffers of the end-to-end leg
-    are then allocated node-local and 8 ranks do not fight over one node's memory controllers.  Best effort, silent."""
+    are then allocated node-local (first touch) and 8 ranks do not pull 8 x 614 MB per step through one socket's memory controllers
+    and the inter-socket link.  Best effort, silent."""
     try:
-        import torch
         cpus = sorted(os.sched_getaffinity(0))
+        node = _gpu_numa_node(local)
         node_cpus = None
-        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
-        if bus is not None:
-            dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
-            p = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node")
-            if p.exists() and int(p.read_text()) >= 0:
-                lst = Path(f"/sys/devices/system/node/node{int(p.read_text())}/cpulist").read_text().strip()
-                node_cpus = []
-                for part in lst.split(","):
-                    lo, _, hi = part.partition("-")
-                    node_cpus += list(range(int(lo), int(hi or lo) + 1))
-                node_cpus = [c for c in node_cpus if c in cpus]
-        pool = node_cpus if node_cpus else cpus
-        per = max(1, len(pool) // max(1, min(world, len(pool))))
-        mine = pool[(local * per) % len(pool):(local * per) % len(pool) + per] or pool
+        if node is not None:
+            lst = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+            node_cpus = []
+            for part in lst.split(","):
+                lo, _, hi = part.partition("-")
+                node_cpus += list(range(int(lo), int(hi or lo) + 1))
+            node_cpus = [c for c in node_cpus if c in cpus] or None
+        if node_cpus:
+            # the ranks that share this node split its cores among themselves (GPUs are numbered node by node on HGX boards)
+            peers = [r for r in range(world) if _gpu_numa_node(r) == node] or [local]
+            per = max(1, len(node_cpus) // len(peers))
+            k = peers.index(local) if local in peers else 0
+            mine = node_cpus[k * per:(k + 1) * per] or node_cpus
+        else:
+            per = max(1, len(cpus) // max(1, min(world, len(cpus))))
+            mine = cpus[(local * per) % len(cpus):(local * per) % len(cpus) + per] or cpus
         os.sched_setaffinity(0, mine)
-        return {"cpus": len(mine), "numa_local": bool(node_cpus)}
+        return {"cpus": len(mine), "numa_node": node, "numa_local": bool(node_cpus)}
     except Exception:
         return None
 
