@@ -309,6 +309,9 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #ifndef DR_W2_SPEC
 #define DR_W2_SPEC 16
 #endif
+#ifndef DR_SELCAP
+#define DR_SELCAP 64    // ranks recorded at merge time (>= W + 3 * W2 covers four steps in a row without a survivor)
+#endif
 #ifndef DR_L2V
 #define DR_L2V 0   // experiment (scripts/build_variants.py): 1 = the serving-shape specialisations keep the visited set in the
 #endif             // CTA's L2-resident table (no shared-memory hash) so that four CTAs fit on an SM; pair with DR_FAST_NT=192
@@ -359,6 +362,10 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
     const bool adj_async = (pf & 16) != 0;   // the launcher clears the bit unless R % 4 == 0 and W <= 16
     const bool spec_code = (pf & 8) != 0;
     uint32_t adj_par = 0u;                   // bit s: parity of s_adjbar[s] this warp waits for next
+    // Selection record: the merge writes the list positions of the first DR_SELCAP unexpanded entries, by rank.  The next steps take
+    // their entries from it by rank offset, so a step that follows a step WITHOUT survivors (list unchanged) needs neither a rescan of
+    // the list nor a block barrier: every thread derives the step's size from ur[n] and its own count of expansions.
+    const bool selrec = (pf & (8 | 16)) == 0;
     const uint8_t *deleted = RW8 == 4 ? nullptr : a.deleted;
     const bool do_rerank = RW8 == 4 ? true : (a.rerank != 0);
     const int R = RW8 ? 32 : a.R, W = RW8 ? 8 : a.W;
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 if (no_smem_hash) my_ovf[fib_slot(a.start ^ 0x9e3779b9u, ovf_shift)] = a.start;
                 else s_hash[fib_slot(a.start, hshift)] = a.start;
                 s_ur0[0] = 0; s_ur0[1] = 1;      // one unexpanded entry
-                s_sel[W] = 0u; s_ns = 1;         // the first step expands list position 0
+                s_sel[selrec ? 0 : W] = 0u; s_ns = 1;         // the first step expands list position 0
                 s_nspec = 0;
                 s_pfkey = DR_KEY_MAX;
                 if (adj_async) {
@@ -458,6 +465,8 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
         }
         int cur = 0, n = 1, hops = 0, nvis = 1, step = 0;
         int ubase = 0;    // entries marked expanded since the ur[] array of the current list was written
+        int sel_base = 0; // selrec: ubase at the time s_sel[0] was (re)written
+        int ns_reg = 1;   // entries the coming step expands
         __syncthreads();
         DR_PT(1);   // table / query staging, start node
 
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             uint16_t *ur_old = cur ? s_ur1 : s_ur0;
             uint16_t *ur_new = cur ? s_ur0 : s_ur1;
             int *p_nn = &s_nn2[step & 1];
-            const int ns = s_ns;
+            const int ns = ns_reg;
             if (ns == 0) break;
             const bool use_ovf_now = (s_hcount + W2 * R > hlimit);   // same value for every thread (read after the last barrier)
             if (use_ovf_now && (s_ovfcount + W2 * R > ovf_limit)) {
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             uint32_t nb2 = DR_EMPTY;
             if (wid < nspec && lane < R) nb2 = __ldg(a.adj + (size_t)key_id(lst[s_sel[wid]]) * R + lane);
             for (int s = wid; s < ns; s += nw) {
-                const int pos = (int)s_sel[W + s];
+                const int pos = (int)s_sel[selrec ? (ubase - sel_base + s) : (W + s)];
                 DR_PT(6);   // (timing build) selection read
                 const uint32_t node = key_id(lst[pos]);
                 __syncwarp();
@@ -667,7 +676,9 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 oth[pos] = key;
                 ur_new[pos] = (uint16_t)rank;
                 if (un) {
-                    if (rank < W) {
+                    if (selrec) {
+                        if (rank < DR_SELCAP) s_sel[rank] = (uint32_t)pos;
+                    } else if (rank < W) {
                         s_sel[W + rank] = (uint32_t)pos;
                         if (adj_async) {                 // its adjacency row travels to shared memory under the rest of the merge
                             mbar_expect_tx(&s_adjbar[rank], (uint32_t)R * 4u);
@@ -750,14 +761,25 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 cur ^= 1;
                 n = nnew;
                 ubase = 0;
+                sel_base = 0;
                 __syncthreads();   // the next step reads the merged list and its selection
+                ns_reg = s_ns;
                 DR_PT(4);   // merge
             } else {
                 // nothing survived: the list stays, the selection moves on by the ns entries just expanded
+                int tot_left = (int)ur_old[n] - ubase;
+                tot_left = tot_left > 0 ? tot_left : 0;
+                const int ns_next = tot_left < W2 ? tot_left : W2;
+                if (selrec && ubase - sel_base + ns_next <= DR_SELCAP) {
+                    ns_reg = ns_next;          // the recorded ranks cover the step: no rescan, no barrier
+                    continue;
+                }
                 for (int x = tid; x < n; x += nt) {
                     const int r = (int)ur_old[x] - ubase;
                     if (!(lst[x] & 1ull)) {
-                        if (r < W2) {
+                        if (selrec) {
+                            if (r < DR_SELCAP) s_sel[r] = (uint32_t)x;
+                        } else if (r < W2) {
                             s_sel[W + r] = (uint32_t)x;
                             if (adj_async) {
                                 mbar_expect_tx(&s_adjbar[r], (uint32_t)R * 4u);
@@ -779,7 +801,9 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                     s_nspec = (W2 != W || tot < W) ? 0 : (tot < 2 * W ? tot - W : W);
                     if (spec && tot < 2 * W) s_pfkey = DR_KEY_MAX;
                 }
+                sel_base = ubase;
                 __syncthreads();
+                ns_reg = s_ns;
                 DR_PT(4);
             }
         }
@@ -881,15 +905,30 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             }
             __syncthreads();
             DR_PT(5);   // rerank distance pass
-            for (int i = tid; i < n; i += nt) {
-                u64 key = s_rrk[i];
+            // rank of every reranked entry among the n (keys are unique: (distance bits, list position)); with n <= 128 and 256
+            // threads two threads share an entry, each counting over half of the keys, so that all eight warps work on the pass
+            const bool split = (nt == 256) && n <= 128;
+            uint32_t *s_part = s_newid;                      // dead after the traversal: the upper halves' partial ranks
+            for (int i0 = 0; i0 < n; i0 += (split ? 128 : nt)) {
+                const int i = i0 + (split ? (tid & 127) : tid);
+                const int hi = split ? (tid >> 7) : 0;
+                const int j0 = (split && hi) ? (n >> 1) : 0, j1 = (split && !hi) ? (n >> 1) : n;
+                u64 key = 0ull;
                 int pos = 0;
-                for (int j = 0; j < n; ++j) pos += (s_rrk[j] < key) ? 1 : 0;
-                if (pos < k) {
-                    float d2 = ord2f((uint32_t)(key >> 32));
-                    a.out_ids[(size_t)b * k + pos] = (int32_t)key_id(lst[i]);
-                    if (a.out_dist) a.out_dist[(size_t)b * k + pos] = a.sqrt_out ? sqrtf(d2) : d2;
-                    if (peer_dst) peer_dst[pos] = (key & 0xFFFFFFFF00000000ull) | (u64)(uint32_t)(key_id(lst[i]) + a.peer_id_offset);
+                if (i < n) {
+                    key = s_rrk[i];
+                    for (int j = j0; j < j1; ++j) pos += (s_rrk[j] < key) ? 1 : 0;
+                    if (split && hi) s_part[i] = (uint32_t)pos;
+                }
+                if (split) __syncthreads();
+                if (i < n && !hi) {
+                    if (split) pos += (int)s_part[i];
+                    if (pos < k) {
+                        float d2 = ord2f((uint32_t)(key >> 32));
+                        a.out_ids[(size_t)b * k + pos] = (int32_t)key_id(lst[i]);
+                        if (a.out_dist) a.out_dist[(size_t)b * k + pos] = a.sqrt_out ? sqrtf(d2) : d2;
+                        if (peer_dst) peer_dst[pos] = (key & 0xFFFFFFFF00000000ull) | (u64)(uint32_t)(key_id(lst[i]) + a.peer_id_offset);
+                    }
                 }
             }
         } else {
@@ -996,7 +1035,7 @@ int launch_search_fast(dr_index *h, const float *d_Q, int64_t B, const dr_search
     const int NC = (a.W2 * h->R + 1) & ~1;
     a.o_newk = off; off += NC * 8;
     a.o_newid = off; off += NC * 4;
-    a.o_sel = off; off += (((p->W + a.W2) * 4 + 7) / 8) * 8;
+    a.o_sel = off; off += ((((p->W + a.W2) > DR_SELCAP ? (p->W + a.W2) : DR_SELCAP) * 4 + 7) / 8) * 8;
     off = (off + 15) / 16 * 16;
     a.o_adjrow = off;
     if (a.prefetch & 16) off += (p->W * h->R * 4 + 15) / 16 * 16;
