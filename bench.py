@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--M", type=int, default=192)
     ap.add_argument("--L", type=int, default=100)
     ap.add_argument("--W", type=int, default=8)
-    ap.add_argument("--W2", type=int, default=16, help="expansions of a step that follows a step without survivors (0 = off; results restated by the oracle)")
+    ap.add_argument("--W2", type=int, default=20, help="expansions of a step that follows a step without survivors (0 = off; results restated by the oracle)")
     ap.add_argument("--adc", default="tree", choices=["seq", "tree"])
     ap.add_argument("--lut", default="u8tc", choices=["f32", "u8", "u8tc"], help="ADC table: f32 reference arithmetic, u8 exact 8-bit, u8tc 8-bit built on tensor cores")
     ap.add_argument("--prefetch", type=int, default=5, help="L2 prefetch bit mask of the throughput kernel (include/diskrag_b200.h); results are unchanged")

@@ -307,7 +307,7 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #endif
 // "empty-step doubling" of the serving-shape specialisations (RW8 >= 1 fixes W = 8): dr_search_params.w_after_empty they are compiled for
 #ifndef DR_W2_SPEC
-#define DR_W2_SPEC 16
+#define DR_W2_SPEC 20
 #endif
 #ifndef DR_SELCAP
 #define DR_SELCAP 64    // ranks recorded at merge time (>= W + 3 * W2 covers four steps in a row without a survivor)

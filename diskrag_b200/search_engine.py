@@ -55,10 +55,10 @@ class GpuSearchEngine:
         L = max(int(L), int(k))
         if pq:
             if self.throughput:
-                # the bench configuration: 8 expansions per step, 8-bit table (built on the tensor cores when the
+                # the bench configuration: 8 expansions per step (20 after a step without survivors), 8-bit table (built on the tensor cores when the
                 # sub-dimension allows), L2 prefetches; at R = 32, D = 1536, L = 100 this is the specialised kernel
                 tc = self.index.M % 4 == 0 and self.index.M <= 256 and (self.dimension // self.index.M) % 8 == 0
-                return self.index.search(Q, k=k, L=L, W=8, dist="pq", rerank=True, lut_fmt="u8tc" if tc else "u8", prefetch=5)
+                return self.index.search(Q, k=k, L=L, W=8, dist="pq", rerank=True, lut_fmt="u8tc" if tc else "u8", prefetch=5, w2=20)
             return self.index.search(Q, k=k, L=L, W=1, dist="pq", adc_order="seq", rerank=True)
         return self.index.search(Q, k=k, L=L, W=1, dist="exact", rerank=False)
 

@@ -196,7 +196,7 @@ def test_u8_prefetch_bits_never_change_results(case, W, L):
         assert np.array_equal(r.hops, ref.hops) and np.array_equal(r.visited, ref.visited), (pf, hc)
 
 
-@pytest.mark.parametrize("W,W2,L", [(8, 16, 100), (4, 8, 48), (2, 32, 64), (8, 16, 20), (1, 4, 32)])
+@pytest.mark.parametrize("W,W2,L", [(8, 16, 100), (8, 20, 100), (4, 8, 48), (2, 32, 64), (8, 16, 20), (1, 4, 32)])
 def test_u8_empty_step_doubling_vs_oracle(case, orc, W, W2, L):
     """w_after_empty: a step that follows a step without survivors expands up to W2 entries.  Bit-for-bit against the oracle's
     restatement of the rule (lists, hops, visited, reranked results), also through the overflow path of a tiny visited table."""
@@ -257,16 +257,16 @@ def test_export_records_roundtrip(golden, gidx):
 
 
 def test_bench_shape_specialisation_vs_oracle(orc):
-    """The compile-time-specialised instantiation the bench runs (D = 1536, M = 192, R = 32, W = 8 doubling to 16 after an empty step,
+    """The compile-time-specialised instantiation the bench runs (D = 1536, M = 192, R = 32, W = 8, 20 after an empty step,
     L = 100, 4096-slot visited table, prefetch mask 5, rerank): bit-for-bit against the restatement with the exact 8-bit table, and the same ids with
     the tensor-core table on all but near-tie queries."""
     from diskrag_b200.engine import GpuIndex
     c = make_case(orc, 2500, 1536, 192, 32, 48, 31, nq=16)
     L, W = 100, 8
     with GpuIndex.from_arrays(c["X"], c["adj"], c["codes"], c["codebook"], c["medoid"]) as idx:
-        r = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=False, lut_fmt="u8", prefetch=5, w2=16)
-        rl = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5, w2=16)   # generic flags path
-        rt = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8tc", prefetch=5, w2=16)
+        r = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=False, lut_fmt="u8", prefetch=5, w2=20)
+        rl = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, want_list=True, lut_fmt="u8", prefetch=5, w2=20)   # generic flags path
+        rt = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8tc", prefetch=5, w2=20)
         rp = [idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8", prefetch=pf) for pf in (13, 21, 29)]
         r0 = idx.search(c["Q"], k=10, L=L, W=W, dist="pq", rerank=True, lut_fmt="u8", prefetch=5)
     assert np.array_equal(r.ids, rl.ids) and np.array_equal(r.dists, rl.dists) and np.array_equal(r.hops, rl.hops)
@@ -279,7 +279,7 @@ def test_bench_shape_specialisation_vs_oracle(orc):
         oi0, od0 = orc.rerank(c["X"], c["Q"][qi], l0["ids"], 10, flavor=orc.FLAVOR_WARP)
         assert np.array_equal(oi0, r0.ids[qi, :len(oi0)]) and np.array_equal(od0, r0.dists[qi, :len(od0)])
         l = orc.search_list(c["adj"], c["medoid"], L, codes=c["codes"], lut_=t8, dist_mode=orc.DIST_ADC_U8, W=W, strict_ties=False,
-                            w_after_empty=16)
+                            w_after_empty=20)
         assert (r.hops[qi], r.visited[qi]) == (l["hops"], l["visited"])
         assert np.array_equal(l["ids"], rl.list_ids[qi, :rl.list_len[qi]])
         oi, od = orc.rerank(c["X"], c["Q"][qi], l["ids"], 10, flavor=orc.FLAVOR_WARP)

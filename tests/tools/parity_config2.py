@@ -8,7 +8,7 @@ Run on the GPU box; prints one JSON summary (kept in profiles/).
              reference-like (double-accumulated, BLAS stand-in) order: ids on all but near-tie queries, distances <= 1e-4 rel
   variant A  greedy_search_cython + ADC callback (cython_utils.pyx:72-122): sequential-order ADC over the f32 table
              ids, ADC distances (bit-equal), hops, visited
-  throughput u8 table, W = 8, fused rerank: ids / distances bit-equal to the list-form restatement
+  throughput u8 table, W = 8 (20 after a step without survivors), fused rerank: ids / distances bit-equal to the list-form restatement
 """
 import json
 import sys
@@ -105,10 +105,10 @@ def run(nq_exact=10_000, nq_oracle=2_000):
         out["variant_A_pq"] = {"gpu_batch_seconds": round(tA, 3), "ids_adc_distances_hops_visited_bit_equal": f"{okA}/{nq_oracle}"}
         # ---- throughput mode ---------------------------------------------------------------------------------
         t = time.time()
-        rT = idx.search(Q, k=k, L=L, W=8, dist="pq", rerank=True, lut_fmt="u8", prefetch=5)
+        rT = idx.search(Q, k=k, L=L, W=8, dist="pq", rerank=True, lut_fmt="u8", prefetch=5, w2=20)
         tT = time.time() - t
         oi, od, oh, ov = O.search_batch(adj, X, Q[:nq_oracle], med, L, k, codes=codes, codebook=cb, dist_mode=O.DIST_ADC_U8,
-                                        flavor=O.FLAVOR_WARP, W=8, rerank_=True)
+                                        flavor=O.FLAVOR_WARP, W=8, rerank_=True, w_after_empty=20)
         out["throughput_u8_W8_rerank"] = {
             "gpu_batch_seconds": round(tT, 3),
             "top_k_ids_and_distances_bit_equal": f"{int(np.sum(np.all(oi == rT.ids[:nq_oracle], axis=1) & np.all(od == rT.dists[:nq_oracle], axis=1)))}/{nq_oracle}",
@@ -118,7 +118,7 @@ def run(nq_exact=10_000, nq_oracle=2_000):
         # search_engine.py:374-379.  The GPU's variant A is bit-equal to the oracle's (checked above), so the whole batch is
         # compared on the device results; the oracle re-runs the composition on the first nq_oracle queries.
         rAr = idx.search(Q, k=k, L=L, W=1, dist="pq", adc_order="seq", rerank=True)
-        rB = idx.search(Q, k=k, L=L, W=8, dist="pq", adc_order="tree", rerank=True, lut_fmt="u8tc", prefetch=5)
+        rB = idx.search(Q, k=k, L=L, W=8, dist="pq", adc_order="tree", rerank=True, lut_fmt="u8tc", prefetch=5, w2=20)   # bench.py's mode
         set_eq = lambda a, b: np.array([set(a[i].tolist()) == set(b[i].tolist()) for i in range(a.shape[0])])
         eqB = set_eq(rB.ids, rAr.ids); eqT = set_eq(rT.ids, rAr.ids)
         okR = 0

@@ -43,7 +43,7 @@ elif what in ("refsearch", "lut", "kmeans"):
     if what == "refsearch":                                       # the reference-order kernel: f32 table, sequential ADC, W = 1, rerank
         p = engine.make_params(k=10, L=100, W=1, dist="pq", adc_order="seq", rerank=True, lut="f32")
     else:                                                         # the two tcgen05 table kernels + the throughput search
-        p = engine.make_params(k=10, L=100, W=8, dist="pq", adc_order="tree", rerank=True, lut="u8tc", prefetch=5, w2=16)
+        p = engine.make_params(k=10, L=100, W=8, dist="pq", adc_order="tree", rerank=True, lut="u8tc", prefetch=5, w2=20)
     torch.cuda.profiler.start()
     idx.search_dev(Q.data_ptr(), B, p, ids.data_ptr(), dd.data_ptr(), hops.data_ptr(), vis.data_ptr(), d_list_len=ll.data_ptr(), stream=st)
     torch.cuda.synchronize()
