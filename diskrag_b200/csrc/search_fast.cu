@@ -309,6 +309,9 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #ifndef DR_W2_SPEC
 #define DR_W2_SPEC 20
 #endif
+#ifndef DR_MERGE_PAIRS
+#define DR_MERGE_PAIRS 1   // linear merge: two lanes per item (all eight warps busy, half the scan per item)
+#endif
 #ifndef DR_SELCAP
 #define DR_SELCAP 64    // ranks recorded at merge time (>= W + 3 * W2 covers four steps in a row without a survivor)
 #endif
@@ -702,6 +705,24 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
             };
             if (mv > 0) {
                 if (mv <= DR_MERGE_LINEAR || mv > 64 * nw) {
+#if DR_MERGE_PAIRS
+                    // two adjacent lanes share an item: each counts the smaller newcomers over half of them, so that a step with
+                    // ~100 + mv items keeps all eight warps busy and the scan every item waits for is half as long
+                    const int hsel = tid & 1, mh = mv >> 1;
+                    const int j0 = hsel ? mh : 0, j1 = hsel ? mv : mh;
+                    for (int x0 = 0; x0 < total; x0 += nt / 2) {
+                        const int x = x0 + (tid >> 1);
+                        u64 key = 0ull;
+                        int from = 0, cnt = 0;
+                        if (x < total) {
+                            if (x < n) { key = lst[x]; from = x; }
+                            else { key = s_newk[x - n]; from = lower_bound_u64<(RW8 >= 3 ? 64 : 512)>(lst, n, key); }
+                            for (int j = j0; j < j1; ++j) cnt += (s_newk[j] < key) ? 1 : 0;
+                        }
+                        cnt += __shfl_xor_sync(DR_FULL, cnt, 1);
+                        if (x < total && hsel == 0) place(key, from + cnt, from, x >= n);
+                    }
+#else
                     for (int x = tid; x < total; x += nt) {
                         u64 key;
                         int pos, from;
@@ -711,6 +732,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                         for (int j = 0; j < mv; ++j) pos += (s_newk[j] < key) ? 1 : 0;
                         place(key, pos, from, x >= n);
                     }
+#endif
                 } else {
                     // every warp bitonic-sorts one 64-key chunk in registers (two keys per lane: element e = lane + 32 r),
                     // then every item sums its binary-search ranks in the other sorted sequences
