@@ -310,7 +310,8 @@ __device__ __forceinline__ int lower_bound_u64(const u64 *a, int n, u64 key) {
 #define DR_W2_SPEC 20
 #endif
 #ifndef DR_MERGE_PAIRS
-#define DR_MERGE_PAIRS 1   // linear merge: two lanes per item (all eight warps busy, half the scan per item)
+#define DR_MERGE_PAIRS 0   // experiment: linear merge with two lanes per item (all eight warps busy, half the scan per item): -0.3 % (more
+                           // instructions issued for a shorter critical path: the kernel is issue-bound, not latency-bound, there)
 #endif
 #ifndef DR_SELCAP
 #define DR_SELCAP 64    // ranks recorded at merge time (>= W + 3 * W2 covers four steps in a row without a survivor)
