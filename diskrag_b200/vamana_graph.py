@@ -477,6 +477,15 @@ def _as_graph(graph) -> VamanaGraphWithPQ:
     if isinstance(graph, VamanaGraphWithPQ):
         return graph
     g = getattr(graph, "_b200_mirror", None)
+    if g is not None:
+        # a foreign graph can be mutated behind the mirror's back (insert_node, delete_node, direct edits of node.neighbors): a cheap
+        # fingerprint of what the searches depend on decides whether the mirror still stands
+        n = len(graph.nodes)
+        fp = (n, sum(len(graph.nodes[i].neighbors) for i in range(n)), sum(1 for i in range(n) if getattr(graph.nodes[i], "is_deleted", False)),
+              getattr(graph, "medoid_idx", 0))
+        if fp != getattr(g, "_foreign_fp", None):
+            g.close()
+            g = None
     if g is None:
         n = len(graph.nodes)
         R = max(int(getattr(graph, "R", 0)), max((len(graph.nodes[i].neighbors) for i in range(n)), default=0), 1)
@@ -491,6 +500,8 @@ def _as_graph(graph) -> VamanaGraphWithPQ:
         g = VamanaGraphWithPQ.from_arrays(vec, adj, deg, codes, getattr(graph, "pq_model", None),
                                           getattr(graph, "medoid_idx", 0) or 0, R, getattr(graph, "distance_metric", "l2"))
         g._deleted = np.array([bool(getattr(graph.nodes[i], "is_deleted", False)) for i in range(n)])
+        g._adopt()
+        g._foreign_fp = (n, int(deg.sum()), int(g._deleted.sum()), getattr(graph, "medoid_idx", 0))
         try:
             graph._b200_mirror = g
         except Exception:

@@ -153,3 +153,37 @@ def test_packed_exchange_kernels_equal_their_numpy_statement():
         oi, od = D._merge_keys_gpu(torch.from_numpy(keys).cuda())
         ei, ed = D.merge_keys_numpy(keys)
         assert np.array_equal(oi.cpu().numpy(), ei) and np.array_equal(od.cpu().numpy(), ed)
+
+
+def test_peer_routed_epilogue_on_one_device(orc):
+    """The index-sharded exchange fused into the search kernel (dr_index_set_peer_route), exercised on ONE device: G receive buffers
+    (one per would-be rank) all live here; the same index plays every rank in turn (its own id offset), the kernel's epilogue stores
+    each query's packed top-k into the buffer of the rank that reduces the query; merging every buffer must give what the explicit
+    pack -> exchange -> merge path gives (numpy statements of both kernels) — ragged slices, chunked launches, fewer than k hits."""
+    import ctypes as C
+    import torch
+    from conftest import make_case
+    from diskrag_b200 import dist as D
+    from diskrag_b200._lib import check, lib
+    from diskrag_b200.engine import GpuIndex
+    c = make_case(orc, 1500, 64, 16, 16, 32, 13, nq=37)
+    B, k, G = 37, 10, 3
+    bq = D.padded_slice_len(B, G)
+    with GpuIndex.from_arrays(c["X"], c["adj"], c["codes"], c["codebook"], c["medoid"]) as idx:
+        plain = idx.search(c["Q"], k=k, L=24, W=4, dist="pq", rerank=True, lut_fmt="u8")
+        bufs = [torch.full((G, bq, k), -1, dtype=torch.int64, device="cuda") for _ in range(G)]
+        table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+        for r in range(G):                                   # "rank" r: same shard content, ids offset by r * N
+            check(lib().dr_index_set_peer_route(idx._h, C.c_void_p(table.data_ptr()), G, r, B, r * c["N"]), "dr_index_set_peer_route")
+            routed = idx.search(c["Q"], k=k, L=24, W=4, dist="pq", rerank=True, lut_fmt="u8", chunk=(0 if r == 0 else 11))
+            assert np.array_equal(routed.ids, plain.ids) and np.array_equal(routed.dists, plain.dists)      # local output unchanged
+        check(lib().dr_index_set_peer_route(idx._h, None, 0, 0, 0, 0), "dr_index_set_peer_route")
+        torch.cuda.synchronize()
+    for g in range(G):
+        lo, hi = D.query_slice(B, g, G)
+        got_i, got_d = D.merge_keys_numpy(bufs[g].cpu().numpy())
+        # the explicit path: every rank packs its lists, block g of every send buffer goes to rank g
+        send = [D.pack_topk_numpy(plain.ids, plain.dists, r * c["N"], G) for r in range(G)]
+        exp_i, exp_d = D.merge_keys_numpy(np.stack([send[r][g] for r in range(G)]))
+        assert np.array_equal(got_i[:hi - lo], exp_i[:hi - lo]) and np.array_equal(got_d[:hi - lo], exp_d[:hi - lo]), g
+        assert (got_i[hi - lo:] == -1).all()                 # rows past the slice stay empty
