@@ -7,7 +7,7 @@
 //   1. greedy search of every batch point from the medoid on the current graph snapshot, exact fp32
 //      distances (search.cu in DR_DIST_EXACT mode, queries addressed through a row map);
 //   2. RobustPrune(alpha, R) of  search list ∪ N(p)  -> new out-row of p         (prune_kernel, mode 0);
-//   3. reverse edges: pairs (j, p) for j in N(p) are sorted by target; each target appends the
+//   3. reverse edges: pairs (j, p) for j in N(p) are sorted by (target, source) with our own bitonic sort; each target appends the
 //      incoming ids while its row has room, otherwise RobustPrune(N(j) ∪ incoming)  (prune_kernel, mode 1).
 // The prune rule is the reference's: candidates sorted by (d, id); after selecting p*, a candidate p'
 // is dropped when alpha * d2(p*, p') <= d2(p, p')  (alpha on SQUARED distances, cython_utils.pyx:483).
@@ -15,7 +15,6 @@
 // stale-tail re-selection of :460-466 is not reproduced; graphs are compared by recall.
 #include "common.cuh"
 
-#include <cub/cub.cuh>
 
 #include <algorithm>
 #include <random>
@@ -31,7 +30,7 @@ struct PruneArgs {
     // mode 0
     const int32_t *nodes; const int32_t *list_ids; const float *list_dist; const int32_t *list_len; int L;
     // mode 1
-    const uint32_t *rkeys; const uint32_t *rvals; const int32_t *heads; const int32_t *n_heads; int n_pairs;
+    const u64 *pairs; const int32_t *heads; const int32_t *n_heads; int n_pairs;   // sorted target << 32 | source keys
     int n_items;
     int *truncated;   // mode 1: targets whose incoming run did not fit PR_CMAX candidates (the rest of the run is dropped); may be NULL
 };
@@ -74,7 +73,7 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
             if (tid == 0) s_n = min(ll + dg, PR_CMAX);
         } else {
             const int h0 = a.heads[item];
-            node = a.rkeys[h0];
+            node = (uint32_t)(a.pairs[h0] >> 32);
             const int dg = a.deg[node];
             n_old = dg;
             for (int i = tid; i < dg; i += nt) { s_id[i] = a.adj[(size_t)node * RS + i]; s_flag[i] = 0; }
@@ -82,8 +81,8 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
             if (tid == 0) {
                 int m = dg;
                 int i = h0;
-                for (; i < a.n_pairs && a.rkeys[i] == node && m < PR_CMAX; ++i) { s_id[m] = a.rvals[i]; s_flag[m] = 0; ++m; }
-                if (a.truncated && i < a.n_pairs && a.rkeys[i] == node) atomicAdd(a.truncated, 1);   // reverse edges beyond the capacity
+                for (; i < a.n_pairs && (uint32_t)(a.pairs[i] >> 32) == node && m < PR_CMAX; ++i) { s_id[m] = (uint32_t)a.pairs[i]; s_flag[m] = 0; ++m; }
+                if (a.truncated && i < a.n_pairs && (uint32_t)(a.pairs[i] >> 32) == node) atomicAdd(a.truncated, 1);   // reverse edges beyond the capacity
                 s_n = m;
             }
         }
@@ -161,24 +160,74 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
     }
 }
 
-// (target, source) pairs of the batch's new out-rows; unused slots get the sentinel key
+// (target, source) pairs of the batch's new out-rows as 64-bit keys target << 32 | source; unused slots and the padding up to the
+// sort's power-of-two length get the all-ones sentinel (sorts last)
 __global__ void emit_pairs_kernel(const int32_t *__restrict__ nodes, int n_items, const uint32_t *__restrict__ adj,
-                                  const int32_t *__restrict__ deg, int R, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                                  const int32_t *__restrict__ deg, int R, u64 *__restrict__ pairs, int n_padded) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_items * R) return;
-    int item = t / R, j = t - item * R;
-    uint32_t node = (uint32_t)nodes[item];
-    bool ok = j < deg[node];
-    keys[t] = ok ? adj[(size_t)node * R + j] : DR_EMPTY;
-    vals[t] = node;
+    if (t >= n_padded) return;
+    u64 key = DR_KEY_MAX;
+    if (t < n_items * R) {
+        int item = t / R, j = t - item * R;
+        uint32_t node = (uint32_t)nodes[item];
+        if (j < deg[node]) key = ((u64)adj[(size_t)node * R + j] << 32) | (u64)node;
+    }
+    pairs[t] = key;
 }
 
-__global__ void heads_kernel(const uint32_t *__restrict__ keys, int n, int32_t *__restrict__ heads, int32_t *__restrict__ n_heads) {
+// Bitonic sort of the pair keys, our own two kernels (the reverse edges of a batch are grouped by target; sorting the unique 64-bit
+// keys also fixes the order inside a group, so the build is deterministic): compare-exchange distances >= BS_TILE go through global
+// memory one launch each, everything below runs inside shared memory in one launch per merge size.
+#define BS_TILE 2048
+__global__ void __launch_bounds__(BS_TILE / 2) bitonic_smem_kernel(u64 *__restrict__ a, int k_first, int k_last) {
+    // sorts / merges inside one tile: for k = k_first .. k_last (doubling), j = min(k, BS_TILE) / 2 .. 1
+    __shared__ u64 s[BS_TILE];
+    const int base = blockIdx.x * BS_TILE, t = threadIdx.x;
+    s[t] = a[base + t]; s[t + BS_TILE / 2] = a[base + t + BS_TILE / 2];
+    __syncthreads();
+    for (int k = k_first; k <= k_last; k <<= 1) {
+        for (int j = (k < BS_TILE ? k : BS_TILE) >> 1; j > 0; j >>= 1) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));          // lower index of this thread's pair
+            const int p = i | j;
+            const bool up = (((base + i) & k) == 0);
+            const u64 x = s[i], y = s[p];
+            if ((x > y) == up) { s[i] = y; s[p] = x; }
+            __syncthreads();
+        }
+    }
+    a[base + t] = s[t]; a[base + t + BS_TILE / 2] = s[t + BS_TILE / 2];
+}
+__global__ void bitonic_global_kernel(u64 *__restrict__ a, int n, int k, int j) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n / 2) return;
+    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const int p = i | j;
+    const bool up = ((i & k) == 0);
+    const u64 x = a[i], y = a[p];
+    if ((x > y) == up) { a[i] = y; a[p] = x; }
+}
+static int bitonic_sort_u64(u64 *d, int n_padded, cudaStream_t s) {      // n_padded: a power of two, >= BS_TILE
+    const int tiles = n_padded / BS_TILE;
+    bitonic_smem_kernel<<<tiles, BS_TILE / 2, 0, s>>>(d, 2, BS_TILE);     // every tile sorted (alternating directions by position)
+    DR_LAUNCHED();
+    for (int k = BS_TILE * 2; k <= n_padded; k <<= 1) {
+        for (int j = k >> 1; j >= BS_TILE; j >>= 1) {
+            bitonic_global_kernel<<<(n_padded / 2 + 255) / 256, 256, 0, s>>>(d, n_padded, k, j);
+            DR_LAUNCHED();
+        }
+        bitonic_smem_kernel<<<tiles, BS_TILE / 2, 0, s>>>(d, k, k);       // the remaining distances of this merge size
+        DR_LAUNCHED();
+    }
+    return 0;
+}
+
+// first pair of every target run (the run order the prune kernel sees is immaterial: every run is its own work item)
+__global__ void heads_kernel(const u64 *__restrict__ pairs, int n, int32_t *__restrict__ heads, int32_t *__restrict__ n_heads) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t k = keys[i];
-    if (k == DR_EMPTY) return;
-    if (i == 0 || keys[i - 1] != k) heads[atomicAdd(n_heads, 1)] = i;
+    const u64 k = pairs[i];
+    if (k == DR_KEY_MAX) return;
+    if (i == 0 || (uint32_t)(pairs[i - 1] >> 32) != (uint32_t)(k >> 32)) heads[atomicAdd(n_heads, 1)] = i;
 }
 
 __global__ void finalize_rows_kernel(uint32_t *__restrict__ adj, const int32_t *__restrict__ deg, long long N, int R) {
@@ -192,11 +241,10 @@ __global__ void finalize_rows_kernel(uint32_t *__restrict__ adj, const int32_t *
 struct BuildBufs {
     int32_t *sigma = nullptr, *list_ids = nullptr, *list_len = nullptr, *heads = nullptr, *n_heads = nullptr, *topk = nullptr;
     float *list_dist = nullptr;
-    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
-    void *cub_tmp = nullptr;
+    u64 *pairs = nullptr;
     ~BuildBufs() {
         cudaFree(sigma); cudaFree(list_ids); cudaFree(list_len); cudaFree(heads); cudaFree(n_heads); cudaFree(topk);
-        cudaFree(list_dist); cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(cub_tmp);
+        cudaFree(list_dist); cudaFree(pairs);
     }
 };
 
@@ -228,17 +276,12 @@ int launch_vamana_build(const float *d_X, int64_t N, int D, int R, int L, float 
     DR_CUDA(cudaMalloc(&b.list_len, (size_t)maxb * 4));
     DR_CUDA(cudaMalloc(&b.topk, (size_t)maxb * 4));
     const int max_pairs = (int)(maxb * R);
-    DR_CUDA(cudaMalloc(&b.keys, (size_t)max_pairs * 4));
-    DR_CUDA(cudaMalloc(&b.vals, (size_t)max_pairs * 4));
-    DR_CUDA(cudaMalloc(&b.keys2, (size_t)max_pairs * 4));
-    DR_CUDA(cudaMalloc(&b.vals2, (size_t)max_pairs * 4));
+    int max_padded = BS_TILE;
+    while (max_padded < max_pairs) max_padded <<= 1;
+    DR_CUDA(cudaMalloc(&b.pairs, (size_t)max_padded * 8));
     DR_CUDA(cudaMalloc(&b.heads, (size_t)max_pairs * 4));
     DR_CUDA(cudaMalloc(&b.n_heads, 8));      // [0] head count of the batch, [1] truncated-run counter of the whole build
     DR_CUDA(cudaMemsetAsync(b.n_heads, 0, 8, s));
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, b.keys, b.keys2, b.vals, b.vals2, max_pairs, 0, 32, s);
-    DR_CUDA(cudaMalloc(&b.cub_tmp, cub_bytes));
-
     DR_CUDA(cudaMemsetAsync(d_deg, 0, (size_t)N * 4, s));
     DR_CUDA(cudaMemsetAsync(d_adj, 0, (size_t)N * R * 4, s));
 
@@ -279,16 +322,16 @@ int launch_vamana_build(const float *d_X, int64_t N, int D, int R, int L, float 
             DR_LAUNCHED();
             // 3. reverse edges
             const int np = (int)(bs * R);
-            emit_pairs_kernel<<<(np + 255) / 256, 256, 0, s>>>(nodes, (int)bs, d_adj, d_deg, R, b.keys, b.vals);
+            int npad = BS_TILE;
+            while (npad < np) npad <<= 1;
+            emit_pairs_kernel<<<(npad + 255) / 256, 256, 0, s>>>(nodes, (int)bs, d_adj, d_deg, R, b.pairs, npad);
             DR_LAUNCHED();
-            size_t tmp = cub_bytes;
-            cub::DeviceRadixSort::SortPairs(b.cub_tmp, tmp, b.keys, b.keys2, b.vals, b.vals2, np, 0, 32, s);
-            g_launches.fetch_add(1);
+            if (bitonic_sort_u64(b.pairs, npad, s)) return 1;
             DR_CUDA(cudaMemsetAsync(b.n_heads, 0, 4, s));
-            heads_kernel<<<(np + 255) / 256, 256, 0, s>>>(b.keys2, np, b.heads, b.n_heads);
+            heads_kernel<<<(np + 255) / 256, 256, 0, s>>>(b.pairs, np, b.heads, b.n_heads);
             DR_LAUNCHED();
             PruneArgs pr = pa;
-            pr.mode = 1; pr.rkeys = b.keys2; pr.rvals = b.vals2; pr.heads = b.heads; pr.n_heads = b.n_heads; pr.n_pairs = np;
+            pr.mode = 1; pr.pairs = b.pairs; pr.heads = b.heads; pr.n_heads = b.n_heads; pr.n_pairs = np;
             pr.truncated = b.n_heads + 1;
             prune_kernel<<<(int)std::min<int64_t>(np, prune_grid_max), PR_THREADS, prune_smem, s>>>(pr);
             DR_LAUNCHED();
