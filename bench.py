@@ -564,9 +564,29 @@ def run_index_sharded(a):
     Qd = torch.empty_like(Q)
     oi_h = torch.empty((qhi - qlo, k), dtype=torch.int32, pin_memory=True); od_h = torch.empty((qhi - qlo, k), dtype=torch.float32, pin_memory=True)
 
+    # Every rank needs the WHOLE batch on its device.  Uploading it G times (once per rank: G x B x D x 4 bytes over PCIe) is what bounds the
+    # end-to-end number; instead every rank uploads only its slice (the one it also reduces) and the slices are all-gathered over NVLink:
+    # the one place on this path where a collective carries real data (B x D x 4 bytes per step, 1.2 GB at the named shape).
+    bq = DD.padded_slice_len(B, world)
+    Qpad = torch.empty((world * bq, a.dim), dtype=torch.float32, device=dev) if world > 1 else None
+    Qslice_h = Qh[qlo:qhi]
+
     def step_e2e():
-        Qd.copy_(Qh, non_blocking=True)
-        ri, rd = step(Qd.data_ptr())
+        if world == 1:
+            Qd.copy_(Qh, non_blocking=True)
+            qptr = Qd.data_ptr()
+        else:
+            mine = Qpad[rank * bq:rank * bq + (qhi - qlo)]
+            mine.copy_(Qslice_h, non_blocking=True)                                   # H2D: this rank's slice only
+            dist.all_gather_into_tensor(Qpad, Qpad[rank * bq:(rank + 1) * bq])         # NVLink: everybody's slices
+            if B % world == 0:
+                qptr = Qpad.data_ptr()
+            else:                                                                      # ragged slices: close the gaps
+                for g in range(world):
+                    glo, ghi = DD.query_slice(B, g, world)
+                    Qd[glo:ghi].copy_(Qpad[g * bq:g * bq + (ghi - glo)], non_blocking=True)
+                qptr = Qd.data_ptr()
+        ri, rd = step(qptr)
         oi_h.copy_(ri[:qhi - qlo], non_blocking=True); od_h.copy_(rd[:qhi - qlo], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
@@ -579,8 +599,15 @@ def run_index_sharded(a):
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": round(B * a.steps / float(te.item()), 1), "unit": UNIT, "h2d_bytes_per_step": int(B * a.dim * 4),
-           "d2h_bytes_per_step": int((qhi - qlo) * k * 8)}
+    if world > 1:                                           # the gathered batch is the batch (checked once, outside the timed region)
+        step_e2e()
+        torch.cuda.synchronize(dev)
+        got = Qpad if B % world == 0 else Qd
+        assert torch.equal(got[:B], Q), "all-gathered query batch differs from the batch"
+    e2e = {"value": round(B * a.steps / float(te.item()), 1), "unit": UNIT,
+           "h2d_bytes_per_step": int((qhi - qlo) * a.dim * 4 * world),       # all ranks together: the batch crosses PCIe once
+           "d2h_bytes_per_step": int(B * k * 8),
+           "nvlink_allgather_bytes_per_step": 0 if world == 1 else int(B * a.dim * 4)}
     if rank == 0:
         emit({"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
               "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
