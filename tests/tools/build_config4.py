@@ -32,7 +32,7 @@ def main():
     from diskrag_b200.engine import GpuIndex
     from diskrag_b200.synth import synth_numpy, synth_torch
     out = {}
-    cached = sorted((ROOT / ".cache").glob("config4_adj_*.npz"), key=lambda p: int(p.stem.split("_")[-1]))
+    cached = sorted(list((ROOT / ".cache").glob("config4_adj_*.npz")) + list((ROOT / "tests" / "golden").glob("config3_adj_*.npz")), key=lambda p: int(p.stem.split("_")[-1]))
     if cached:
         z = np.load(cached[-1])
         adj_ref, med, N, D, R, L, seed = z["adj"], int(z["medoid"]), int(z["N"]), int(z["D"]), int(z["R"]), int(z["L"]), int(z["seed"])
