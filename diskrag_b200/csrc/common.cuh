@@ -138,6 +138,27 @@ __device__ __forceinline__ float warp_sum_butterfly(float v) {
 
 __device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
+// a - b per component, IEEE round-to-nearest like four __fsub_rn; with DR_F32X2 the four subtractions are two packed
+// sub.rn.f32x2 (FADD2 on sm_100a: one issue slot for two results; the vector loads already deliver aligned register pairs)
+#ifndef DR_F32X2
+#define DR_F32X2 1
+#endif
+__device__ __forceinline__ void f4sub(const float4 &a, const float4 &b, float &d0, float &d1, float &d2, float &d3) {
+#if DR_F32X2 && defined(__CUDA_ARCH__)   // (the host-side warp emulator of tests/ compiles this text with g++: scalar path)
+    unsigned long long alo, ahi, blo, bhi, dlo, dhi;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(alo) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ahi) : "f"(a.z), "f"(a.w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(blo) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bhi) : "f"(b.z), "f"(b.w));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dlo) : "l"(alo), "l"(blo));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dhi) : "l"(ahi), "l"(bhi));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dlo));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d2), "=f"(d3) : "l"(dhi));
+#else
+    d0 = __fsub_rn(a.x, b.x); d1 = __fsub_rn(a.y, b.y); d2 = __fsub_rn(a.z, b.z); d3 = __fsub_rn(a.w, b.w);
+#endif
+}
+
 // Canonical exact fp32 squared L2 of one row against a query held in shared memory, one warp per row.
 // Order (restated by oracle.c:orc_l2sq_warp): lane l owns elements (j*32+l)*VW+c, VW = 4 if D%4==0
 // else 1; per lane fmaf accumulation in increasing index; xor-butterfly 16,8,4,2,1.
@@ -149,7 +170,8 @@ __device__ __forceinline__ float warp_l2sq(const float *__restrict__ row, const 
         for (; base < D; base += 128) {
             float4 a = ldg_f4(row + base);
             float4 b = *reinterpret_cast<const float4 *>(q + base);
-            float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y), d2 = __fsub_rn(a.z, b.z), d3 = __fsub_rn(a.w, b.w);
+            float d0, d1, d2, d3;
+            f4sub(a, b, d0, d1, d2, d3);
             acc = __fmaf_rn(d0, d0, acc);
             acc = __fmaf_rn(d1, d1, acc);
             acc = __fmaf_rn(d2, d2, acc);
@@ -203,9 +225,11 @@ __device__ __forceinline__ void warp_l2sq_x2(const float *__restrict__ rowA, con
             float4 a = ldg_f4(rowA + base);
             float4 c = ldg_f4(rowB + base);
             float4 b = *reinterpret_cast<const float4 *>(q + base);
-            float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y), d2 = __fsub_rn(a.z, b.z), d3 = __fsub_rn(a.w, b.w);
+            float d0, d1, d2, d3;
+            f4sub(a, b, d0, d1, d2, d3);
             accA = __fmaf_rn(d0, d0, accA); accA = __fmaf_rn(d1, d1, accA); accA = __fmaf_rn(d2, d2, accA); accA = __fmaf_rn(d3, d3, accA);
-            float e0 = __fsub_rn(c.x, b.x), e1 = __fsub_rn(c.y, b.y), e2 = __fsub_rn(c.z, b.z), e3 = __fsub_rn(c.w, b.w);
+            float e0, e1, e2, e3;
+            f4sub(c, b, e0, e1, e2, e3);
             accB = __fmaf_rn(e0, e0, accB); accB = __fmaf_rn(e1, e1, accB); accB = __fmaf_rn(e2, e2, accB); accB = __fmaf_rn(e3, e3, accB);
         }
     } else {

@@ -242,7 +242,8 @@ __device__ __forceinline__ float l2sq_piece_smem(const float *__restrict__ row, 
         for (int it = 0; it < FULL; ++it) {
             const float4 x = *reinterpret_cast<const float4 *>(r0 + it * 128);
             const float4 y = *reinterpret_cast<const float4 *>(q0 + it * 128);
-            const float d0 = __fsub_rn(x.x, y.x), d1 = __fsub_rn(x.y, y.y), d2 = __fsub_rn(x.z, y.z), d3 = __fsub_rn(x.w, y.w);
+            float d0, d1, d2, d3;
+            f4sub(x, y, d0, d1, d2, d3);
             acc = __fmaf_rn(d0, d0, acc);
             acc = __fmaf_rn(d1, d1, acc);
             acc = __fmaf_rn(d2, d2, acc);
@@ -255,7 +256,8 @@ __device__ __forceinline__ float l2sq_piece_smem(const float *__restrict__ row, 
     for (int base = e0 + lane * 4; base < e1; base += 128) {
         const float4 x = *reinterpret_cast<const float4 *>(row + base);
         const float4 y = *reinterpret_cast<const float4 *>(q + base);
-        const float d0 = __fsub_rn(x.x, y.x), d1 = __fsub_rn(x.y, y.y), d2 = __fsub_rn(x.z, y.z), d3 = __fsub_rn(x.w, y.w);
+        float d0, d1, d2, d3;
+        f4sub(x, y, d0, d1, d2, d3);
         acc = __fmaf_rn(d0, d0, acc);
         acc = __fmaf_rn(d1, d1, acc);
         acc = __fmaf_rn(d2, d2, acc);
