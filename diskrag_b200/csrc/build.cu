@@ -15,6 +15,10 @@
 // stale-tail re-selection of :460-466 is not reproduced; graphs are compared by recall.
 #include "common.cuh"
 
+#ifndef DR_BUILD_W
+#define DR_BUILD_W 4   // list entries expanded per step by the build's batched search
+#endif
+
 
 #include <algorithm>
 #include <random>
@@ -287,7 +291,7 @@ int launch_vamana_build(const float *d_X, int64_t N, int D, int R, int L, float 
 
     dr_search_params sp;
     memset(&sp, 0, sizeof(sp));
-    sp.k = 1; sp.L = L; sp.W = 4; sp.dist = DR_DIST_EXACT; sp.rerank = 0;
+    sp.k = 1; sp.L = L; sp.W = DR_BUILD_W; sp.dist = DR_DIST_EXACT; sp.rerank = 0;
 
     const size_t prune_smem = (size_t)2 * D * 4;
     DR_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prune_smem));

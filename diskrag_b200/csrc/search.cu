@@ -18,6 +18,13 @@
 // PQ code rows with 128-bit loads, full vectors (exact mode / rerank) with coalesced float4 loads.
 #include "common.cuh"
 
+#ifndef DR_COMPACT_NEWK
+#define DR_COMPACT_NEWK 1   // W > 1: survivors appended compactly (merge cost ~ survivors, not newcomers)
+#endif
+#ifndef DR_EXACT_X2
+#define DR_EXACT_X2 1   // exact-distance phase of search_kernel: two rows per warp in flight (the graph build's search)
+#endif
+
 #include <vector>
 
 struct SearchArgs {
@@ -294,14 +301,18 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
             const bool full = (n >= L);
             const u64 worstk = lst[n - 1] & ~1ull;
             const uint32_t worst_db = key_dbits(worstk);
+            // survivors are appended compactly when their order cannot matter (keys are unique and the rank merge is
+            // order-free): the merge then costs (n + survivors) x survivors compares instead of (n + newcomers) x newcomers.
+            // The reference-order tie mode keeps one slot per newcomer: its sequential fallback inserts in discovery order.
+            const bool compact = DR_COMPACT_NEWK && !strict;
             if (pq && !a.adc_tree) {
                 for (int i = tid; i < nn; i += nt) {
                     uint32_t id = s_newid[i];
                     float d = adc_seq(a.codes + (size_t)id * M, s_lut, M);
                     u64 key = make_key(d, id);
                     bool ok = !full || (strict ? (key_dbits(key) < worst_db) : (key < worstk));
-                    s_newk[i] = ok ? key : DR_KEY_MAX;
-                    if (ok) atomicAdd(&s_mvalid, 1);
+                    if (compact) { if (ok) s_newk[atomicAdd(&s_mvalid, 1)] = key; }
+                    else { s_newk[i] = ok ? key : DR_KEY_MAX; if (ok) atomicAdd(&s_mvalid, 1); }
                 }
             } else if (pq && (M & 3) == 0 && M <= 256) {
                 constexpr int G = 4;
@@ -322,9 +333,33 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
                             if (g < cnt) {
                                 u64 key = make_key(gd[g], gid[g]);
                                 bool ok = !full || (strict ? (key_dbits(key) < worst_db) : (key < worstk));
-                                s_newk[base + g * nw] = ok ? key : DR_KEY_MAX;
-                                if (ok) atomicAdd(&s_mvalid, 1);
+                                if (compact) { if (ok) s_newk[atomicAdd(&s_mvalid, 1)] = key; }
+                                else { s_newk[base + g * nw] = ok ? key : DR_KEY_MAX; if (ok) atomicAdd(&s_mvalid, 1); }
                             }
+                        }
+                    }
+                }
+            } else if (!pq && !cosine && DR_EXACT_X2) {
+                // exact L2: two rows per warp at a time (twice the bytes in flight per warp; each row keeps the canonical order)
+                for (int i = wid; i < nn; i += 2 * nw) {
+                    const int i2 = i + nw;
+                    const uint32_t idA = s_newid[i], idB = s_newid[i2 < nn ? i2 : i];
+                    float dA, dB;
+                    if (i2 < nn) warp_l2sq_x2(a.vec + (size_t)idA * D, a.vec + (size_t)idB * D, s_q, D, lane, dA, dB);
+                    else { dA = warp_l2sq(a.vec + (size_t)idA * D, s_q, D, lane); dB = 0.0f; }
+                    if (lane == 0) {
+                        const u64 keyA = make_key(dA, idA);
+                        const bool okA = !full || (strict ? (key_dbits(keyA) < worst_db) : (keyA < worstk));
+                        const u64 keyB = make_key(dB, idB);
+                        const bool okB = i2 < nn && (!full || (strict ? (key_dbits(keyB) < worst_db) : (keyB < worstk)));
+                        const int okn = (okA ? 1 : 0) + (okB ? 1 : 0);
+                        int slot = okn ? atomicAdd(&s_mvalid, okn) : 0;
+                        if (compact) {
+                            if (okA) s_newk[slot++] = keyA;
+                            if (okB) s_newk[slot] = keyB;
+                        } else {
+                            s_newk[i] = okA ? keyA : DR_KEY_MAX;
+                            if (i2 < nn) s_newk[i2] = okB ? keyB : DR_KEY_MAX;
                         }
                     }
                 }
@@ -336,8 +371,8 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
                     if (lane == 0) {
                         u64 key = make_key(d, id);
                         bool ok = !full || (strict ? (key_dbits(key) < worst_db) : (key < worstk));
-                        s_newk[i] = ok ? key : DR_KEY_MAX;
-                        if (ok) atomicAdd(&s_mvalid, 1);
+                        if (compact) { if (ok) s_newk[atomicAdd(&s_mvalid, 1)] = key; }
+                        else { s_newk[i] = ok ? key : DR_KEY_MAX; if (ok) atomicAdd(&s_mvalid, 1); }
                     }
                 }
             }
@@ -355,20 +390,21 @@ __global__ void __launch_bounds__(512, 1) search_kernel(const SearchArgs a) {
 
             // (4) rank-merge newcomers into the other buffer; best L stay
             if (mvalid > 0) {
-                const int total = n + nn;
+                const int nk = compact ? mvalid : nn;      // keys in s_newk: the survivors only, or one slot per newcomer
+                const int total = n + nk;
                 for (int x = tid; x < total; x += nt) {
                     u64 key;
                     int pos;
                     if (x < n) {
                         key = lst[x];
                         int c = 0;
-                        for (int j = 0; j < nn; ++j) c += (s_newk[j] < key) ? 1 : 0;
+                        for (int j = 0; j < nk; ++j) c += (s_newk[j] < key) ? 1 : 0;
                         pos = x + c;
                     } else {
                         key = s_newk[x - n];
                         if (key == DR_KEY_MAX) continue;
                         int c = 0;
-                        for (int j = 0; j < nn; ++j) c += (s_newk[j] < key) ? 1 : 0;
+                        for (int j = 0; j < nk; ++j) c += (s_newk[j] < key) ? 1 : 0;
                         int lo = 0, hi = n;
                         while (lo < hi) {
                             int mid = (lo + hi) >> 1;
