@@ -15,6 +15,9 @@
 // stale-tail re-selection of :460-466 is not reproduced; graphs are compared by recall.
 #include "common.cuh"
 
+#ifndef DR_PRUNE_X2
+#define DR_PRUNE_X2 1   // RobustPrune distance loops: two candidate rows per warp in flight
+#endif
 #ifndef DR_BUILD_W
 #define DR_BUILD_W 4   // list entries expanded per step by the build's batched search
 #endif
@@ -117,11 +120,29 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
         // ---- distances to p ------------------------------------------------------------------------------
         for (int i = tid; i < D; i += nt) s_p[i] = __ldg(a.X + (size_t)node * D + i);
         __syncthreads();
+#if DR_PRUNE_X2
+        for (int i = wid; i < n;) {   // two unknown candidates per warp at a time (twice the bytes in flight; same sums)
+            while (i < n && (s_flag[i] & 3)) i += nw;  // known or duplicate
+            if (i >= n) break;
+            int i2 = i + nw;
+            while (i2 < n && (s_flag[i2] & 3)) i2 += nw;
+            if (i2 < n) {
+                float dA, dB;
+                warp_l2sq_x2(a.X + (size_t)s_id[i] * D, a.X + (size_t)s_id[i2] * D, s_p, D, lane, dA, dB);
+                if (lane == 0) { s_d[i] = dA; s_d[i2] = dB; }
+            } else {
+                const float d = warp_l2sq(a.X + (size_t)s_id[i] * D, s_p, D, lane);
+                if (lane == 0) s_d[i] = d;
+            }
+            i = i2 + nw;
+        }
+#else
         for (int i = wid; i < n; i += nw) {
             if (s_flag[i] & 3) continue;  // known or duplicate
             float d = warp_l2sq(a.X + (size_t)s_id[i] * D, s_p, D, lane);
             if (lane == 0) s_d[i] = d;
         }
+#endif
         __syncthreads();
         // ---- sort by (d, id): rank counting ----------------------------------------------------------------
         for (int i = tid; i < n; i += nt) s_key[i] = (s_flag[i] & 2) ? DR_KEY_MAX : make_key(s_d[i], s_id[i]);
@@ -151,11 +172,34 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
             if (s_nalive <= cnt) continue;  // everything still alive is already selected or will be without tests
             for (int t = tid; t < D; t += nt) s_star[t] = __ldg(a.X + (size_t)s_sid[i] * D + t);
             __syncthreads();
+#if DR_PRUNE_X2
+            for (int j = i + 1 + wid; j < nu;) {   // entries j, j + nw, ... belong to this warp alone: their flags only change here
+                while (j < nu && !s_flag[j]) j += nw;
+                if (j >= nu) break;
+                int j2 = j + nw;
+                while (j2 < nu && !s_flag[j2]) j2 += nw;
+                if (j2 < nu) {
+                    float dA, dB;
+                    warp_l2sq_x2(a.X + (size_t)s_sid[j] * D, a.X + (size_t)s_sid[j2] * D, s_star, D, lane, dA, dB);
+                    if (lane == 0) {
+                        int killed = 0;
+                        if (__fmul_rn(a.alpha, dA) <= s_sd[j]) { s_flag[j] = 0; ++killed; }
+                        if (__fmul_rn(a.alpha, dB) <= s_sd[j2]) { s_flag[j2] = 0; ++killed; }
+                        if (killed) atomicSub(&s_nalive, killed);
+                    }
+                } else {
+                    const float d = warp_l2sq(a.X + (size_t)s_sid[j] * D, s_star, D, lane);
+                    if (lane == 0 && __fmul_rn(a.alpha, d) <= s_sd[j]) { s_flag[j] = 0; atomicSub(&s_nalive, 1); }
+                }
+                j = j2 + nw;
+            }
+#else
             for (int j = i + 1 + wid; j < nu; j += nw) {
                 if (!s_flag[j]) continue;
                 float d = warp_l2sq(a.X + (size_t)s_sid[j] * D, s_star, D, lane);
                 if (lane == 0 && __fmul_rn(a.alpha, d) <= s_sd[j]) { s_flag[j] = 0; atomicSub(&s_nalive, 1); }
             }
+#endif
             __syncthreads();
         }
         __syncthreads();

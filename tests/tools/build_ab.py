@@ -25,12 +25,16 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = prev
     adj = torch.empty((N, R), dtype=torch.int32, device=dev); deg = torch.empty(N, dtype=torch.int32, device=dev)
     times = []
-    for rep in range(2):
+    import os
+    profile_only = bool(os.environ.get("BUILD_AB_PROFILE"))     # one build, no recall leg (under ncu)
+    for rep in range(1 if profile_only else 2):
         torch.cuda.synchronize(); t = time.time()
         check(lib().dr_vamana_build_dev(X.data_ptr(), N, D, R, L, 1.2, 0, 1, adj.data_ptr(), deg.data_ptr(), 0, 0), "dr_vamana_build_dev")
         torch.cuda.synchronize(); times.append(round(time.time() - t, 3))
     out = {"N": N, "D": D, "R": R, "L": L, "build_s": times, "mean_degree": round(float(deg.float().mean()), 2),
            "truncated": int(lib().dr_vamana_build_last_truncated())}
+    if profile_only:
+        print("BUILD_AB", json.dumps(out)); return
     Xh = X.cpu().numpy(); Qh = Q.cpu().numpy(); adjh = adj.cpu().numpy().view(np.uint32)
     del X
     with GpuIndex.from_arrays(Xh, adjh, medoid=0) as idx:
