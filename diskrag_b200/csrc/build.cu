@@ -18,6 +18,14 @@
 #ifndef DR_PRUNE_X2
 #define DR_PRUNE_X2 1   // RobustPrune distance loops: two candidate rows per warp in flight
 #endif
+#ifndef DR_BUILD_HASH
+#define DR_BUILD_HASH 4096   // visited-table slots in shared memory of the build's search (0 = the search's own sizing, 16384 at R = 64);
+                             // a query that visits more spills to the search's per-CTA global table
+#endif
+#ifndef DR_BUILD_THREADS
+#define DR_BUILD_THREADS 128 // threads per CTA of the build's search: four small CTAs per SM beat two of 256 threads (1M x 768, R = 64:
+                             // 3.17 -> 2.75 s; 64 threads: 2.67-2.96 s)
+#endif
 #ifndef DR_BUILD_W
 #define DR_BUILD_W 4   // list entries expanded per step by the build's batched search
 #endif
@@ -341,6 +349,7 @@ int launch_vamana_build(const float *d_X, int64_t N, int D, int R, int L, float 
     dr_search_params sp;
     memset(&sp, 0, sizeof(sp));
     sp.k = 1; sp.L = L; sp.W = DR_BUILD_W; sp.dist = DR_DIST_EXACT; sp.rerank = 0;
+    sp.hash_cap = DR_BUILD_HASH; sp.threads = DR_BUILD_THREADS;
 
     const size_t prune_smem = (size_t)2 * D * 4;
     DR_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prune_smem));

@@ -16,10 +16,13 @@ for spec in sys.argv[1:]:
     src = "search_fast.cu"
     if "@" in name:
         name, src = name.split("@", 1)
-    o = out / f"{src[:-3]}_{name}.o"
-    cmd = [B._nvcc(), *[f for f in B.NVCC_FLAGS if f != "-shared"], *flags.split(), "-c", str(B.CSRC / src), "-o", str(o)]
-    subprocess.check_call(cmd)
-    objs = [str(o) if s == src else str(B.HERE / "build" / (s + ".o")) for s in B.SOURCES]
+    repl = {}
+    for one in src.split(","):                                  # name@a.cu,b.cu: the same flags on several sources
+        o = out / f"{one[:-3]}_{name}.o"
+        cmd = [B._nvcc(), *[f for f in B.NVCC_FLAGS if f != "-shared"], *flags.split(), "-c", str(B.CSRC / one), "-o", str(o)]
+        subprocess.check_call(cmd)
+        repl[one] = str(o)
+    objs = [repl.get(s, str(B.HERE / "build" / (s + ".o"))) for s in B.SOURCES]
     lib = out / f"lib_{name}.so"
     subprocess.check_call([B._nvcc(), "-shared", "-o", str(lib), *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
     print(lib)
