@@ -176,15 +176,22 @@ __global__ void __launch_bounds__(TC_THREADS, TC_CTAS) lut_u8_tc_kernel(const Lu
             stage_mma(tmem, a_base, b_base, nks1, &s_bar, phase, tid);
             stage_wait(&s_bar, phase);
             if (PHASE == 1) {
+                // the four subspaces' loads go out together and are waited for once (a tcgen05.ld round trip is ~230 cycles with
+                // eight warps on the port: one wait per load made this pass a chain of eight of them per stage)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int i8 = 0; i8 < HQ / 8; ++i8) {
+                    float v0[8], v1[8], v2[8], v3[8];
+                    tmem_ld8(tlane + (uint32_t)(0 * TC_NQ + i8 * 8), v0);
+                    tmem_ld8(tlane + (uint32_t)(1 * TC_NQ + i8 * 8), v1);
+                    tmem_ld8(tlane + (uint32_t)(2 * TC_NQ + i8 * 8), v2);
+                    tmem_ld8(tlane + (uint32_t)(3 * TC_NQ + i8 * 8), v3);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int i8 = 0; i8 < HQ / 8; ++i8) {
-                        float v[8];
-                        tmem_ld8(tlane + (uint32_t)(j * TC_NQ + i8 * 8), v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { lo[j] = fminf(lo[j], v[i]); hi[j] = fmaxf(hi[j], v[i]); }
+                    for (int i = 0; i < 8; ++i) {
+                        lo[0] = fminf(lo[0], v0[i]); hi[0] = fmaxf(hi[0], v0[i]);
+                        lo[1] = fminf(lo[1], v1[i]); hi[1] = fmaxf(hi[1], v1[i]);
+                        lo[2] = fminf(lo[2], v2[i]); hi[2] = fmaxf(hi[2], v2[i]);
+                        lo[3] = fminf(lo[3], v3[i]); hi[3] = fmaxf(hi[3], v3[i]);
                     }
                 }
             } else {
