@@ -570,7 +570,11 @@ def _graph_prune(graph, point_idx, candidate_set, alpha, R):
 
 def _graph_prune_nearest(graph, point_idx, candidate_set, R):
     """The reference's prune as it behaves (see _graph_prune): the R nearest live candidates by squared L2, ties by id
-    (`candidates_with_dist.sort()` on (dist, cid) tuples), inserted into a fresh set in that order."""
+    (`candidates_with_dist.sort()` on (dist, cid) tuples), inserted into a fresh set in that order.
+    Squared L2 also on a graph whose distance_metric is 'cosine': robust_prune_cython calls
+    compute_distance_fn(graph, a, b, graph.distance_metric) (cython_utils.pyx:141,160), and compute_distance's fourth positional
+    parameter is query_vector (vamana_graph.py:259) -- the metric never arrives, distance_metric keeps its default 'l2'.  (With
+    use_pq_for_search on, that stray string reaches compute_distance_table and the reference's insert raises; here it prunes.)"""
     g, cands = _prune_inputs(graph, point_idx, candidate_set, keep_self=True)   # the reference does not exclude the point itself
     new = set()
     if cands.size:

@@ -256,6 +256,29 @@ def test_reference_python_prune_keeps_the_R_nearest(world, ref):
             assert g.nodes[p].neighbors == set(c for _, c in d[:w["R"]]), (alpha, p)
 
 
+def test_reference_prune_uses_l2_on_a_cosine_graph(world, ref):
+    """Evidence for the shim's insert_node on a distance_metric='cosine' graph (round-1 advice asked whether pruning by squared
+    L2 there is a bug): robust_prune_cython passes graph.distance_metric as the FOURTH positional argument of compute_distance
+    (cython_utils.pyx:141,160), which is query_vector (vamana_graph.py:259) -- the metric never arrives and the reference prunes by
+    squared L2 whatever the graph's metric is.  Vectors of different norms make the two orders differ."""
+    w = world
+    vg, cu = ref["vamana_graph"], ref["cython_utils"]
+    rng = np.random.default_rng(23)
+    X = (w["X"] * rng.uniform(0.2, 5.0, size=(w["N"], 1))).astype(np.float32)        # cosine order != L2 order
+    g = vg.VamanaGraphWithPQ(w["R"], None, distance_metric='cosine')
+    for i in range(w["N"]):
+        g.nodes[i] = vg.Node(i, X[i], None)
+    differs = 0
+    for p in (0, 7, 123, 599):
+        cands = set(int(c) for c in rng.choice(w["N"], 40, replace=False) if int(c) != p)
+        cu.robust_prune_cython(g, p, cands, 1.0, w["R"], vg.compute_distance)
+        by_l2 = sorted((cu.l2_distance_fast_cython(X[p], X[c]), c) for c in cands)
+        by_cos = sorted((cu.cosine_similarity_cython(X[p], X[c]), c) for c in cands)
+        assert g.nodes[p].neighbors == set(c for _, c in by_l2[:w["R"]]), p
+        differs += g.nodes[p].neighbors != set(c for _, c in by_cos[:w["R"]])
+    assert differs > 0          # the fixture does tell the two metrics apart
+
+
 def test_variant_A_with_lazily_deleted_nodes(world, orc, ref):
     """greedy_search_cython on a graph with is_deleted nodes (cython_utils.pyx:84-90, 100-101, 109, 120; §8 a14): deleted nodes are
     never visited and never returned, a deleted start is replaced by the first live node.  Heap form == the reference's list in its
