@@ -23,6 +23,9 @@
 // each), so one CTA's staging + MMA round trip hides behind the other's epilogue.
 #include "tc_common.cuh"
 
+#ifndef DR_LUT_PREFETCH_B
+#define DR_LUT_PREFETCH_B 1
+#endif
 #define TC_ROWS 128      // queries per CTA tile = TMEM lanes
 #define TC_THREADS 256   // two threads per query row: warps 0-3 take the first half of a stage's centroids, warps 4-7 the second
 #ifndef TC_NQ
@@ -87,6 +90,32 @@ __device__ __forceinline__ void stage_B(const float *__restrict__ codebook, int 
     }
 }
 
+// The same staging in two halves for the compile-time sub-dimensions: the loads of stage s+1 are issued right after the MMAs of
+// stage s (their L2 round trip hides behind the MMA wait and the epilogue), the convert + store runs when the epilogue is done.
+template <int DS>
+__device__ __forceinline__ void stage_B_load(const float *__restrict__ codebook, int w, int c0, int wid, int lane, float4 (&v)[DS / 4]) {
+    static_assert(TC_NQ == 32, "one centroid row per lane");
+    const float *src = codebook + ((size_t)(4 * w + wid) * 256 + c0 + lane) * DS;
+#pragma unroll
+    for (int kc = 0; kc < DS / 4; ++kc) v[kc] = ldg_f4(src + kc * 4);
+}
+template <int DS>
+__device__ __forceinline__ void stage_B_store(const float4 (&v)[DS / 4], unsigned char *sB, int wid, int lane) {
+    constexpr int nks = DS >> 3, nks1 = nks + 1;
+    const int j = wid, r = lane;
+    float cn = 0.0f;
+#pragma unroll
+    for (int kc = 0; kc < DS / 4; ++kc) {
+        cn = __fmaf_rn(v[kc].x, v[kc].x, cn); cn = __fmaf_rn(v[kc].y, v[kc].y, cn);
+        cn = __fmaf_rn(v[kc].z, v[kc].z, cn); cn = __fmaf_rn(v[kc].w, v[kc].w, cn);
+        *reinterpret_cast<float4 *>(sB + (j * nks1 + (kc >> 1)) * (TC_NQ * 32) + core_off(r, kc & 1)) = tf32_rna4(v[kc]);
+    }
+    const float ch = tf32_hi(cn);
+    unsigned char *x = sB + (j * nks1 + nks) * (TC_NQ * 32);
+    *reinterpret_cast<float4 *>(x + core_off(r, 0)) = make_float4(ch, cn - ch, ch, 1.0f);
+    *reinterpret_cast<float4 *>(x + core_off(r, 1)) = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+}
+
 // grid (query tiles, word groups), 256 threads: two per query row (= TMEM lane), each reducing half of a stage's centroids, so that
 // eight warps per CTA (32 per SM) cover the TMEM round trips and the store latency.
 // PHASE 1: lo[b][m] = min_c t and range_bits[b] = max(range_bits[b], max_c t - lo)        (then lut_u8_finalize_kernel)
@@ -148,6 +177,9 @@ __global__ void __launch_bounds__(TC_THREADS, TC_CTAS) lut_u8_tc_kernel(const Lu
         }
     }
     float rmax = 0.0f;
+    constexpr bool PF = DR_LUT_PREFETCH_B && (DS == 8 || (DS == 16 && PHASE == 1)) && TC_NQ == 32;   // register prefetch of the next stage's centroids
+    float4 pfv[PF ? DS / 4 : 1];
+    if (PF && wid < 4 && w_begin < w_end) stage_B_load<(PF ? DS : 4)>(a.codebook, w_begin, 0, wid, lane, pfv);
     for (int w = w_begin; w < w_end; ++w) {
         // A for this word: the row's 4 * ds query elements times -2 (phase 2: -2 inv), then the extra K-step
         for (int j = 0; j < 4 && owner; ++j) {
@@ -172,8 +204,16 @@ __global__ void __launch_bounds__(TC_THREADS, TC_CTAS) lut_u8_tc_kernel(const Lu
 #pragma unroll
         for (int j = 0; j < 4; ++j) { lo[j] = __int_as_float(0x7f800000); hi[j] = -__int_as_float(0x7f800000); }
         for (int c0 = 0; c0 < 256; c0 += TC_NQ) {
-            if (wid < 4) stage_B(a.codebook, w, c0, ds, nks, sB, wid, lane);
+            if (wid < 4) {
+                if (PF) stage_B_store<(PF ? DS : 4)>(pfv, sB, wid, lane);
+                else stage_B(a.codebook, w, c0, ds, nks, sB, wid, lane);
+            }
             stage_mma(tmem, a_base, b_base, nks1, &s_bar, phase, tid);
+            if (PF && wid < 4) {
+                const bool last_c = c0 + TC_NQ >= 256;
+                const int wn = last_c ? w + 1 : w, cn0 = last_c ? 0 : c0 + TC_NQ;
+                if (wn < w_end) stage_B_load<(PF ? DS : 4)>(a.codebook, wn, cn0, wid, lane, pfv);
+            }
             stage_wait(&s_bar, phase);
             if (PHASE == 1) {
                 // the four subspaces' loads go out together and are waited for once (a tcgen05.ld round trip is ~230 cycles with
