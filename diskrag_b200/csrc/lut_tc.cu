@@ -94,7 +94,6 @@ __device__ __forceinline__ void stage_B(const float *__restrict__ codebook, int 
 // stage s (their L2 round trip hides behind the MMA wait and the epilogue), the convert + store runs when the epilogue is done.
 template <int DS>
 __device__ __forceinline__ void stage_B_load(const float *__restrict__ codebook, int w, int c0, int wid, int lane, float4 (&v)[DS / 4]) {
-    static_assert(TC_NQ == 32, "one centroid row per lane");
     const float *src = codebook + ((size_t)(4 * w + wid) * 256 + c0 + lane) * DS;
 #pragma unroll
     for (int kc = 0; kc < DS / 4; ++kc) v[kc] = ldg_f4(src + kc * 4);
