@@ -23,6 +23,9 @@
 // each), so one CTA's staging + MMA round trip hides behind the other's epilogue.
 #include "tc_common.cuh"
 
+#ifndef DR_LUT_PAIR
+#define DR_LUT_PAIR 1
+#endif
 #ifndef DR_LUT_PREFETCH_B
 #define DR_LUT_PREFETCH_B 1
 #endif
@@ -297,6 +300,215 @@ __global__ void __launch_bounds__(TC_THREADS, TC_CTAS) lut_u8_tc_kernel(const Lu
     if (wid == 0) tmem_dealloc(tmem, TC_COLS);
 }
 
+// ---- pair stages: N = 64 centroids per MMA ---------------------------------------------------------------------------------
+// Same contraction, same 128 TMEM columns per CTA (four CTAs per SM), but a stage is TWO subspaces x 64 centroids instead of four
+// x 32: every tcgen05.mma re-reads its 4 KB A tile (128 queries x 8) from shared memory whatever N is, so N = 64 halves the
+// A-operand bytes per table entry (the kernel's shared-memory traffic is what bounds it).  A packed output word needs
+// the bytes of all four subspaces of the code word: the stage of subspaces 0-1 leaves its 16-bit halves in registers (two
+// centroids per register), the stage of subspaces 2-3 of the same 64 centroids completes the words and stores them.
+#define T2_NQ 64
+#define T2_COLS (2 * T2_NQ)
+#define T2_CTAS (512 / T2_COLS)
+
+// rows of the B operand of a pair stage: staging warp wid holds subspace jj = wid >> 1 of the pair, centroids (wid & 1) * 32 + lane
+template <int DS>
+__device__ __forceinline__ void stage_B2_load(const float *__restrict__ codebook, int w, int pr, int c0, int wid, int lane, float4 (&v)[DS / 4]) {
+    const float *src = codebook + ((size_t)(4 * w + 2 * pr + (wid >> 1)) * 256 + c0 + (wid & 1) * 32 + lane) * DS;
+#pragma unroll
+    for (int kc = 0; kc < DS / 4; ++kc) v[kc] = ldg_f4(src + kc * 4);
+}
+template <int DS>
+__device__ __forceinline__ void stage_B2_store(const float4 (&v)[DS / 4], unsigned char *sB, int wid, int lane) {
+    constexpr int nks = DS >> 3, nks1 = nks + 1;
+    const int jj = wid >> 1, r = (wid & 1) * 32 + lane;
+    float cn = 0.0f;
+#pragma unroll
+    for (int kc = 0; kc < DS / 4; ++kc) {
+        cn = __fmaf_rn(v[kc].x, v[kc].x, cn); cn = __fmaf_rn(v[kc].y, v[kc].y, cn);
+        cn = __fmaf_rn(v[kc].z, v[kc].z, cn); cn = __fmaf_rn(v[kc].w, v[kc].w, cn);
+        *reinterpret_cast<float4 *>(sB + (jj * nks1 + (kc >> 1)) * (T2_NQ * 32) + core_off(r, kc & 1)) = tf32_rna4(v[kc]);
+    }
+    const float ch = tf32_hi(cn);
+    unsigned char *x = sB + (jj * nks1 + nks) * (T2_NQ * 32);
+    *reinterpret_cast<float4 *>(x + core_off(r, 0)) = make_float4(ch, cn - ch, ch, 1.0f);
+    *reinterpret_cast<float4 *>(x + core_off(r, 1)) = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+}
+
+template <int PHASE, int DS>   // DS = 8 (compile-time; other sub-dimensions use lut_u8_tc_kernel)
+__global__ void __launch_bounds__(TC_THREADS, T2_CTAS) lut_u8_tc2_kernel(const LutTcArgs a) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int ds = DS, nks = DS >> 3, nks1 = nks + 1;
+    const int words = a.M >> 2, D = a.D, M = a.M;
+    unsigned char *sA = tc_smem;
+    unsigned char *sB = tc_smem + 4 * nks1 * (TC_ROWS * 32);
+    float *sS = reinterpret_cast<float *>(sB + 2 * nks1 * (T2_NQ * 32));
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+
+    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    if (wid == 0) tmem_alloc(&s_tmem, T2_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int half = wid >> 2, row = tid & (TC_ROWS - 1);
+    const bool owner = tid < TC_ROWS;
+    constexpr int HQ = T2_NQ / 2;                                       // 32 centroids of a stage per thread (per subspace)
+    const uint32_t tlane = tmem + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)(half * HQ);
+    uint32_t phase = 0;
+
+    const long long b0 = (long long)blockIdx.x * TC_ROWS;
+    const long long b = b0 + row;
+    const bool live = b < a.B;
+    const float *qrow = a.Q + (size_t)(live ? b : b0) * D;
+    const int w_begin = blockIdx.y * a.words_per_cta;
+    const int w_end = (w_begin + a.words_per_cta < words) ? (w_begin + a.words_per_cta) : words;
+
+    float mul = -2.0f, inv = 1.0f, inv_hi = 1.0f, inv_lo = 0.0f;
+    if (PHASE == 2) {     // as in lut_u8_tc_kernel: scale from the statistics pass; the first word group publishes scale / offset
+        const float range = __uint_as_float(a.range_bits[live ? b : b0]);
+        const float scale = range > 0.0f ? __fdiv_rn(range, 255.0f) : 1.0f;
+        inv = __fdiv_rn(1.0f, scale);
+        inv_hi = tf32_hi(inv); inv_lo = inv - inv_hi; mul = -2.0f * inv;
+        if (blockIdx.y == 0 && live && owner) {
+            float acc = 0.0f, qn = 0.0f;
+            for (int m = 0; m < M; ++m) acc = __fadd_rn(acc, a.lo[(size_t)b * M + m]);
+            for (int j = 0; j < D; j += 4) {
+                const float4 v = ldg_f4(qrow + j);
+                qn = __fmaf_rn(v.x, v.x, qn); qn = __fmaf_rn(v.y, v.y, qn); qn = __fmaf_rn(v.z, v.z, qn); qn = __fmaf_rn(v.w, v.w, qn);
+            }
+            a.scale[b] = scale;
+            a.offset[b] = __fadd_rn(acc, qn);
+        }
+    }
+    float rmax = 0.0f;
+    float4 pfv[DS / 4];
+    if (wid < 4 && w_begin < w_end) stage_B2_load<DS>(a.codebook, w_begin, 0, 0, wid, lane, pfv);
+    for (int w = w_begin; w < w_end; ++w) {
+        for (int j = 0; j < 4 && owner; ++j) {
+            const float *src = qrow + (size_t)(4 * w + j) * ds;
+#pragma unroll
+            for (int kc = 0; kc < (ds >> 2); ++kc) {
+                float4 v = ldg_f4(src + kc * 4);
+                v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+                *reinterpret_cast<float4 *>(sA + (j * nks1 + (kc >> 1)) * (TC_ROWS * 32) + core_off(row, kc & 1)) = tf32_rna4(v);
+            }
+            unsigned char *x = sA + (j * nks1 + nks) * (TC_ROWS * 32);
+            if (PHASE == 1) {
+                *reinterpret_cast<float4 *>(x + core_off(row, 0)) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+                *reinterpret_cast<float4 *>(x + core_off(row, 1)) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            } else {
+                const float k0 = -__fmul_rn(a.lo[(size_t)(live ? b : b0) * M + 4 * w + j], inv);
+                const float kh = tf32_hi(k0);
+                *reinterpret_cast<float4 *>(x + core_off(row, 0)) = make_float4(inv_hi, inv_hi, inv_lo, kh);
+                *reinterpret_cast<float4 *>(x + core_off(row, 1)) = make_float4(k0 - kh, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        float lo[4], hi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { lo[j] = __int_as_float(0x7f800000); hi[j] = -__int_as_float(0x7f800000); }
+        for (int c0 = 0; c0 < 256; c0 += T2_NQ) {
+            uint32_t held[HQ / 2];              // phase 2: bytes of subspaces 0-1, two centroids per register
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                if (wid < 4) stage_B2_store<DS>(pfv, sB, wid, lane);
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    constexpr uint32_t idesc = umma_idesc_tf32(TC_ROWS, T2_NQ);
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int ks = 0; ks < nks1; ++ks)
+                            umma_tf32(tmem + (uint32_t)(jj * T2_NQ), umma_desc(a_base + (uint32_t)(((2 * pr + jj) * nks1 + ks) * (TC_ROWS * 32))),
+                                      umma_desc(b_base + (uint32_t)((jj * nks1 + ks) * (T2_NQ * 32))), idesc, ks > 0 ? 1u : 0u);
+                    umma_commit(&s_bar);
+                }
+                if (wid < 4) {                  // the next stage's centroid rows travel under the MMA wait and the read-out
+                    const bool last_c = c0 + T2_NQ >= 256;
+                    const int wn = (pr == 1 && last_c) ? w + 1 : w;
+                    const int cn0 = pr == 0 ? c0 : (last_c ? 0 : c0 + T2_NQ);
+                    if (wn < w_end) stage_B2_load<DS>(a.codebook, wn, pr ^ 1, cn0, wid, lane, pfv);
+                }
+                stage_wait(&s_bar, phase);
+                if (PHASE == 1) {
+#pragma unroll
+                    for (int i8 = 0; i8 < HQ / 8; ++i8) {
+                        float v0[8], v1[8];
+                        tmem_ld8(tlane + (uint32_t)(0 * T2_NQ + i8 * 8), v0);
+                        tmem_ld8(tlane + (uint32_t)(1 * T2_NQ + i8 * 8), v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            lo[2 * pr] = fminf(lo[2 * pr], v0[i]); hi[2 * pr] = fmaxf(hi[2 * pr], v0[i]);
+                            lo[2 * pr + 1] = fminf(lo[2 * pr + 1], v1[i]); hi[2 * pr + 1] = fmaxf(hi[2 * pr + 1], v1[i]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i8 = 0; i8 < HQ / 8; ++i8) {
+                        float v0[8], v1[8];
+                        tmem_ld8(tlane + (uint32_t)(0 * T2_NQ + i8 * 8), v0);
+                        tmem_ld8(tlane + (uint32_t)(1 * T2_NQ + i8 * 8), v1);
+                        tmem_ld_wait();
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            uint32_t q0, q1;
+                            asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q0) : "f"(v0[i]));
+                            asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q1) : "f"(v1[i]));
+                            const uint32_t h16 = q0 | (q1 << 8);
+                            if (pr == 0) {
+                                if (i & 1) held[i8 * 4 + (i >> 1)] |= h16 << 16; else held[i8 * 4 + (i >> 1)] = h16;
+                            } else {
+                                pk[i] = __byte_perm(held[i8 * 4 + (i >> 1)], h16, (i & 1) ? 0x5432 : 0x5410);
+                            }
+                        }
+                        if (pr == 1) {
+                            // lane pairs trade halves so that one store instruction writes whole 32-byte sectors (as in lut_u8_tc_kernel)
+                            const bool odd = lane & 1;
+                            uint32_t s0[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) s0[i] = __shfl_xor_sync(DR_FULL, odd ? pk[i] : pk[4 + i], 1);
+                            const long long br = b0 + (row & ~1);
+                            uint32_t *o = a.out32 + ((size_t)br * words + w) * 256 + c0 + half * HQ + i8 * 8;
+                            const size_t rstride = (size_t)words * 256;
+                            if (br < a.B)
+                                *reinterpret_cast<uint4 *>(o + (odd ? 4 : 0)) = odd ? make_uint4(s0[0], s0[1], s0[2], s0[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            if (br + 1 < a.B)
+                                *reinterpret_cast<uint4 *>(o + rstride + (odd ? 4 : 0)) = odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(s0[0], s0[1], s0[2], s0[3]);
+                        }
+                    }
+                }
+            }
+        }
+        if (PHASE == 1) {
+            __syncthreads();
+            if (!owner) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { sS[row * 8 + j] = lo[j]; sS[row * 8 + 4 + j] = hi[j]; }
+            }
+            __syncthreads();
+            if (owner) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float l = fminf(lo[j], sS[row * 8 + j]), h = fmaxf(hi[j], sS[row * 8 + 4 + j]);
+                    rmax = fmaxf(rmax, h - l);
+                    if (live) a.lo[(size_t)b * M + 4 * w + j] = l;
+                }
+            }
+        }
+    }
+    if (PHASE == 1 && live && owner) atomicMax(a.range_bits + b, __float_as_uint(rmax));
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 0) tmem_dealloc(tmem, T2_COLS);
+}
+
 }  // namespace
 
 // Same contract as launch_lut_build_u8(..., word_layout = 1): needs M % 4 == 0 and (D / M) % 8 == 0.
@@ -316,8 +528,13 @@ int launch_lut_build_u8_tc(const float *d_codebook, const float *d_Q, int64_t B,
     void (*k1)(const LutTcArgs) = lut_u8_tc_kernel<1, 0>;
     void (*k2)(const LutTcArgs) = lut_u8_tc_kernel<2, 0>;
     switch (ds) {
+#if DR_LUT_PAIR
+        case 8: k1 = lut_u8_tc2_kernel<1, 8>; k2 = lut_u8_tc2_kernel<2, 8>; break;     // pair stages (N = 64): same smem / TMEM footprint
+        case 16: k1 = lut_u8_tc_kernel<1, 16>; k2 = lut_u8_tc_kernel<2, 16>; break;
+#else
         case 8: k1 = lut_u8_tc_kernel<1, 8>; k2 = lut_u8_tc_kernel<2, 8>; break;
         case 16: k1 = lut_u8_tc_kernel<1, 16>; k2 = lut_u8_tc_kernel<2, 16>; break;
+#endif
         case 24: k1 = lut_u8_tc_kernel<1, 24>; k2 = lut_u8_tc_kernel<2, 24>; break;
         default: break;
     }
