@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
                 if (j2 < nu) {
                     float dA, dB;
                     warp_l2sq_x2(a.X + (size_t)s_sid[j] * D, a.X + (size_t)s_sid[j2] * D, s_star, D, lane, dA, dB);
+                    __syncwarp();             // every lane has read s_flag[j], s_flag[j2] before lane 0 clears them
                     if (lane == 0) {
                         int killed = 0;
                         if (__fmul_rn(a.alpha, dA) <= s_sd[j]) { s_flag[j] = 0; ++killed; }
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
                     }
                 } else {
                     const float d = warp_l2sq(a.X + (size_t)s_sid[j] * D, s_star, D, lane);
+                    __syncwarp();
                     if (lane == 0 && __fmul_rn(a.alpha, d) <= s_sd[j]) { s_flag[j] = 0; atomicSub(&s_nalive, 1); }
                 }
                 j = j2 + nw;
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(PR_THREADS) prune_kernel(const PruneArgs a) {
             for (int j = i + 1 + wid; j < nu; j += nw) {
                 if (!s_flag[j]) continue;
                 float d = warp_l2sq(a.X + (size_t)s_sid[j] * D, s_star, D, lane);
+                __syncwarp();
                 if (lane == 0 && __fmul_rn(a.alpha, d) <= s_sd[j]) { s_flag[j] = 0; atomicSub(&s_nalive, 1); }
             }
 #endif

@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
         int ubase = 0;    // entries marked expanded since the ur[] array of the current list was written
         int sel_base = 0; // selrec: ubase at the time s_sel[0] was (re)written
         int ns_reg = 1;   // entries the coming step expands
+        bool mv_dirty = true;   // s_mvalid has to be reset before this step's ADC phase counts survivors
         __syncthreads();
         DR_PT(1);   // table / query staging, start node
 
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 break;
             }
             if (tid == 0) {
-                s_mvalid = 0;
+                if (mv_dirty) s_mvalid = 0;   // (after a barrier-free empty step it is still 0, and a slower warp may not have read it yet)
                 if (use_ovf_now) s_ovfused = 1;
             }
             const bool spec = (pf & 2) != 0;
@@ -789,6 +790,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 sel_base = 0;
                 __syncthreads();   // the next step reads the merged list and its selection
                 ns_reg = s_ns;
+                mv_dirty = true;
                 DR_PT(4);   // merge
             } else {
                 // nothing survived: the list stays, the selection moves on by the ns entries just expanded
@@ -797,6 +799,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 const int ns_next = tot_left < W2 ? tot_left : W2;
                 if (selrec && ubase - sel_base + ns_next <= DR_SELCAP) {
                     ns_reg = ns_next;          // the recorded ranks cover the step: no rescan, no barrier
+                    mv_dirty = false;          // nothing survived: s_mvalid is 0 and stays untouched until the next ADC phase
                     continue;
                 }
                 for (int x = tid; x < n; x += nt) {
@@ -829,6 +832,7 @@ __global__ void __launch_bounds__(DR_FAST_NT, MINB) search_fast_kernel(const Fas
                 sel_base = ubase;
                 __syncthreads();
                 ns_reg = s_ns;
+                mv_dirty = true;
                 DR_PT(4);
             }
         }
